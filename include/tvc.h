@@ -1,0 +1,205 @@
+/*
+ * tvc.h — C ABI of libtvc.so: the B200 (sm_100a) text-variant-consistency (TVC) scoring and
+ * retrieval hot path.
+ *
+ * Every entry point replaces a library call site of the reference (which is 100 % Python and has
+ * no FFI of its own; citations are path:line under the reference tree):
+ *
+ *   tvc_gallery_create / _append   faiss.IndexFlatIP(d) + index.add(features)   src/retrieval.py:477-525
+ *                                  np.array([ref.vector ...]) rebuilt per query  src/ref_bank.py:475
+ *   tvc_search                     index.search(q.astype(f32), k)               src/retrieval.py:652-656
+ *                                  cosine_similarity + np.argsort[::-1][:k]      src/retrieval.py:669-671
+ *                                  dot/(|r||q|+1e-8), where(>=thr), argsort      src/ref_bank.py:475-484,197-203
+ *                                  np.dot + np.argpartition                      experiments/defenses/retrieval_ref.py:246-290
+ *                                  F.cosine_similarity + torch.topk(.,1)         src/attacks/hubness_attack.py:482-489
+ *   tvc_similarity_matrix          cosine_similarity(T, I) / np.dot(T, I.T)      src/retrieval.py:706-708
+ *                                  torch.mm(x_hat, y_hat.T)                      src/utils/metrics.py:156-159
+ *   tvc_consistency_sims / _emb    per-pair cosine loops + mean/std/var/min/max  src/detector.py:461-485,528-542,573-579,653-682,399
+ *                                                                                experiments/defenses/detector.py:228-300
+ *                                                                                experiments/defenses/consistency_checker.py:74-272
+ *                                                                                experiments/defenses/text_variants.py:412-451
+ *   tvc_k_occurrence               hubness_counts[j] += 1 double loop            references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:43-57
+ *                                  (top1 == 0).sum()                             src/attacks/hubness_attack.py:492-496
+ *   tvc_merge_topk                 (new) merge of per-shard top-k candidates after the NCCL all-gather
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a tvc_status (0 = ok) and never throws.
+ *   - data pointers may be host or device memory (detected with cudaPointerGetAttributes); host
+ *     buffers are staged through the context's device workspace and the call returns after the
+ *     results are back in the host buffer. With device pointers the call is asynchronous on `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - search results are ordered by (similarity descending, index ascending); unused slots carry
+ *     index -1 and similarity -inf (the FAISS convention the reference relies on,
+ *     experiments/defenses/retrieval_ref.py:257).
+ *   - a gallery is immutable under concurrent tvc_search calls; tvc_gallery_append needs external
+ *     exclusion (the Python wrappers hold the lock the reference's ReferenceBank holds).
+ */
+#ifndef TVC_H_
+#define TVC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVC_VERSION 100
+
+typedef enum {
+  TVC_OK = 0,
+  TVC_ERR_INVALID = 1,     /* bad argument (null pointer, d mismatch, k out of range ...) */
+  TVC_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed; see tvc_last_error */
+  TVC_ERR_NO_DEVICE = 3,   /* no sm_100 device: there is no CPU fallback */
+  TVC_ERR_UNSUPPORTED = 4, /* valid request this build cannot serve (k > TVC_MAX_K ...) */
+  TVC_ERR_OOM = 5
+} tvc_status;
+
+typedef enum { TVC_F32 = 0, TVC_BF16 = 1, TVC_F16 = 2 } tvc_dtype;
+
+/* gallery flags */
+#define TVC_GALLERY_NORMALIZE 1u   /* L2-normalise rows at ingest (cosine metric; ReferenceBank) */
+#define TVC_GALLERY_NO_MASTER 2u   /* keep bf16 rows only: no fp32 master, no fp32 re-rank */
+
+/* search flags */
+#define TVC_SEARCH_NORMALIZE_Q 1u  /* L2-normalise query rows (cosine metric) */
+#define TVC_SEARCH_SKIP_SELF 2u    /* query set == gallery: drop candidate idx == query row (hubness spec [:,1:k+1]) */
+
+#define TVC_MAX_K 56               /* largest k served by the in-register top-k epilogue */
+#define TVC_MAX_VARIANTS 16
+#define TVC_MAX_REFS 16
+#define TVC_NSCORES 24             /* floats written per query by tvc_consistency_* */
+
+typedef struct tvc_ctx tvc_ctx;
+typedef struct tvc_gallery tvc_gallery;
+
+/* Column layout of the [Q, TVC_NSCORES] score matrix written by tvc_consistency_*. */
+enum {
+  TVC_S_ORIGINAL = 0,        /* s0 = cos(image, text)                         detector.py:461 / defenses/detector.py:240 */
+  TVC_S_TV_MEAN = 1,         /* text_variant_consistency = mean_v s_v          defenses/detector.py:252 */
+  TVC_S_TV_STD = 2,          /* text_variant_std (ddof=0)                      defenses/detector.py:253 */
+  TVC_S_TV_MIN = 3,
+  TVC_S_TV_VAR = 4,
+  TVC_S_RET_MEAN = 5,        /* retrieval_consistency                          defenses/detector.py:266 */
+  TVC_S_RET_STD = 6,
+  TVC_S_GEN_MEAN = 7,        /* generative_consistency / mean_similarity       defenses/detector.py:279, detector.py:537 */
+  TVC_S_GEN_STD = 8,
+  TVC_S_GEN_MAX = 9,         /* max_similarity                                 detector.py:538 */
+  TVC_S_CROSS_MODAL_VAR = 10,/* var(ddof=0) of the positive means              defenses/detector.py:295-300 */
+  TVC_S_XV_MEAN = 11,        /* variant<->variant pair cosines                 defenses/text_variants.py:412-451 */
+  TVC_S_XV_MIN = 12,
+  TVC_S_XV_VAR = 13,
+  TVC_S_DET_TV = 14,         /* 1-(0.7*consistency+0.3*variability)            detector.py:474-485 */
+  TVC_S_DET_SD = 15,         /* 1-mean(r)                                      detector.py:542 */
+  TVC_S_DET_C = 16,          /* 1-s0                                           detector.py:573-579 */
+  TVC_S_DET_AGG = 17,        /* _aggregate_scores                              detector.py:643-682 */
+  TVC_S_CC_OVERALL = 18,     /* ConsistencyChecker overall score               consistency_checker.py:119-212 */
+  TVC_S_CC_THRESHOLD = 19,   /* stateless adaptive threshold                   consistency_checker.py:214-242 */
+  TVC_S_CC_CONFIDENCE = 20,  /*                                                consistency_checker.py:244-272 */
+  TVC_S_N_RET = 21,          /* retrieval references used (after de-duplication) */
+  TVC_S_N_GEN = 22,
+  TVC_S_REF_SIGMA = 23       /* std of cos(image, all references): the README sigma-rule, README.md:474-482 */
+};
+
+/* decision bits written per query by tvc_consistency_* */
+#define TVC_FLAG_DET_ADV 1u   /* aggregated > detection_threshold      detector.py:399 */
+#define TVC_FLAG_CC_ADV 2u    /* overall < threshold                   consistency_checker.py:93 */
+#define TVC_FLAG_SIGMA_ADV 4u /* ref sigma > sigma_threshold           README.md:846 */
+
+typedef struct {
+  int32_t n_variants;          /* V, stride of the variant arrays (<= TVC_MAX_VARIANTS) */
+  int32_t n_retrieval;         /* R, stride of the retrieval arrays (<= TVC_MAX_REFS) */
+  int32_t n_generative;        /* G, stride of the generative arrays (<= TVC_MAX_REFS) */
+  uint32_t methods;            /* bit0 text_variants, bit1 sd_reference, bit2 consistency (DetectorConfig.detection_methods) */
+  int32_t aggregation;         /* 0 weighted_mean, 1 mean, 2 max, 3 min (DetectorConfig.score_aggregation) */
+  float w_text_variants;       /* 0.4  detector.py:662-666 */
+  float w_sd_reference;        /* 0.4 */
+  float w_consistency;         /* 0.2 */
+  float detection_threshold;   /* 0.5  detector.py:194 */
+  int32_t voting;              /* 0 simple, 1 weighted, 2 adaptive (ConsistencyChecker.voting_strategy) */
+  float cc_weights[4];         /* original, text_variant, retrieval, generative: 0.25 each */
+  float cc_base_threshold;     /* 0.5 */
+  int32_t cc_adaptive;         /* 1: apply the stateless part of _get_adaptive_threshold */
+  float dedup_threshold;       /* 0.95 defenses/detector.py:318; <= -1 disables feature de-duplication */
+  float sigma_threshold;       /* 0.30 README.md:846 */
+} tvc_detector_params;
+
+int tvc_version(void);
+const char* tvc_status_string(int status);
+void tvc_detector_params_default(tvc_detector_params* p);
+
+int tvc_ctx_create(int device, tvc_ctx** out);
+int tvc_ctx_destroy(tvc_ctx* ctx);
+const char* tvc_last_error(tvc_ctx* ctx);
+/* kernels launched through this context since creation (bench.py's gpu_launches) */
+int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
+/* CUDA-event time in ms of the last gemm_topk launch made with timing enabled (roofline.achieved) */
+int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled);
+int tvc_ctx_last_search_kernel_ms(tvc_ctx* ctx, float* ms, int64_t* launches);
+
+/* Gallery: N rows of dimension d resident in HBM as bf16 [N, d_pad] (GEMM operand, d_pad = d
+ * rounded up to 64) plus an fp32 master [N, d] used to re-rank the bf16 candidates.
+ * `global_row_offset` is added to every returned index (row-sharded galleries). */
+int tvc_gallery_create(tvc_ctx* ctx, const void* rows, int dtype, int64_t n, int32_t d,
+                       int64_t global_row_offset, uint32_t flags, int64_t capacity_hint, void* stream,
+                       tvc_gallery** out);
+int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, void* stream);
+int tvc_gallery_truncate(tvc_gallery* g, int64_t n);
+/* copy row `src` over row `dst` (swap-with-last removal used by the ReferenceBank eviction policies,
+ * src/ref_bank.py:365-399) */
+int tvc_gallery_move_row(tvc_gallery* g, int64_t src, int64_t dst, void* stream);
+int tvc_gallery_info(const tvc_gallery* g, int64_t* n, int32_t* d, int64_t* global_row_offset,
+                     uint32_t* flags);
+/* device pointers of the resident copies (for zero-copy consumers; may be NULL when absent) */
+int tvc_gallery_device_ptrs(const tvc_gallery* g, const void** bf16_rows, int32_t* d_pad,
+                            const float** f32_rows);
+/* gather rows (local indices) as fp32 [n, d] into host or device memory */
+int tvc_gallery_get_rows(tvc_gallery* g, const int64_t* idx, int64_t n, float* out, void* stream);
+int tvc_gallery_destroy(tvc_gallery* g);
+
+/* Exact top-k of every query row against the gallery: out_sim [m, k] f32, out_idx [m, k] i64.
+ * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K. */
+int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
+               int32_t k, float threshold, uint32_t flags, float* out_sim, int64_t* out_idx,
+               void* stream);
+
+/* Dense [m, N] fp32 similarity matrix (tcgen05 GEMM, plain store epilogue). Only for sizes that
+ * fit; the search path never materialises it. */
+int tvc_similarity_matrix(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m,
+                          int32_t d, uint32_t flags, float* out, void* stream);
+
+/* Merge `parts` candidate lists per row (the all-gathered per-shard top-k): in_sim/in_idx
+ * [m, parts, k] -> out [m, k], ordered (sim desc, idx asc); idx < 0 entries are ignored. */
+int tvc_merge_topk(tvc_ctx* ctx, const float* in_sim, const int64_t* in_idx, int64_t m,
+                   int32_t parts, int32_t k, float* out_sim, int64_t* out_idx, void* stream);
+
+/* Variant-consistency reduction fed precomputed similarities.
+ *  s0 [Q]; sv [Q,V]; sr [Q,R] with r_cnt [Q] (NULL = all R valid); sg [Q,G] with g_cnt [Q];
+ *  sxv [Q, V*(V-1)/2] variant<->variant cosines (may be NULL).  scores [Q, TVC_NSCORES]; flags [Q]. */
+int tvc_consistency_sims(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, const float* s0,
+                         const float* sv, const float* sr, const int32_t* r_cnt, const float* sg,
+                         const int32_t* g_cnt, const float* sxv, float* scores, uint8_t* flags,
+                         void* stream);
+
+/* Variant-consistency reduction fed embedding rows (fp32, L2-normalised by the encoders).
+ *  img [Q,d]; txt [Q,d]; var [Q,V,d];
+ *  retrieval refs: ret_idx [Q, n_ret_cand] global indices into `ret_gallery` (the search output,
+ *  variant-major), greedily de-duplicated (index, then cosine > dedup_threshold) and cut to R;
+ *  generative refs: either gen [Q,G,d] with g_cnt [Q], or gen_idx [Q, n_gen_cand] into `gen_gallery`.
+ *  Optional outputs: out_sv [Q,V], out_sr [Q,R], out_sg [Q,G] (unused slots = 0). */
+int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, int32_t d,
+                        const float* img, const float* txt, const float* var,
+                        tvc_gallery* ret_gallery, const int64_t* ret_idx, int32_t n_ret_cand,
+                        const float* gen, const int32_t* g_cnt, tvc_gallery* gen_gallery,
+                        const int64_t* gen_idx, int32_t n_gen_cand, float* scores, uint8_t* flags,
+                        float* out_sv, float* out_sr, float* out_sg, void* stream);
+
+/* k-occurrence histogram N_k(j) = #{rows i : j in idx[i, :k]}; idx < 0 or >= n_bins ignored.
+ * counts [n_bins] int32; zero_first != 0 clears it before accumulating. `idx_base` is subtracted
+ * from every index first (a rank histogramming global indices into its own slice passes 0). */
+int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int64_t idx_base,
+                     int64_t n_bins, int32_t* counts, int zero_first, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVC_H_ */

@@ -1,0 +1,825 @@
+// C ABI of libtvc.so (include/tvc.h): contexts, HBM-resident galleries, workspace management and
+// the orchestration of the kernels.  Plain pointers and sizes; no exceptions cross the boundary.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tvc_internal.h"
+
+using namespace tvc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct tvc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::mutex mu;
+  std::string err;
+  EncodeTiledFn encode = nullptr;
+  struct Ws {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+  };
+  std::map<cudaStream_t, Ws> ws;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+  int64_t launches0 = 0;
+};
+
+struct tvc_gallery {
+  tvc_ctx* ctx = nullptr;
+  int64_t n = 0, cap = 0;
+  int d = 0, d_pad = 0;
+  int64_t offset = 0;
+  uint32_t flags = 0;
+  __nv_bfloat16* bf16 = nullptr;
+  float* f32 = nullptr;
+  CUtensorMap tmap;
+  int64_t tmap_rows = -1;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int fail(tvc_ctx* ctx, int status, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+int fail_cuda(tvc_ctx* ctx, cudaError_t e, const char* where) {
+  cudaGetLastError();
+  return fail(ctx, e == cudaErrorMemoryAllocation ? TVC_ERR_OOM : TVC_ERR_CUDA,
+              std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define TVC_CUDA(ctx, call)                                   \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+size_t elem_size(int dtype) { return dtype == TVC_F32 ? 4 : 2; }
+size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// Grow-only per-stream workspace; calls on one stream are stream-ordered so reuse is safe.
+int get_ws(tvc_ctx* ctx, cudaStream_t st, size_t bytes, uint8_t** out) {
+  tvc_ctx::Ws& w = ctx->ws[st];
+  if (w.bytes < bytes) {
+    if (w.ptr) {
+      TVC_CUDA(ctx, cudaStreamSynchronize(st));
+      TVC_CUDA(ctx, cudaFree(w.ptr));
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    const size_t want = bytes + (bytes >> 3);
+    TVC_CUDA(ctx, cudaMalloc(&w.ptr, want));
+    w.bytes = want;
+  }
+  *out = static_cast<uint8_t*>(w.ptr);
+  return TVC_OK;
+}
+
+int make_tmap(tvc_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, int d_pad, int box_rows) {
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d_pad) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                                 gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ctx, TVC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return TVC_OK;
+}
+
+int gallery_tmap(tvc_gallery* g) {
+  if (g->tmap_rows == g->n) return TVC_OK;
+  const int rc = make_tmap(g->ctx, &g->tmap, g->bf16, g->n, g->d_pad, kBN);
+  if (rc == TVC_OK) g->tmap_rows = g->n;
+  return rc;
+}
+
+int gallery_reserve(tvc_gallery* g, int64_t need, cudaStream_t st) {
+  if (need <= g->cap) return TVC_OK;
+  tvc_ctx* ctx = g->ctx;
+  int64_t cap = g->cap + (g->cap >> 1);
+  if (cap < need) cap = need;
+  if (cap < 64) cap = 64;
+  __nv_bfloat16* nb = nullptr;
+  float* nf = nullptr;
+  TVC_CUDA(ctx, cudaMalloc(&nb, static_cast<size_t>(cap) * g->d_pad * 2));
+  if (!(g->flags & TVC_GALLERY_NO_MASTER)) {
+    cudaError_t e = cudaMalloc(&nf, static_cast<size_t>(cap) * g->d * 4);
+    if (e != cudaSuccess) {
+      cudaFree(nb);
+      return fail_cuda(ctx, e, "cudaMalloc(master)");
+    }
+  }
+  if (g->n > 0) {
+    TVC_CUDA(ctx, cudaMemcpyAsync(nb, g->bf16, static_cast<size_t>(g->n) * g->d_pad * 2,
+                                  cudaMemcpyDeviceToDevice, st));
+    if (nf)
+      TVC_CUDA(ctx, cudaMemcpyAsync(nf, g->f32, static_cast<size_t>(g->n) * g->d * 4,
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+  TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (g->bf16) cudaFree(g->bf16);
+  if (g->f32) cudaFree(g->f32);
+  g->bf16 = nb;
+  g->f32 = nf;
+  g->cap = cap;
+  g->tmap_rows = -1;
+  return TVC_OK;
+}
+
+// rows (host or device) -> device pointer usable by a kernel on `st` (staged in `stage` if host)
+int to_device(tvc_ctx* ctx, const void* src, size_t bytes, uint8_t* stage, cudaStream_t st,
+              const void** out) {
+  if (is_device_ptr(src)) {
+    *out = src;
+    return TVC_OK;
+  }
+  TVC_CUDA(ctx, cudaMemcpyAsync(stage, src, bytes, cudaMemcpyHostToDevice, st));
+  *out = stage;
+  return TVC_OK;
+}
+
+cudaEvent_t get_event(tvc_ctx*) {
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+constexpr int64_t kMaxRowsPerLaunch = 1 << 20;
+
+// Stages a host array on the device (or passes a device pointer through); nullptr stays nullptr.
+struct Stager {
+  tvc_ctx* ctx;
+  cudaStream_t st;
+  uint8_t* ws;
+  size_t off = 0;
+  bool any_host = false;
+  template <typename T>
+  int in(const T* src, size_t count, const T** out) {
+    *out = src;
+    if (!src || count == 0 || is_device_ptr(src)) return TVC_OK;
+    T* dst = reinterpret_cast<T*>(ws + off);
+    off += up256(count * sizeof(T));
+    any_host = true;
+    TVC_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *out = dst;
+    return TVC_OK;
+  }
+  template <typename T>
+  T* out_buf(T* dst, size_t count, bool* staged) {
+    *staged = false;
+    if (!dst || count == 0 || is_device_ptr(dst)) return dst;
+    T* b = reinterpret_cast<T*>(ws + off);
+    off += up256(count * sizeof(T));
+    any_host = true;
+    *staged = true;
+    return b;
+  }
+};
+
+
+}  // namespace
+
+extern "C" {
+
+int tvc_version(void) { return TVC_VERSION; }
+
+const char* tvc_status_string(int s) {
+  switch (s) {
+    case TVC_OK: return "ok";
+    case TVC_ERR_INVALID: return "invalid argument";
+    case TVC_ERR_CUDA: return "CUDA error";
+    case TVC_ERR_NO_DEVICE: return "no sm_100 CUDA device (libtvc has no CPU fallback)";
+    case TVC_ERR_UNSUPPORTED: return "unsupported request";
+    case TVC_ERR_OOM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+
+void tvc_detector_params_default(tvc_detector_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->n_variants = 5;        /* DetectorConfig.num_text_variants, src/detector.py:183 */
+  p->n_retrieval = 10;      /* DetectionConfig.retrieval_top_k, experiments/defenses/detector.py:29 */
+  p->n_generative = 3;      /* DetectorConfig.num_reference_images, src/detector.py:188 */
+  p->methods = 7u;
+  p->aggregation = 0;
+  p->w_text_variants = 0.4f;
+  p->w_sd_reference = 0.4f;
+  p->w_consistency = 0.2f;
+  p->detection_threshold = 0.5f;
+  p->voting = 1;
+  for (int i = 0; i < 4; ++i) p->cc_weights[i] = 0.25f;
+  p->cc_base_threshold = 0.5f;
+  p->cc_adaptive = 1;
+  p->dedup_threshold = 0.95f;
+  p->sigma_threshold = 0.30f;
+}
+
+int tvc_ctx_create(int device, tvc_ctx** out) {
+  if (!out) return TVC_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return TVC_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return TVC_ERR_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TVC_ERR_CUDA;
+  if (prop.major != 10) return TVC_ERR_NO_DEVICE;  // tcgen05/TMEM kernels: sm_100 family only
+  tvc_ctx* ctx = new (std::nothrow) tvc_ctx();
+  if (!ctx) return TVC_ERR_OOM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  DeviceGuard guard(device);
+  cudaFree(0);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      fn == nullptr) {
+    cudaGetLastError();
+    delete ctx;
+    return TVC_ERR_CUDA;
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  ctx->launches0 = launches_so_far();
+  *out = ctx;
+  return TVC_OK;
+}
+
+int tvc_ctx_destroy(tvc_ctx* ctx) {
+  if (!ctx) return TVC_OK;
+  {
+    DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->ws)
+      if (kv.second.ptr) cudaFree(kv.second.ptr);
+    for (auto& pr : ctx->timed) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    for (auto& pr : ctx->event_pool) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  }
+  delete ctx;
+  return TVC_OK;
+}
+
+const char* tvc_last_error(tvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t tvc_ctx_launch_count(tvc_ctx* ctx) { return ctx ? launches_so_far() - ctx->launches0 : 0; }
+
+int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled) {
+  if (!ctx) return TVC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->timing = enabled != 0;
+  return TVC_OK;
+}
+
+int tvc_ctx_last_search_kernel_ms(tvc_ctx* ctx, float* ms, int64_t* launches) {
+  if (!ctx || !ms) return TVC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  float total = 0.f;
+  for (auto& pr : ctx->timed) {
+    TVC_CUDA(ctx, cudaEventSynchronize(pr.second));
+    float t = 0.f;
+    TVC_CUDA(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+    total += t;
+  }
+  *ms = total;
+  if (launches) *launches = static_cast<int64_t>(ctx->timed.size());
+  for (auto& pr : ctx->timed) ctx->event_pool.push_back(pr);
+  ctx->timed.clear();
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------- gallery
+int tvc_gallery_create(tvc_ctx* ctx, const void* rows, int dtype, int64_t n, int32_t d,
+                       int64_t global_row_offset, uint32_t flags, int64_t capacity_hint, void* stream,
+                       tvc_gallery** out) {
+  if (!ctx || !out || d <= 0 || n < 0 || (n > 0 && !rows) || dtype < 0 || dtype > TVC_F16)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_create: bad argument");
+  if (n >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
+  *out = nullptr;
+  tvc_gallery* g = new (std::nothrow) tvc_gallery();
+  if (!g) return TVC_ERR_OOM;
+  g->ctx = ctx;
+  g->d = d;
+  g->d_pad = (d + kBK - 1) / kBK * kBK;
+  g->offset = global_row_offset;
+  g->flags = flags;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    rc = gallery_reserve(g, capacity_hint > n ? capacity_hint : n, static_cast<cudaStream_t>(stream));
+  }
+  if (rc == TVC_OK && n > 0) rc = tvc_gallery_append(g, rows, dtype, n, stream);
+  if (rc != TVC_OK) {
+    tvc_gallery_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return TVC_OK;
+}
+
+int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, void* stream) {
+  if (!g || n < 0 || (n > 0 && !rows) || dtype < 0 || dtype > TVC_F16) return TVC_ERR_INVALID;
+  if (n == 0) return TVC_OK;
+  tvc_ctx* ctx = g->ctx;
+  if (g->n + n >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  int rc = gallery_reserve(g, g->n + n, st);
+  if (rc != TVC_OK) return rc;
+  const size_t bytes = static_cast<size_t>(n) * g->d * elem_size(dtype);
+  const bool host_src = !is_device_ptr(rows);
+  const void* src = rows;
+  if (host_src) {
+    uint8_t* ws;
+    rc = get_ws(ctx, st, up256(bytes), &ws);
+    if (rc != TVC_OK) return rc;
+    rc = to_device(ctx, rows, bytes, ws, st, &src);
+    if (rc != TVC_OK) return rc;
+  }
+  TVC_CUDA(ctx, launch_prep_rows(src, dtype, n, g->d, g->d_pad, (g->flags & TVC_GALLERY_NORMALIZE) != 0,
+                                 g->bf16 + static_cast<size_t>(g->n) * g->d_pad,
+                                 g->f32 ? g->f32 + static_cast<size_t>(g->n) * g->d : nullptr, st));
+  g->n += n;
+  g->tmap_rows = -1;
+  if (host_src) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+int tvc_gallery_truncate(tvc_gallery* g, int64_t n) {
+  if (!g || n < 0 || n > g->n) return TVC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g->ctx->mu);
+  g->n = n;
+  g->tmap_rows = -1;
+  return TVC_OK;
+}
+
+int tvc_gallery_move_row(tvc_gallery* g, int64_t src, int64_t dst, void* stream) {
+  if (!g || src < 0 || dst < 0 || src >= g->n || dst >= g->n) return TVC_ERR_INVALID;
+  if (src == dst) return TVC_OK;
+  tvc_ctx* ctx = g->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, cudaMemcpyAsync(g->bf16 + dst * g->d_pad, g->bf16 + src * g->d_pad,
+                                static_cast<size_t>(g->d_pad) * 2, cudaMemcpyDeviceToDevice, st));
+  if (g->f32)
+    TVC_CUDA(ctx, cudaMemcpyAsync(g->f32 + dst * g->d, g->f32 + src * g->d,
+                                  static_cast<size_t>(g->d) * 4, cudaMemcpyDeviceToDevice, st));
+  return TVC_OK;
+}
+
+int tvc_gallery_info(const tvc_gallery* g, int64_t* n, int32_t* d, int64_t* global_row_offset,
+                     uint32_t* flags) {
+  if (!g) return TVC_ERR_INVALID;
+  if (n) *n = g->n;
+  if (d) *d = g->d;
+  if (global_row_offset) *global_row_offset = g->offset;
+  if (flags) *flags = g->flags;
+  return TVC_OK;
+}
+
+int tvc_gallery_device_ptrs(const tvc_gallery* g, const void** bf16_rows, int32_t* d_pad,
+                            const float** f32_rows) {
+  if (!g) return TVC_ERR_INVALID;
+  if (bf16_rows) *bf16_rows = g->bf16;
+  if (d_pad) *d_pad = g->d_pad;
+  if (f32_rows) *f32_rows = g->f32;
+  return TVC_OK;
+}
+
+int tvc_gallery_get_rows(tvc_gallery* g, const int64_t* idx, int64_t n, float* out, void* stream) {
+  if (!g || n < 0 || (n > 0 && (!idx || !out))) return TVC_ERR_INVALID;
+  if (n == 0) return TVC_OK;
+  tvc_ctx* ctx = g->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const bool idx_dev = is_device_ptr(idx), out_dev = is_device_ptr(out);
+  const size_t idx_b = up256(static_cast<size_t>(n) * 8), out_b = up256(static_cast<size_t>(n) * g->d * 4);
+  uint8_t* ws = nullptr;
+  if (!idx_dev || !out_dev) {
+    int rc = get_ws(ctx, st, idx_b + out_b, &ws);
+    if (rc != TVC_OK) return rc;
+  }
+  const void* didx = idx;
+  if (!idx_dev) {
+    int rc = to_device(ctx, idx, static_cast<size_t>(n) * 8, ws, st, &didx);
+    if (rc != TVC_OK) return rc;
+  }
+  float* dout = out_dev ? out : reinterpret_cast<float*>(ws + idx_b);
+  TVC_CUDA(ctx, launch_gather_rows(g->f32, g->bf16, g->d, g->d_pad, static_cast<const int64_t*>(didx), n,
+                                   g->n, dout, st));
+  if (!out_dev) {
+    TVC_CUDA(ctx, cudaMemcpyAsync(out, dout, static_cast<size_t>(n) * g->d * 4, cudaMemcpyDeviceToHost, st));
+    TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  } else if (!idx_dev) {
+    TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TVC_OK;
+}
+
+int tvc_gallery_destroy(tvc_gallery* g) {
+  if (!g) return TVC_OK;
+  {
+    DeviceGuard guard(g->ctx->device);
+    cudaDeviceSynchronize();
+    if (g->bf16) cudaFree(g->bf16);
+    if (g->f32) cudaFree(g->f32);
+  }
+  delete g;
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------- search
+static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool q_dev, int q_dtype,
+                        int64_t m, int64_t row0, int32_t k, float threshold, uint32_t flags,
+                        float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev, cudaStream_t st) {
+  const int d = g->d, d_pad = g->d_pad;
+  SearchPlan plan = make_search_plan(m, g->n, d_pad, k, ctx->sm_count);
+  plan.skip_self = (flags & TVC_SEARCH_SKIP_SELF) ? 1 : 0;
+  plan.self_offset = row0 - g->offset;  // query row i <-> global gallery row i
+  const size_t q_in_b = q_dev ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
+  const size_t q_bf_b = up256(static_cast<size_t>(m) * d_pad * 2);
+  const size_t q_f32_b = g->f32 ? up256(static_cast<size_t>(m) * d * 4) : 0;
+  const size_t cand_n = static_cast<size_t>(m) * plan.splits * plan.kp;
+  const size_t cand_b = up256(cand_n * 4);
+  const size_t os_b = sim_dev ? 0 : up256(static_cast<size_t>(m) * k * 4);
+  const size_t oi_b = idx_dev ? 0 : up256(static_cast<size_t>(m) * k * 8);
+  uint8_t* ws;
+  int rc = get_ws(ctx, st, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b, &ws);
+  if (rc != TVC_OK) return rc;
+  uint8_t* p = ws;
+  uint8_t* q_in = p; p += q_in_b;
+  __nv_bfloat16* q_bf = reinterpret_cast<__nv_bfloat16*>(p); p += q_bf_b;
+  float* q_f32 = g->f32 ? reinterpret_cast<float*>(p) : nullptr; p += q_f32_b;
+  float* cand_val = reinterpret_cast<float*>(p); p += cand_b;
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(p); p += cand_b;
+  float* d_sim = sim_dev ? out_sim : reinterpret_cast<float*>(p); p += os_b;
+  int64_t* d_idx = idx_dev ? out_idx : reinterpret_cast<int64_t*>(p); p += oi_b;
+
+  const void* q_src = queries;
+  if (!q_dev) {
+    rc = to_device(ctx, queries, static_cast<size_t>(m) * d * elem_size(q_dtype), q_in, st, &q_src);
+    if (rc != TVC_OK) return rc;
+  }
+  TVC_CUDA(ctx, launch_prep_rows(q_src, q_dtype, m, d, d_pad, (flags & TVC_SEARCH_NORMALIZE_Q) != 0, q_bf,
+                                 q_f32, st));
+  CUtensorMap tq;
+  rc = make_tmap(ctx, &tq, q_bf, m, d_pad, kBM);
+  if (rc != TVC_OK) return rc;
+  rc = gallery_tmap(g);
+  if (rc != TVC_OK) return rc;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (ctx->timing) {
+    if (!ctx->event_pool.empty()) {
+      ev = ctx->event_pool.back();
+      ctx->event_pool.pop_back();
+    } else {
+      ev.first = get_event(ctx);
+      ev.second = get_event(ctx);
+    }
+    TVC_CUDA(ctx, cudaEventRecord(ev.first, st));
+  }
+  TVC_CUDA(ctx, launch_gemm_topk(tq, g->tmap, plan, cand_val, cand_idx, st));
+  if (ctx->timing) {
+    TVC_CUDA(ctx, cudaEventRecord(ev.second, st));
+    ctx->timed.push_back(ev);
+  }
+  TVC_CUDA(ctx, launch_rerank(cand_val, cand_idx, m, plan.splits, plan.kp, k, q_f32, g->f32, d, threshold,
+                              g->offset, d_sim, d_idx, st));
+  if (!sim_dev)
+    TVC_CUDA(ctx, cudaMemcpyAsync(out_sim, d_sim, static_cast<size_t>(m) * k * 4, cudaMemcpyDeviceToHost, st));
+  if (!idx_dev)
+    TVC_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, st));
+  return TVC_OK;
+}
+
+int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
+               int32_t k, float threshold, uint32_t flags, float* out_sim, int64_t* out_idx,
+               void* stream) {
+  if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad handle");
+  if (m < 0 || (m > 0 && (!queries || !out_sim || !out_idx)) || q_dtype < 0 || q_dtype > TVC_F16)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad argument");
+  if (d != g->d) return fail(ctx, TVC_ERR_INVALID, "tvc_search: query dimension != gallery dimension");
+  if (k < 1) return fail(ctx, TVC_ERR_INVALID, "tvc_search: k < 1");
+  if (k > TVC_MAX_K) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search: k > TVC_MAX_K");
+  if (m == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const bool q_dev = is_device_ptr(queries), sim_dev = is_device_ptr(out_sim),
+             idx_dev = is_device_ptr(out_idx);
+  if (g->n == 0) {
+    // empty gallery: every slot unused
+    std::vector<float> hs(static_cast<size_t>(m) * k, -INFINITY);
+    std::vector<int64_t> hi(static_cast<size_t>(m) * k, -1);
+    TVC_CUDA(ctx, cudaMemcpyAsync(out_sim, hs.data(), hs.size() * 4,
+                                  sim_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, st));
+    TVC_CUDA(ctx, cudaMemcpyAsync(out_idx, hi.data(), hi.size() * 8,
+                                  idx_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, st));
+    TVC_CUDA(ctx, cudaStreamSynchronize(st));
+    return TVC_OK;
+  }
+  const size_t q_row_b = static_cast<size_t>(d) * elem_size(q_dtype);
+  for (int64_t r0 = 0; r0 < m; r0 += kMaxRowsPerLaunch) {
+    const int64_t mc = m - r0 < kMaxRowsPerLaunch ? m - r0 : kMaxRowsPerLaunch;
+    const int rc = search_chunk(ctx, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, q_dev, q_dtype,
+                                mc, r0, k, threshold, flags, out_sim + r0 * k, sim_dev, out_idx + r0 * k,
+                                idx_dev, st);
+    if (rc != TVC_OK) return rc;
+    // host staging in the shared workspace is reused by the next chunk
+    if ((!q_dev || !sim_dev || !idx_dev) && r0 + mc < m) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  if (!q_dev || !sim_dev || !idx_dev) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+int tvc_similarity_matrix(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m,
+                          int32_t d, uint32_t flags, float* out, void* stream) {
+  if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_similarity_matrix: bad handle");
+  if (m < 0 || (m > 0 && (!queries || !out)) || q_dtype < 0 || q_dtype > TVC_F16 || d != g->d)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_similarity_matrix: bad argument");
+  if (m == 0 || g->n == 0) return TVC_OK;
+  if (m >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_similarity_matrix: m too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const bool q_dev = is_device_ptr(queries), out_dev = is_device_ptr(out);
+  const size_t q_in_b = q_dev ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
+  const size_t q_bf_b = up256(static_cast<size_t>(m) * g->d_pad * 2);
+  const size_t out_b = out_dev ? 0 : up256(static_cast<size_t>(m) * g->n * 4);
+  uint8_t* ws;
+  int rc = get_ws(ctx, st, q_in_b + q_bf_b + out_b, &ws);
+  if (rc != TVC_OK) return rc;
+  const void* q_src = queries;
+  if (!q_dev) {
+    rc = to_device(ctx, queries, static_cast<size_t>(m) * d * elem_size(q_dtype), ws, st, &q_src);
+    if (rc != TVC_OK) return rc;
+  }
+  __nv_bfloat16* q_bf = reinterpret_cast<__nv_bfloat16*>(ws + q_in_b);
+  float* d_out = out_dev ? out : reinterpret_cast<float*>(ws + q_in_b + q_bf_b);
+  TVC_CUDA(ctx, launch_prep_rows(q_src, q_dtype, m, d, g->d_pad, (flags & TVC_SEARCH_NORMALIZE_Q) != 0, q_bf,
+                                 nullptr, st));
+  CUtensorMap tq;
+  rc = make_tmap(ctx, &tq, q_bf, m, g->d_pad, kBM);
+  if (rc != TVC_OK) return rc;
+  rc = gallery_tmap(g);
+  if (rc != TVC_OK) return rc;
+  TVC_CUDA(ctx, launch_gemm_store(tq, g->tmap, static_cast<int>(m), static_cast<int>(g->n), g->d_pad / kBK,
+                                  d_out, g->n, ctx->sm_count, st));
+  if (!out_dev) {
+    TVC_CUDA(ctx, cudaMemcpyAsync(out, d_out, static_cast<size_t>(m) * g->n * 4, cudaMemcpyDeviceToHost, st));
+    TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  } else if (!q_dev) {
+    TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TVC_OK;
+}
+
+int tvc_merge_topk(tvc_ctx* ctx, const float* in_sim, const int64_t* in_idx, int64_t m, int32_t parts,
+                   int32_t k, float* out_sim, int64_t* out_idx, void* stream) {
+  if (!ctx || m < 0 || parts < 1 || k < 1 || (m > 0 && (!in_sim || !in_idx || !out_sim || !out_idx)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_merge_topk: bad argument");
+  if (m == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const bool dev = is_device_ptr(in_sim) && is_device_ptr(in_idx) && is_device_ptr(out_sim) &&
+                   is_device_ptr(out_idx);
+  if (dev) {
+    TVC_CUDA(ctx, launch_merge_topk(in_sim, in_idx, m, parts, k, out_sim, out_idx, st));
+    return TVC_OK;
+  }
+  if (is_device_ptr(in_sim) || is_device_ptr(in_idx) || is_device_ptr(out_sim) || is_device_ptr(out_idx))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_merge_topk: mix of host and device pointers");
+  const size_t n_in = static_cast<size_t>(m) * parts * k, n_out = static_cast<size_t>(m) * k;
+  const size_t b0 = up256(n_in * 4), b1 = up256(n_in * 8), b2 = up256(n_out * 4), b3 = up256(n_out * 8);
+  uint8_t* ws;
+  int rc = get_ws(ctx, st, b0 + b1 + b2 + b3, &ws);
+  if (rc != TVC_OK) return rc;
+  float* ds = reinterpret_cast<float*>(ws);
+  int64_t* di = reinterpret_cast<int64_t*>(ws + b0);
+  float* os = reinterpret_cast<float*>(ws + b0 + b1);
+  int64_t* oi = reinterpret_cast<int64_t*>(ws + b0 + b1 + b2);
+  TVC_CUDA(ctx, cudaMemcpyAsync(ds, in_sim, n_in * 4, cudaMemcpyHostToDevice, st));
+  TVC_CUDA(ctx, cudaMemcpyAsync(di, in_idx, n_in * 8, cudaMemcpyHostToDevice, st));
+  TVC_CUDA(ctx, launch_merge_topk(ds, di, m, parts, k, os, oi, st));
+  TVC_CUDA(ctx, cudaMemcpyAsync(out_sim, os, n_out * 4, cudaMemcpyDeviceToHost, st));
+  TVC_CUDA(ctx, cudaMemcpyAsync(out_idx, oi, n_out * 8, cudaMemcpyDeviceToHost, st));
+  TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------- kernel (b)
+static int check_params(tvc_ctx* ctx, const tvc_detector_params* p) {
+  if (!p) return fail(ctx, TVC_ERR_INVALID, "null detector params");
+  if (p->n_variants < 0 || p->n_variants > TVC_MAX_VARIANTS || p->n_retrieval < 0 ||
+      p->n_retrieval > TVC_MAX_REFS || p->n_generative < 0 || p->n_generative > TVC_MAX_REFS)
+    return fail(ctx, TVC_ERR_UNSUPPORTED, "V/R/G exceed TVC_MAX_VARIANTS/TVC_MAX_REFS");
+  if (p->aggregation < 0 || p->aggregation > 3 || p->voting < 0 || p->voting > 2)
+    return fail(ctx, TVC_ERR_INVALID, "bad aggregation/voting");
+  return TVC_OK;
+}
+
+int tvc_consistency_sims(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, const float* s0,
+                         const float* sv, const float* sr, const int32_t* r_cnt, const float* sg,
+                         const int32_t* g_cnt, const float* sxv, float* scores, uint8_t* flags,
+                         void* stream) {
+  if (!ctx) return TVC_ERR_INVALID;
+  int rc = check_params(ctx, p);
+  if (rc != TVC_OK) return rc;
+  if (q < 0 || (q > 0 && (!s0 || !scores || !flags)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_sims: bad argument");
+  if (q == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const size_t V = p->n_variants, R = p->n_retrieval, G = p->n_generative, X = V * (V - (V > 0)) / 2;
+  const size_t Q = static_cast<size_t>(q);
+  const size_t need = up256(Q * 4) + up256(Q * V * 4) + up256(Q * R * 4) + up256(Q * 4) + up256(Q * G * 4) +
+                      up256(Q * 4) + up256(Q * X * 4) + up256(Q * TVC_NSCORES * 4) + up256(Q) + 4096;
+  uint8_t* ws;
+  rc = get_ws(ctx, st, need, &ws);
+  if (rc != TVC_OK) return rc;
+  Stager sg_{ctx, st, ws};
+  const float *d_s0, *d_sv, *d_sr, *d_sg, *d_sx;
+  const int32_t *d_rc, *d_gc;
+  if ((rc = sg_.in(s0, Q, &d_s0)) || (rc = sg_.in(sv, Q * V, &d_sv)) || (rc = sg_.in(sr, Q * R, &d_sr)) ||
+      (rc = sg_.in(r_cnt, Q, &d_rc)) || (rc = sg_.in(sg, Q * G, &d_sg)) || (rc = sg_.in(g_cnt, Q, &d_gc)) ||
+      (rc = sg_.in(sxv, Q * X, &d_sx)))
+    return rc;
+  bool st_scores, st_flags;
+  float* d_scores = sg_.out_buf(scores, Q * TVC_NSCORES, &st_scores);
+  uint8_t* d_flags = sg_.out_buf(flags, Q, &st_flags);
+  TVC_CUDA(ctx, launch_consistency_sims(*p, q, d_s0, V ? d_sv : nullptr, R ? d_sr : nullptr, d_rc,
+                                        G ? d_sg : nullptr, d_gc, X ? d_sx : nullptr, d_scores, d_flags, st));
+  if (st_scores)
+    TVC_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, Q * TVC_NSCORES * 4, cudaMemcpyDeviceToHost, st));
+  if (st_flags) TVC_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, Q, cudaMemcpyDeviceToHost, st));
+  if (sg_.any_host) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, int32_t d,
+                        const float* img, const float* txt, const float* var,
+                        tvc_gallery* ret_gallery, const int64_t* ret_idx, int32_t n_ret_cand,
+                        const float* gen, const int32_t* g_cnt, tvc_gallery* gen_gallery,
+                        const int64_t* gen_idx, int32_t n_gen_cand, float* scores, uint8_t* flags,
+                        float* out_sv, float* out_sr, float* out_sg, void* stream) {
+  if (!ctx) return TVC_ERR_INVALID;
+  int rc = check_params(ctx, p);
+  if (rc != TVC_OK) return rc;
+  if (q < 0 || d <= 0 || (q > 0 && (!img || !txt || !scores || !flags)) || n_ret_cand < 0 || n_gen_cand < 0)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_emb: bad argument");
+  if ((ret_idx && !ret_gallery) || (gen_idx && !gen_gallery))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_emb: index list without its gallery");
+  if ((ret_gallery && ret_gallery->d != d) || (gen_gallery && gen_gallery->d != d))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_emb: gallery dimension mismatch");
+  if (q == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const size_t V = p->n_variants, R = p->n_retrieval, G = p->n_generative, Q = static_cast<size_t>(q);
+  const size_t D = static_cast<size_t>(d);
+  const size_t need = 2 * up256(Q * D * 4) + up256(Q * V * D * 4) + up256(Q * n_ret_cand * 8) +
+                      up256(Q * G * D * 4) + up256(Q * 4) + up256(Q * n_gen_cand * 8) +
+                      up256(Q * TVC_NSCORES * 4) + up256(Q) + up256(Q * V * 4) + up256(Q * R * 4) +
+                      up256(Q * G * 4) + 4096;
+  // only pay for the staging we need: all-device callers get a minimal workspace
+  const bool all_dev = is_device_ptr(img) && is_device_ptr(txt) && (!var || is_device_ptr(var)) &&
+                       (!ret_idx || is_device_ptr(ret_idx)) && (!gen || is_device_ptr(gen)) &&
+                       (!g_cnt || is_device_ptr(g_cnt)) && (!gen_idx || is_device_ptr(gen_idx)) &&
+                       is_device_ptr(scores) && is_device_ptr(flags) &&
+                       (!out_sv || is_device_ptr(out_sv)) && (!out_sr || is_device_ptr(out_sr)) &&
+                       (!out_sg || is_device_ptr(out_sg));
+  uint8_t* ws;
+  rc = get_ws(ctx, st, all_dev ? 4096 : need, &ws);
+  if (rc != TVC_OK) return rc;
+  Stager sg_{ctx, st, ws};
+  ConsistencyEmbArgs a{};
+  if ((rc = sg_.in(img, Q * D, &a.img)) || (rc = sg_.in(txt, Q * D, &a.txt)) ||
+      (rc = sg_.in(var, Q * V * D, &a.var)) ||
+      (rc = sg_.in(ret_idx, Q * static_cast<size_t>(n_ret_cand), &a.ret_idx)) ||
+      (rc = sg_.in(gen, Q * G * D, &a.gen)) || (rc = sg_.in(g_cnt, Q, &a.g_cnt)) ||
+      (rc = sg_.in(gen_idx, Q * static_cast<size_t>(n_gen_cand), &a.gen_idx)))
+    return rc;
+  if (V == 0) a.var = nullptr;
+  if (G == 0) a.gen = nullptr;
+  if (ret_gallery && ret_idx && R > 0 && n_ret_cand > 0) {
+    a.ret_rows = ret_gallery->f32;
+    a.ret_rows_bf16 = ret_gallery->bf16;
+    a.ret_dpad = ret_gallery->d_pad;
+    a.ret_n = ret_gallery->n;
+    a.ret_offset = ret_gallery->offset;
+    a.n_ret_cand = n_ret_cand;
+  } else {
+    a.ret_idx = nullptr;
+  }
+  if (!a.gen && gen_gallery && gen_idx && G > 0 && n_gen_cand > 0) {
+    a.gen_rows = gen_gallery->f32;
+    a.gen_rows_bf16 = gen_gallery->bf16;
+    a.gen_dpad = gen_gallery->d_pad;
+    a.gen_n = gen_gallery->n;
+    a.gen_offset = gen_gallery->offset;
+    a.n_gen_cand = n_gen_cand;
+  } else {
+    a.gen_idx = nullptr;
+  }
+  bool s0_, s1_, s2_, s3_, s4_;
+  float* d_scores = sg_.out_buf(scores, Q * TVC_NSCORES, &s0_);
+  uint8_t* d_flags = sg_.out_buf(flags, Q, &s1_);
+  a.out_sv = sg_.out_buf(out_sv, Q * V, &s2_);
+  a.out_sr = sg_.out_buf(out_sr, Q * R, &s3_);
+  a.out_sg = sg_.out_buf(out_sg, Q * G, &s4_);
+  TVC_CUDA(ctx, launch_consistency_emb(*p, q, d, a, d_scores, d_flags, st));
+  if (s0_) TVC_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, Q * TVC_NSCORES * 4, cudaMemcpyDeviceToHost, st));
+  if (s1_) TVC_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, Q, cudaMemcpyDeviceToHost, st));
+  if (s2_) TVC_CUDA(ctx, cudaMemcpyAsync(out_sv, a.out_sv, Q * V * 4, cudaMemcpyDeviceToHost, st));
+  if (s3_) TVC_CUDA(ctx, cudaMemcpyAsync(out_sr, a.out_sr, Q * R * 4, cudaMemcpyDeviceToHost, st));
+  if (s4_) TVC_CUDA(ctx, cudaMemcpyAsync(out_sg, a.out_sg, Q * G * 4, cudaMemcpyDeviceToHost, st));
+  if (sg_.any_host) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------- kernel (c)
+int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int64_t idx_base,
+                     int64_t n_bins, int32_t* counts, int zero_first, void* stream) {
+  if (!ctx || m < 0 || k < 1 || n_bins < 0 || (n_bins > 0 && !counts) || (m > 0 && !idx))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_k_occurrence: bad argument");
+  if (n_bins == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const bool idx_dev = m == 0 || is_device_ptr(idx), cnt_dev = is_device_ptr(counts);
+  const size_t ib = up256(static_cast<size_t>(m) * k * 8), cb = up256(static_cast<size_t>(n_bins) * 4);
+  uint8_t* ws = nullptr;
+  if (!idx_dev || !cnt_dev) {
+    int rc = get_ws(ctx, st, ib + cb, &ws);
+    if (rc != TVC_OK) return rc;
+  }
+  const int64_t* d_idx = idx;
+  if (!idx_dev) {
+    TVC_CUDA(ctx, cudaMemcpyAsync(ws, idx, static_cast<size_t>(m) * k * 8, cudaMemcpyHostToDevice, st));
+    d_idx = reinterpret_cast<const int64_t*>(ws);
+  }
+  int32_t* d_cnt = counts;
+  if (!cnt_dev) {
+    d_cnt = reinterpret_cast<int32_t*>(ws + ib);
+    if (!zero_first)
+      TVC_CUDA(ctx, cudaMemcpyAsync(d_cnt, counts, static_cast<size_t>(n_bins) * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (zero_first) TVC_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, static_cast<size_t>(n_bins) * 4, st));
+  TVC_CUDA(ctx, launch_k_occurrence(d_idx, m, k, idx_base, n_bins, d_cnt, ctx->sm_count, st));
+  if (!cnt_dev)
+    TVC_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, static_cast<size_t>(n_bins) * 4, cudaMemcpyDeviceToHost, st));
+  if (!idx_dev || !cnt_dev) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// Internal declarations shared by the libtvc.so translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tvc.h"
+
+namespace tvc {
+
+// ---- tile geometry of the fused GEMM + top-k kernel (tvc_gemm_topk.cu) ----------------------
+constexpr int kBM = 128;      // query rows per CTA tile (UMMA M, one TMEM lane per row)
+constexpr int kBN = 256;      // gallery rows per MMA tile (UMMA N)
+constexpr int kBK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 4;    // smem ring depth
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kBBytes = kBN * kBK * 2;
+constexpr int kThreads = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+
+struct SearchPlan {
+  int m_rows;           // valid query rows
+  int n_rows;           // valid gallery rows
+  int kblocks;          // d_pad / 64
+  int m_tiles;
+  int n_tiles;
+  int splits;           // gallery ranges per query tile (each owns a candidate list)
+  int tiles_per_split;
+  int kp;               // candidates kept per (row, split): 16 / 32 / 64
+  int grid;
+  int skip_self;        // drop candidate == query row (+ self_offset)
+  int64_t self_offset;  // global row of query 0 minus global row of gallery row 0
+};
+
+// plans the unit decomposition for `sm_count` persistent CTAs
+SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count);
+
+cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g,
+                             const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                             cudaStream_t stream);
+
+cudaError_t launch_gemm_store(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g, int m, int n,
+                              int kblocks, float* out, int64_t ld_out, int sm_count,
+                              cudaStream_t stream);
+
+// ---- auxiliary kernels (tvc_aux.cu) -----------------------------------------------------------
+// rows [n, d] of dtype -> bf16 [n, d_pad] (zero padded) and optional fp32 [n, d]; optional L2 norm.
+cudaError_t launch_prep_rows(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
+                             __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t stream);
+
+// select top-kp by GEMM score over splits, re-score in fp32 from the masters, emit ordered top-k.
+cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
+                          int kp, int k, const float* q_f32, const float* g_f32, int d,
+                          float threshold, int64_t global_row_offset, float* out_sim,
+                          int64_t* out_idx, cudaStream_t stream);
+
+cudaError_t launch_merge_topk(const float* in_sim, const int64_t* in_idx, int64_t m, int parts, int k,
+                              float* out_sim, int64_t* out_idx, cudaStream_t stream);
+
+cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t idx_base,
+                                int64_t n_bins, int32_t* counts, int sm_count, cudaStream_t stream);
+
+cudaError_t launch_gather_rows(const float* g_f32, const __nv_bfloat16* g_bf16, int d, int d_pad,
+                               const int64_t* idx, int64_t n, int64_t n_rows, float* out,
+                               cudaStream_t stream);
+
+struct ConsistencyEmbArgs {
+  const float* img;
+  const float* txt;
+  const float* var;
+  const float* ret_rows;  // fp32 master of the retrieval gallery (or null)
+  const __nv_bfloat16* ret_rows_bf16;
+  int ret_dpad;
+  int64_t ret_n;
+  int64_t ret_offset;
+  const int64_t* ret_idx;
+  int n_ret_cand;
+  const float* gen;  // direct generative embeddings [Q,G,d] (or null)
+  const int32_t* g_cnt;
+  const float* gen_rows;
+  const __nv_bfloat16* gen_rows_bf16;
+  int gen_dpad;
+  int64_t gen_n;
+  int64_t gen_offset;
+  const int64_t* gen_idx;
+  int n_gen_cand;
+  float* out_sv;
+  float* out_sr;
+  float* out_sg;
+};
+
+cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, const float* s0,
+                                    const float* sv, const float* sr, const int32_t* r_cnt,
+                                    const float* sg, const int32_t* g_cnt, const float* sxv,
+                                    float* scores, uint8_t* flags, cudaStream_t stream);
+
+cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int d,
+                                   const ConsistencyEmbArgs& a, float* scores, uint8_t* flags,
+                                   cudaStream_t stream);
+
+// counts every kernel launch made by the library (reported through tvc_ctx_launch_count)
+void note_launch(int n = 1);
+int64_t launches_so_far();
+
+}  // namespace tvc

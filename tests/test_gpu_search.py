@@ -1,0 +1,153 @@
+"""Kernel (a) parity: libtvc.so tvc_search (tcgen05 GEMM + in-register top-k + fp32 re-rank) against
+the NumPy oracle on the same seeded inputs.  Indices bit-exact except inside the 1e-3 similarity
+band north_star allows; similarities within 2e-3 (bf16 operands, fp32 accumulate)."""
+import numpy as np
+import pytest
+
+from oracle import tvc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIM_TOL = 2e-3
+BAND = 1e-3
+
+
+def _check_topk(sims, idx, ref_s, ref_i, full_sims=None):
+    sims, idx = np.asarray(sims), np.asarray(idx)
+    assert sims.shape == ref_s.shape and idx.shape == ref_i.shape
+    fin = np.isfinite(ref_s)
+    assert np.array_equal(np.isfinite(sims), fin)
+    assert np.array_equal(idx < 0, ~fin)
+    assert np.abs(sims[fin] - ref_s[fin]).max(initial=0.0) <= SIM_TOL
+    bad = (idx != ref_i)
+    if bad.any():
+        # disagreement allowed only where the two candidates' similarities lie within the band
+        assert np.abs(sims[bad] - ref_s[bad]).max() <= BAND, "index mismatch outside the 1e-3 band"
+        if full_sims is not None:
+            rows, cols = np.nonzero(bad)
+            true_of_ours = full_sims[rows, idx[rows, cols]]
+            assert np.abs(true_of_ours - ref_s[rows, cols]).max() <= BAND
+    return float(bad.mean())
+
+
+def _unit(rng, n, d):
+    return O.l2_normalize(rng.standard_normal((n, d), dtype=np.float32))
+
+
+@pytest.mark.parametrize("m,n,d,k", [
+    (5, 300, 64, 10),        # one tile, ragged everything
+    (128, 256, 128, 10),     # exactly one tile
+    (129, 257, 512, 10),     # one row / one column over the tile edge
+    (1000, 5000, 512, 10),   # C1 scale-down of the reference CPU config
+    (300, 4000, 768, 5),     # pipeline top_k=5 (src/pipeline.py:452)
+    (64, 3000, 768, 20),     # rerank_top_k=20 (experiments/defenses/retrieval_ref.py)
+    (40, 2000, 96, 50),      # KP=64 path
+    (17, 1000, 100, 3),      # d not a multiple of 64 / 8
+])
+def test_search_matches_oracle(tvc_ctx, m, n, d, k):
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(m * 7919 + n)
+    g, q = _unit(rng, n, d), _unit(rng, m, d)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = gal.search(q, k)
+    ref_s, ref_i = O.search(q, g, k)
+    frac = _check_topk(sims, idx, ref_s, ref_i, q @ g.T)
+    assert frac < 0.01
+    # every returned similarity is the true fp32 dot of the returned index
+    rows = np.arange(m)[:, None]
+    assert np.abs((q @ g.T)[rows, idx] - sims).max() <= 1e-5
+
+
+def test_fewer_rows_than_k_and_empty(tvc_ctx):
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(3)
+    g, q = _unit(rng, 4, 64), _unit(rng, 6, 64)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = gal.search(q, 10)
+    ref_s, ref_i = O.search(q, g, 10)
+    _check_topk(sims, idx, ref_s, ref_i)
+    assert (idx[:, 4:] == -1).all() and np.isneginf(sims[:, 4:]).all()
+    empty = tvc.Gallery(dim=64, ctx=tvc_ctx)
+    s2, i2 = empty.search(q, 3)
+    assert (i2 == -1).all() and np.isneginf(s2).all()
+
+
+def test_ties_break_to_lower_index(tvc_ctx):
+    """Duplicate gallery rows score identically; the lower index must win (north_star)."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(11)
+    base = _unit(rng, 50, 128)
+    g = np.concatenate([base, base, base], axis=0)  # every row appears 3 times: i, i+50, i+100
+    q = _unit(rng, 33, 128)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = gal.search(q, 9)
+    ref_s, ref_i = O.search(q, g, 9)
+    assert np.array_equal(idx, ref_i)
+    assert np.abs(sims - ref_s).max() <= 1e-5
+    trip = idx.reshape(33, 3, 3)
+    assert (trip[:, :, 1] == trip[:, :, 0] + 50).all() and (trip[:, :, 2] == trip[:, :, 0] + 100).all()
+
+
+def test_threshold_offset_and_cosine(tvc_ctx):
+    """ReferenceBank semantics: un-normalised rows, cosine, `>= threshold` (src/ref_bank.py:172-224)."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal((500, 512)).astype(np.float32) * 3.0
+    q = (g[rng.integers(0, 500, 20)] + 0.7 * rng.standard_normal((20, 512)).astype(np.float32) * 3.0)
+    gal = tvc.Gallery(g, normalize=True, global_row_offset=1000, ctx=tvc_ctx)
+    sims, idx = gal.search(q, 10, threshold=0.3, normalize_queries=True)
+    ref_s, ref_i = O.search(q, g, 10, metric="cosine", threshold=0.3, index_offset=1000)
+    _check_topk(sims, idx, ref_s, ref_i)
+    assert (idx[idx >= 0] >= 1000).all()
+    assert (sims[np.isfinite(sims)] >= 0.3).all()
+
+
+def test_many_splits_small_m(tvc_ctx):
+    """Few query rows over a long gallery: the gallery is split across CTAs and merged."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(8)
+    g, q = _unit(rng, 70000, 128), _unit(rng, 5, 128)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = gal.search(q, 10)
+    ref_s, ref_i = O.search(q, g, 10)
+    _check_topk(sims, idx, ref_s, ref_i, q @ g.T)
+
+
+def test_torch_device_path_and_append(tvc_ctx):
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(21)
+    g, q = _unit(rng, 3000, 256), _unit(rng, 200, 256)
+    gal = tvc.Gallery(torch.from_numpy(g[:1000]).cuda(), ctx=tvc_ctx)
+    gal.append(g[1000:2500])
+    gal.append(torch.from_numpy(g[2500:]).cuda().bfloat16().float())  # bf16-exact rows
+    g2 = g.copy()
+    g2[2500:] = O.bf16_round(g[2500:])
+    assert len(gal) == 3000
+    sims, idx = gal.search(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    ref_s, ref_i = O.search(q, g2, 10)
+    _check_topk(sims.cpu().numpy(), idx.cpu().numpy(), ref_s, ref_i, q @ g2.T)
+    assert np.abs(gal.get_rows(np.array([0, 1500, 2999])) - g2[[0, 1500, 2999]]).max() < 1e-6
+
+
+def test_similarity_matrix(tvc_ctx):
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(4)
+    g, q = _unit(rng, 700, 192), _unit(rng, 150, 192)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    s = gal.similarity_matrix(q)
+    ref = O.bf16_round(q) @ O.bf16_round(g).T
+    assert np.abs(s - ref).max() <= 1e-5          # exact for the bf16 operands
+    assert np.abs(s - q @ g.T).max() <= SIM_TOL   # and within tolerance of fp32
+
+
+def test_skip_self_hubness_knn(tvc_ctx):
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(9)
+    f = _unit(rng, 1500, 128)
+    gal = tvc.Gallery(f, ctx=tvc_ctx)
+    sims, idx = gal.search(f, 10, skip_self=True)
+    ref_s, ref_i = O.search(f, f, 10, skip_self=True)
+    _check_topk(sims, idx, ref_s, ref_i, f @ f.T)
+    assert (idx != np.arange(1500)[:, None]).all()

@@ -226,6 +226,46 @@ def _f32(x: float) -> float:
     return float(np.float32(x))
 
 
+def consistency_from_scores(s0, tv_c, tv_s, rt_c, rt_s, gn_c, gn_s, cmv, params=None,
+                            threshold_history: Optional[Sequence[float]] = None):
+    """experiments/defenses/consistency_checker.py:74-272 make_decision from the score dict:
+    voting (:119-212), adaptive threshold (:214-242; the history blend :234-239 only when
+    `threshold_history` is given — it is host-side state), decision (:93), confidence (:244-272).
+    Returns (overall_score, threshold, confidence, is_adversarial)."""
+    p = dict(DEFAULT_PARAMS)
+    if params:
+        p.update(params)
+    four = [float(s0), float(tv_c), float(rt_c), float(gn_c)]
+    valid = [s for s in four if s > 0]
+    if p["voting"] == 0:
+        overall = float(np.mean(valid)) if valid else 0.0
+    else:
+        if p["voting"] == 1:
+            w = [float(np.float32(x)) for x in p["cc_weights"]]
+        else:
+            w = [1.0, 1.0 / (1.0 + tv_s), 1.0 / (1.0 + rt_s), 1.0 / (1.0 + gn_s)]
+            t = sum(w)
+            w = [x / t for x in w] if t > 0 else w
+        ws = sum(s * wi for s, wi in zip(four, w) if s > 0)
+        tw = sum(wi for s, wi in zip(four, w) if s > 0)
+        overall = ws / tw if tw != 0 else 0.0
+    thr = _f32(p["cc_base_threshold"])
+    if p["cc_adaptive"]:
+        if cmv > 0.1:
+            thr += 0.1
+        if (tv_s + rt_s + gn_s) / 3.0 > 0.2:
+            thr += 0.05
+        if threshold_history is not None and len(threshold_history) > 10:
+            thr = 0.7 * thr + 0.3 * float(np.mean(list(threshold_history)[-10:]))
+        thr = min(max(thr, 0.1), 0.9)
+    cc_adv = overall < thr
+    dist_conf = abs(overall - thr) / thr
+    cons_conf = 1.0 - float(np.std(valid)) if len(valid) > 1 else 0.5
+    var_conf = 1.0 - min(float(cmv), 1.0)
+    conf = min(max((dist_conf + cons_conf + var_conf) / 3.0, 0.0), 1.0)
+    return overall, thr, conf, cc_adv
+
+
 def consistency_one(s0: float, sv: Sequence[float], sr: Sequence[float], sg: Sequence[float],
                     sxv: Sequence[float] = (), params: Optional[Dict[str, object]] = None
                     ) -> Tuple[np.ndarray, int]:
@@ -283,30 +323,7 @@ def consistency_one(s0: float, sv: Sequence[float], sr: Sequence[float], sg: Seq
     cmv = float(np.var(valid)) if len(valid) >= 2 else 0.0
 
     # --- ConsistencyChecker
-    if p["voting"] == 0:
-        overall = float(np.mean(valid)) if valid else 0.0
-    else:
-        if p["voting"] == 1:
-            w = [float(np.float32(x)) for x in p["cc_weights"]]
-        else:
-            w = [1.0, 1.0 / (1.0 + tv_s), 1.0 / (1.0 + rt_s), 1.0 / (1.0 + gn_s)]
-            t = sum(w)
-            w = [x / t for x in w] if t > 0 else w
-        ws = sum(s * wi for s, wi in zip(four, w) if s > 0)
-        tw = sum(wi for s, wi in zip(four, w) if s > 0)
-        overall = ws / tw if tw != 0 else 0.0
-    thr = _f32(p["cc_base_threshold"])
-    if p["cc_adaptive"]:
-        if cmv > 0.1:
-            thr += 0.1
-        if (tv_s + rt_s + gn_s) / 3.0 > 0.2:
-            thr += 0.05
-        thr = min(max(thr, 0.1), 0.9)
-    cc_adv = overall < thr
-    dist_conf = abs(overall - thr) / thr
-    cons_conf = 1.0 - float(np.std(valid)) if len(valid) > 1 else 0.5
-    var_conf = 1.0 - min(cmv, 1.0)
-    conf = min(max((dist_conf + cons_conf + var_conf) / 3.0, 0.0), 1.0)
+    overall, thr, conf, cc_adv = consistency_from_scores(s0, tv_c, tv_s, rt_c, rt_s, gn_c, gn_s, cmv, p)
 
     refs = np.concatenate([sr, sg])
     sigma = float(refs.std()) if len(refs) else 0.0

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — TVC-scored queries/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                      # our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]     # CPU reference arm
+    torchrun --nproc-per-node N bench.py --gpus N ...                        # N > 1
+
+A step = one pass of the hot path over one batch: Q queries x V=5 text variants searched top-10
+against the image gallery and the reference bank (kernel a), variant-consistency reduction with
+detector decisions (kernel b), k-occurrence histogram of the gallery hits (kernel c).
+
+Default workload (named in config.workload): the 1M-image ViT-L/14 gallery + 100k reference bank of
+north_star / configs[4], which fits one GPU (the configs[1] Flickr-scale case is a parity-test case
+and is about 1 ms of GEMM: too small to time).  Scaling is STRONG: total work is fixed, the gallery
+and the bank are row-sharded over the ranks (north_star), every rank searches all query rows on
+its shard, candidates are exchanged with NCCL all-to-all and merged, kernel (b) runs on each
+rank's slice of the queries, the histogram is all-reduced.
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+The gallery (1.5 GB bf16 + 3 GB fp32 master) is far larger than the 126 MB L2, so no L2 flush is
+needed between iterations ("inputs larger than L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "tvc_scored_queries_per_s"
+UNIT = "queries/s"
+
+
+# ----------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--queries", type=int, default=16384, help="queries per step (each with V variants)")
+    ap.add_argument("--variants", type=int, default=5)
+    ap.add_argument("--gallery", type=int, default=1_000_000)
+    ap.add_argument("--bank", type=int, default=100_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto, ~10-20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return dict(hbm_gbs=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                        bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+        except Exception:
+            pass
+    # fallback stated in B200_PROFILING.md
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return dict(sm_mhz=statistics.median(load) if load else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic workload: clustered unit-norm gallery, queries near gallery rows,
+# variants near their query, 30 % "attacked" images pulled towards a hub direction
+def synth_device(torch, args, device, n_rows, seed, lo=0, hi=None, centers=None):
+    hi = n_rows if hi is None else hi
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    d = args.dim
+    if centers is None:
+        centers = torch.nn.functional.normalize(torch.randn(1024, d, device=device, generator=gen), dim=1)
+    out = torch.empty(hi - lo, d, device=device)
+    chunk = 1 << 18
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        g2 = torch.Generator(device=device)
+        g2.manual_seed(seed * 1_000_003 + c0)          # chunk-seeded: identical rows for any sharding
+        assign = torch.randint(0, centers.shape[0], (c1 - c0,), device=device, generator=g2)
+        x = centers[assign] + (0.35 / math.sqrt(d)) * torch.randn(c1 - c0, d, device=device, generator=g2)
+        out[c0 - lo:c1 - lo] = torch.nn.functional.normalize(x, dim=1)
+    return out, centers
+
+
+def synth_queries(torch, args, device, centers, seed):
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    q, v, d = args.queries, args.variants, args.dim
+    sd = 1.0 / math.sqrt(d)
+    base = centers[torch.randint(0, centers.shape[0], (q,), device=device, generator=gen)]
+    base = torch.nn.functional.normalize(base + 0.35 * sd * torch.randn(q, d, device=device, generator=gen), dim=1)
+    txt = torch.nn.functional.normalize(base + 0.5 * sd * torch.randn(q, d, device=device, generator=gen), dim=1)
+    img = torch.nn.functional.normalize(base + 0.5 * sd * torch.randn(q, d, device=device, generator=gen), dim=1)
+    attacked = torch.rand(q, device=device, generator=gen) < 0.3
+    hub = torch.nn.functional.normalize(txt[:100].mean(0), dim=0)
+    img[attacked] = torch.nn.functional.normalize(0.5 * img[attacked] + 0.8 * hub, dim=1)
+    var = txt[:, None, :] + 0.15 * sd * torch.randn(q, v, d, device=device, generator=gen)
+    var = torch.nn.functional.normalize(var, dim=2)
+    return img.contiguous(), txt.contiguous(), var.contiguous()
+
+
+def step_flops(args):
+    return 2.0 * args.queries * args.variants * (args.gallery + args.bank) * args.dim
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step(torch, np, O, g_host, b_host, img, txt, var, k, params=None):
+    """The reference's CPU path for one batch (the oracle port): exact fp32 inner-product top-k
+    (IndexFlatIP-equivalent: torch fp32 matmul in row chunks + topk + running merge, all host
+    threads) for gallery and bank, then the fp64 NumPy scoring and np.bincount histogram."""
+    q, v, d = var.shape
+    rows = torch.from_numpy(var.reshape(q * v, d))
+
+    def flat_ip(mat):
+        best_s = torch.full((q * v, k), -float("inf"))
+        best_i = torch.full((q * v, k), -1, dtype=torch.int64)
+        for c0 in range(0, mat.shape[0], 100_000):
+            s = rows @ mat[c0:c0 + 100_000].T
+            cs, ci = torch.topk(s, min(k, s.shape[1]), dim=1)
+            ms = torch.cat([best_s, cs], 1)
+            mi = torch.cat([best_i, ci + c0], 1)
+            o = torch.topk(ms, k, dim=1)
+            best_s, best_i = o.values, torch.gather(mi, 1, o.indices)
+        return best_s.numpy(), best_i.numpy()
+
+    gs, gi = flat_ip(g_host)
+    bs, bi = flat_ip(b_host) if b_host is not None else (None, None)
+    scores, flags, _ = O.consistency_emb(img, txt, var, ret_rows=g_host.numpy(), ret_idx=gi.reshape(q, v * k),
+                                         gen_rows=b_host.numpy() if b_host is not None else None,
+                                         gen_idx=bi.reshape(q, v * k) if bi is not None else None, params=params)
+    hub = O.k_occurrence(gi, g_host.shape[0])
+    return scores, flags, gi, hub
+
+
+def run_cpu_sample(torch, args, g_host, b_host, img, txt, var, sample_q, reps=1):
+    import numpy as np
+    from oracle import tvc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sq = max(1, min(sample_q, img.shape[0]))
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(torch, np, O, g_host, b_host, img[:sq], txt[:sq], var[:sq], args.topk)
+        best = min(best, time.perf_counter() - t0)
+    return sq / best, sq, best, cores
+
+
+def auto_sample(torch, args, g_host, b_host, img, txt, var):
+    """Probe with 8 queries, then size the sample for ~12 s of CPU work."""
+    qps, _, _, _ = run_cpu_sample(torch, args, g_host, b_host, img, txt, var, 8)
+    return int(max(16, min(img.shape[0], qps * 12.0)))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"metric": METRIC, "error": "no CUDA device: libtvc has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    import multimodal_detection_consistency_b200 as tvc
+    from multimodal_detection_consistency_b200.pipeline import TVCScorer, shard_bounds
+
+    ctx = tvc.Context.get(local_rank)
+    glo, ghi = shard_bounds(args.gallery, world, rank)
+    blo, bhi = shard_bounds(args.bank, world, rank)
+    g_rows, centers = synth_device(torch, args, device, args.gallery, 42, glo, ghi)
+    b_rows, _ = synth_device(torch, args, device, args.bank, 43, blo, bhi, centers)
+    scorer = TVCScorer(g_rows, b_rows, k=args.topk, total_gallery_rows=args.gallery, total_bank_rows=args.bank,
+                       device=device)
+    g_host = b_host = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        g_host, b_host = g_rows.cpu(), b_rows.cpu()
+    del g_rows, b_rows
+    img, txt, var = synth_queries(torch, args, device, centers, 123)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm -------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    ctx.set_timing(True)
+    for _ in range(args.warmup):
+        scorer.score_batch(img, txt, var)
+    barrier()
+    ctx.search_kernel_ms()
+    launches0 = ctx.launch_count()
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(lambda: scorer.score_batch(img, txt, var), args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    k_ms, k_n = ctx.search_kernel_ms()
+    ctx.set_timing(False)
+    value = args.queries * args.steps / (total_ms / 1e3)
+
+    # ---- end-to-end arm: pinned host inputs, H2D + D2H inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        h_img, h_txt, h_var = (t.cpu().pin_memory() for t in (img, txt, var))
+        res = {}
+
+        def e2e_step():
+            res["out"] = scorer.score_batch(h_img, h_txt, h_var, to_host=True)
+
+        e2e_ms = timed(e2e_step, args.steps, max(1, args.warmup - 1))
+        out = res["out"]
+        h2d = sum(t.numel() * t.element_size() for t in (h_img, h_txt, h_var))
+        d2h = sum(t.numel() * t.element_size() for n, t in out.items() if n != "slice")
+        e2e = dict(value=args.queries * args.steps / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
+                   api="TVCScorer.score_batch(pinned host tensors, to_host=True)")
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    # dominant kernel: gemm_topk (tensor bound).  Algorithmic FLOPs per launch = 2*M*N_shard*d for the
+    # gallery and the bank launch of a step; achieved = those FLOPs / the launches' CUDA-event time.
+    shard_flops = 2.0 * args.queries * args.variants * ((ghi - glo) + (bhi - blo)) * args.dim
+    achieved = shard_flops * args.steps / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
+    roofline = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                    frac=(achieved / peaks["bf16_sustained"]) if achieved else None, traffic=None,
+                    kernel="gemm_topk_kernel<16> (tcgen05 GEMM + top-k epilogue)",
+                    kernel_ms_per_step=k_ms / args.steps, kernel_launches=k_n,
+                    kernel_share_of_step=k_ms / total_ms, peak_source=f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
+                    frac_of_burst_peak=(achieved / peaks["bf16"]) if achieved else None)
+
+    cpu = None
+    if g_host is not None:
+        h = [t.cpu().numpy() for t in (img, txt, var)]
+        sq = args.cpu_sample or auto_sample(torch, args, g_host, b_host, *h)
+        qps, sq, secs, cores = run_cpu_sample(torch, args, g_host, b_host, *h, sq)
+        cpu = dict(value=qps, unit=UNIT, cores=cores, kind="port",
+                   sample=f"{sq} of the step's {args.queries} queries x {args.variants} variants vs the full "
+                          f"{args.gallery}+{args.bank} rows, torch fp32 matmul+topk on {cores} threads + NumPy fp64 "
+                          f"scoring ({secs:.1f} s)")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 operands, fp32 accumulate, fp32 re-rank, fp64 statistics", "data": "synthetic",
+        "config": {"workload": f"north_star/configs[4] on {world} GPU(s): {args.queries} queries x {args.variants} "
+                               f"variants, top-{args.topk}, {args.gallery}-image + {args.bank}-reference bank, "
+                               f"d={args.dim} (ViT-L/14)",
+                   "queries_per_step": args.queries, "variants": args.variants, "top_k": args.topk,
+                   "gallery_rows": args.gallery, "bank_rows": args.bank, "dim": args.dim,
+                   "parallelism": f"gallery+bank row-sharded x{world}, candidate all-to-all + merge, histogram all-reduce"
+                   if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (gallery 1.5 GB bf16 streamed every step)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "tflops": step_flops(args) * args.steps / (total_ms / 1e3) / 1e12,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args):
+    """CPU reference arm: the oracle port of the reference's CPU path on the host cores, each step a
+    bounded sample of the same workload (same gallery, bank, k, V)."""
+    import numpy as np
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dev = torch.device("cpu")
+
+    g_host, centers = synth_device(torch, args, dev, args.gallery, 42)
+    b_host, _ = synth_device(torch, args, dev, args.bank, 43, centers=centers)
+    sample = args.cpu_sample or 0
+    a2 = argparse.Namespace(**vars(args))
+    a2.queries = max(sample, 256)
+    img, txt, var = (t.numpy() for t in synth_queries(torch, a2, dev, centers, 123))
+    if not sample:
+        sample = min(auto_sample(torch, args, g_host, b_host, img, txt, var), 256)
+        # keep the whole --steps/--warmup run within a few minutes
+        sample = max(8, int(sample * min(1.0, 8.0 / max(1, args.steps + args.warmup))))
+    from oracle import tvc_oracle as O
+    for _ in range(args.warmup):
+        cpu_reference_step(torch, np, O, g_host, b_host, img[:sample], txt[:sample], var[:sample], args.topk)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(torch, np, O, g_host, b_host, img[:sample], txt[:sample], var[:sample], args.topk)
+    secs = time.perf_counter() - t0
+    value = sample * args.steps / secs
+    desc = (f"{sample} queries x {args.variants} variants per step vs the full {args.gallery}+{args.bank} rows; "
+            f"torch fp32 matmul+topk (IndexFlatIP-equivalent; faiss is not installable offline) on {cores} threads + "
+            f"NumPy fp64 scoring + np.bincount")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32 (fp64 statistics)", "data": "synthetic",
+        "config": {"workload": f"north_star/configs[4]: {args.variants} variants, top-{args.topk}, {args.gallery}-image "
+                               f"+ {args.bank}-reference bank, d={args.dim}; bounded sample of {sample} queries per step",
+                   "queries_per_step": sample, "variants": args.variants, "top_k": args.topk,
+                   "gallery_rows": args.gallery, "bank_rows": args.bank, "dim": args.dim},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -155,6 +155,10 @@ int tvc_gallery_device_ptrs(const tvc_gallery* g, const void** bf16_rows, int32_
 /* gather rows (local indices) as fp32 [n, d] into host or device memory */
 int tvc_gallery_get_rows(tvc_gallery* g, const int64_t* idx, int64_t n, float* out, void* stream);
 int tvc_gallery_destroy(tvc_gallery* g);
+/* Non-owning view over caller-owned fp32 device rows [n, d] (rows fetched from peer shards): usable
+ * as ret_gallery / gen_gallery of tvc_consistency_emb and with tvc_gallery_get_rows; not searchable. */
+int tvc_gallery_wrap_f32(tvc_ctx* ctx, const float* device_rows, int64_t n, int32_t d,
+                         int64_t global_row_offset, tvc_gallery** out);
 
 /* Exact top-k of every query row against the gallery: out_sim [m, k] f32, out_idx [m, k] i64.
  * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K. */

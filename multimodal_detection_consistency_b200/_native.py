@@ -74,6 +74,8 @@ _EXPORTS = {
                                           C.POINTER(C.c_void_p)]),
     "tvc_gallery_get_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tvc_gallery_destroy": (C.c_int, [C.c_void_p]),
+    "tvc_gallery_wrap_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                       C.POINTER(C.c_void_p)]),
     "tvc_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int32,
                              C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tvc_similarity_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32,
@@ -364,6 +366,25 @@ class Gallery:
         self.handle = h
         self.global_row_offset = int(global_row_offset)
 
+    @classmethod
+    def wrap_rows(cls, rows, global_row_offset: int = 0, ctx: Optional[Context] = None) -> "Gallery":
+        """Non-owning view over fp32 CUDA rows [n, d] (keeps `rows` alive); not searchable."""
+        if not (_is_torch(rows) and rows.is_cuda and rows.dim() == 2):
+            raise ValueError("wrap_rows needs a 2-D CUDA tensor")
+        import torch
+        rows = rows.contiguous().to(torch.float32)
+        self = cls.__new__(cls)
+        self.ctx = ctx or Context.get(rows.device.index)
+        self.dim = int(rows.shape[1])
+        self.flags = 0
+        self._keepalive = rows
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tvc_gallery_wrap_f32(self.ctx.handle, _ptr(rows), int(rows.shape[0]), self.dim,
+                                                         int(global_row_offset), C.byref(h)))
+        self.handle = h
+        self.global_row_offset = int(global_row_offset)
+        return self
+
     def __len__(self) -> int:
         n = C.c_int64()
         self.ctx.check(self.ctx.lib.tvc_gallery_info(self.handle, C.byref(n), None, None, None))
@@ -388,7 +409,15 @@ class Gallery:
     def move_row(self, src: int, dst: int):
         self.ctx.check(self.ctx.lib.tvc_gallery_move_row(self.handle, int(src), int(dst), None))
 
-    def get_rows(self, idx) -> np.ndarray:
+    def get_rows(self, idx):
+        """fp32 rows for LOCAL indices: numpy in -> numpy out, torch cuda in -> torch cuda out."""
+        if _is_torch(idx) and idx.is_cuda:
+            import torch
+            idx = idx.contiguous().to(torch.int64)
+            out = torch.empty((int(idx.shape[0]), self.dim), dtype=torch.float32, device=idx.device)
+            self.ctx.check(self.ctx.lib.tvc_gallery_get_rows(self.handle, _ptr(idx), int(idx.shape[0]), _ptr(out),
+                                                             _stream_of(idx)))
+            return out
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         out = np.empty((idx.shape[0], self.dim), np.float32)
         self.ctx.check(self.ctx.lib.tvc_gallery_get_rows(self.handle, _ptr(idx), int(idx.shape[0]), _ptr(out), None))

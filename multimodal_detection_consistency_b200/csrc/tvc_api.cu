@@ -41,6 +41,7 @@ struct tvc_gallery {
   int d = 0, d_pad = 0;
   int64_t offset = 0;
   uint32_t flags = 0;
+  bool external = false;  // wraps caller-owned fp32 rows (tvc_gallery_wrap_f32): never freed, not searchable
   __nv_bfloat16* bf16 = nullptr;
   float* f32 = nullptr;
   CUtensorMap tmap;
@@ -366,6 +367,7 @@ int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, v
   if (!g || n < 0 || (n > 0 && !rows) || dtype < 0 || dtype > TVC_F16) return TVC_ERR_INVALID;
   if (n == 0) return TVC_OK;
   tvc_ctx* ctx = g->ctx;
+  if (g->external) return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_append: wrapped row view");
   if (g->n + n >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -400,7 +402,7 @@ int tvc_gallery_truncate(tvc_gallery* g, int64_t n) {
 }
 
 int tvc_gallery_move_row(tvc_gallery* g, int64_t src, int64_t dst, void* stream) {
-  if (!g || src < 0 || dst < 0 || src >= g->n || dst >= g->n) return TVC_ERR_INVALID;
+  if (!g || g->external || src < 0 || dst < 0 || src >= g->n || dst >= g->n) return TVC_ERR_INVALID;
   if (src == dst) return TVC_OK;
   tvc_ctx* ctx = g->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -468,11 +470,33 @@ int tvc_gallery_destroy(tvc_gallery* g) {
   if (!g) return TVC_OK;
   {
     DeviceGuard guard(g->ctx->device);
-    cudaDeviceSynchronize();
-    if (g->bf16) cudaFree(g->bf16);
-    if (g->f32) cudaFree(g->f32);
+    if (!g->external) {
+      cudaDeviceSynchronize();
+      if (g->bf16) cudaFree(g->bf16);
+      if (g->f32) cudaFree(g->f32);
+    }
   }
   delete g;
+  return TVC_OK;
+}
+
+int tvc_gallery_wrap_f32(tvc_ctx* ctx, const float* device_rows, int64_t n, int32_t d,
+                         int64_t global_row_offset, tvc_gallery** out) {
+  if (!ctx || !out || d <= 0 || n < 0 || (n > 0 && !device_rows))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_wrap_f32: bad argument");
+  if (n > 0 && !is_device_ptr(device_rows))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_wrap_f32: rows must be device memory");
+  tvc_gallery* g = new (std::nothrow) tvc_gallery();
+  if (!g) return TVC_ERR_OOM;
+  g->ctx = ctx;
+  g->n = g->cap = n;
+  g->d = d;
+  g->d_pad = (d + kBK - 1) / kBK * kBK;
+  g->offset = global_row_offset;
+  g->flags = 0;
+  g->external = true;
+  g->f32 = const_cast<float*>(device_rows);
+  *out = g;
   return TVC_OK;
 }
 
@@ -546,6 +570,7 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
   if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad handle");
   if (m < 0 || (m > 0 && (!queries || !out_sim || !out_idx)) || q_dtype < 0 || q_dtype > TVC_F16)
     return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad argument");
+  if (g->external) return fail(ctx, TVC_ERR_INVALID, "tvc_search: wrapped row views are not searchable");
   if (d != g->d) return fail(ctx, TVC_ERR_INVALID, "tvc_search: query dimension != gallery dimension");
   if (k < 1) return fail(ctx, TVC_ERR_INVALID, "tvc_search: k < 1");
   if (k > TVC_MAX_K) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search: k > TVC_MAX_K");
@@ -583,7 +608,7 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
 int tvc_similarity_matrix(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m,
                           int32_t d, uint32_t flags, float* out, void* stream) {
   if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_similarity_matrix: bad handle");
-  if (m < 0 || (m > 0 && (!queries || !out)) || q_dtype < 0 || q_dtype > TVC_F16 || d != g->d)
+  if (m < 0 || (m > 0 && (!queries || !out)) || q_dtype < 0 || q_dtype > TVC_F16 || d != g->d || g->external)
     return fail(ctx, TVC_ERR_INVALID, "tvc_similarity_matrix: bad argument");
   if (m == 0 || g->n == 0) return TVC_OK;
   if (m >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_similarity_matrix: m too large");

@@ -1,0 +1,239 @@
+"""Batched TVC scoring: the public call that feeds whole [Q, V, d] tiles through kernels (a), (b), (c).
+
+One "TVC-scored query" (BASELINE.json metric; the stack of experiments/defenses/detector.py:117-170):
+  1. every text-variant row is searched top-k against the image gallery and the reference bank
+     (kernel a: tvc_search),
+  2. the per-query candidate lists (variant-major) are greedily de-duplicated into <= R retrieval and
+     <= G generative references and the query image is scored against text, variants and references;
+     statistics + AdversarialDetector / ConsistencyChecker decisions (kernel b: tvc_consistency_emb),
+  3. the gallery hits are accumulated into the k-occurrence hubness histogram (kernel c).
+
+Multi-GPU: the gallery and the bank are row-sharded, one process per GPU.  Every rank
+searches all query rows against its shard; the packed (sim, global idx) candidates are exchanged so
+that each rank owns the merged global top-k of its slice of the queries (one all-to-all of 12·k
+bytes per row per rank), fetches the few gallery rows its slice needs from the owning shards
+(index + row all-to-all), runs kernel (b) on its slice, and the histogram is all-reduced.
+`torch.distributed` carries the collectives (NCCL on GPUs; gloo + a CPU engine in the tests).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as N
+
+
+class CudaEngine:
+    """Kernels through libtvc.so.  (tests substitute an oracle-backed engine to exercise the
+    multi-rank host logic on CPU with gloo; the product has no other engine.)"""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise N.TvcError(N.TVC_ERR_NO_DEVICE, "TVCScorer needs a CUDA device; libtvc has no CPU fallback")
+        self.device = device
+        self.ctx = N.Context.get(device.index if device.index is not None else torch.cuda.current_device())
+
+    def make_gallery(self, rows, offset, normalize=False):
+        return N.Gallery(rows, global_row_offset=offset, normalize=normalize, ctx=self.ctx)
+
+    def wrap_rows(self, rows, offset=0):
+        return N.Gallery.wrap_rows(rows, offset, ctx=self.ctx)
+
+    def search(self, gallery, q, k, threshold=-math.inf):
+        return gallery.search(q, k, threshold)
+
+    def merge(self, sims, idx, k):
+        return self.ctx.merge_topk(sims, idx, k)
+
+    def get_rows(self, gallery, local_idx):
+        return gallery.get_rows(local_idx)
+
+    def consistency(self, params, img, txt, var, ret_gallery, ret_idx, gen, g_cnt, gen_gallery, gen_idx):
+        return self.ctx.consistency_emb(params, img, txt, var, ret_gallery=ret_gallery, ret_idx=ret_idx, gen=gen,
+                                        g_cnt=g_cnt, gen_gallery=gen_gallery, gen_idx=gen_idx)
+
+    def k_occurrence(self, idx, n_bins, counts):
+        return self.ctx.k_occurrence(idx, n_bins, 0, counts)
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous row shard of rank `rank`: rows [lo, hi) with ceil(n / world) rows per rank."""
+    per = -(-n // world) if world > 0 else n
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def slice_bounds(q: int, world: int, rank: int):
+    per = -(-q // world)
+    lo = min(q, rank * per)
+    return lo, min(q, lo + per)
+
+
+class TVCScorer:
+    """score_batch(img, txt, var) -> scores, decisions, top-k; see the module docstring."""
+
+    def __init__(self, gallery_rows, bank_rows=None, *, k: int = 10, params: Optional[N.DetectorParams] = None,
+                 device=None, total_gallery_rows: Optional[int] = None, total_bank_rows: Optional[int] = None,
+                 bank_threshold: float = -math.inf, track_hubness: bool = True, process_group=None,
+                 engine=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = process_group
+        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        self.rank = self.dist.get_rank(process_group) if self.dist else 0
+        if engine is None:
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            engine = CudaEngine(dev)
+        self.engine = engine
+        self.device = engine.device
+        self.k = int(k)
+        self.params = params if params is not None else N.default_params()
+        self.bank_threshold = float(bank_threshold)
+        n_local = int(gallery_rows.shape[0])
+        self.n_total = int(total_gallery_rows) if total_gallery_rows is not None else n_local
+        self.g_lo, self.g_hi = shard_bounds(self.n_total, self.world, self.rank)
+        if self.g_hi - self.g_lo != n_local:
+            raise ValueError(f"rank {self.rank}: gallery shard has {n_local} rows, expected {self.g_hi - self.g_lo}")
+        self.gallery = engine.make_gallery(gallery_rows, self.g_lo)
+        self.bank = None
+        self.b_total = 0
+        if bank_rows is not None:
+            b_local = int(bank_rows.shape[0])
+            self.b_total = int(total_bank_rows) if total_bank_rows is not None else b_local
+            self.b_lo, self.b_hi = shard_bounds(self.b_total, self.world, self.rank)
+            if self.b_hi - self.b_lo != b_local:
+                raise ValueError(f"rank {self.rank}: bank shard has {b_local} rows, expected {self.b_hi - self.b_lo}")
+            self.bank = engine.make_gallery(bank_rows, self.b_lo)
+        self.track_hubness = track_hubness
+        self.k_occurrence = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
+        self._host: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, x, dtype=torch.float32):
+        if x is None:
+            return None
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(x)
+        return x.to(self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def _pinned(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        buf = self._host.get(name)
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=self.device.type == "cuda")
+            self._host[name] = buf
+        return buf
+
+    def _a2a(self, send: torch.Tensor, send_counts, recv_counts) -> torch.Tensor:
+        """all_to_all_single over dim 0 with per-peer row counts."""
+        out = torch.empty((int(sum(recv_counts)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        self.dist.all_to_all_single(out, send.contiguous(), list(map(int, recv_counts)), list(map(int, send_counts)),
+                                    group=self.group)
+        return out
+
+    def _global_topk(self, gallery, rows_all: torch.Tensor, q_total: int, v: int, threshold: float):
+        """Local search of every row, then (multi-rank) exchange + merge so that this rank holds the
+        global top-k of its query slice.  Returns (sims [Qs*V, k], idx [Qs*V, k])."""
+        sims, idx = self.engine.search(gallery, rows_all, self.k, threshold)
+        if self.world == 1:
+            return sims, idx
+        k = self.k
+        per = -(-q_total // self.world)
+        send_counts = []
+        for r in range(self.world):
+            lo, hi = slice_bounds(q_total, self.world, r)
+            send_counts.append((hi - lo) * v)
+        lo, hi = slice_bounds(q_total, self.world, self.rank)
+        mine = (hi - lo) * v
+        recv_counts = [mine] * self.world
+        del per
+        rs = self._a2a(sims, send_counts, recv_counts).view(self.world, mine, k)
+        ri = self._a2a(idx, send_counts, recv_counts).view(self.world, mine, k)
+        return self.engine.merge(rs.permute(1, 0, 2).contiguous(), ri.permute(1, 0, 2).contiguous(), k)
+
+    def _fetch_rows(self, gallery, total_rows: int, idx: torch.Tensor):
+        """Rows of the (sharded) gallery for the global indices in `idx`: returns (view gallery over
+        the fetched rows [U, d], remapped idx with the same shape pointing into it)."""
+        flat = idx.reshape(-1)
+        uniq, inv = torch.unique(flat, return_inverse=True)      # sorted; a leading -1 marks unused slots
+        valid = uniq >= 0
+        per = -(-total_rows // self.world)
+        owner = torch.div(uniq.clamp(min=0), per, rounding_mode="floor")
+        owner[~valid] = self.world                                  # never sent
+        send_counts = torch.bincount(owner, minlength=self.world + 1)[: self.world]
+        recv_counts = torch.empty_like(send_counts)
+        self.dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        want = uniq[valid]                                          # sorted by index == sorted by owner
+        asked = self._a2a(want, sc, rc)                             # global indices peers want from me
+        lo, _ = shard_bounds(total_rows, self.world, self.rank)
+        rows = self.engine.get_rows(gallery, asked - lo)            # [sum(rc), d] fp32
+        got = self._a2a(rows, rc, sc)                               # rows for `want`, same order
+        # remap: position of every idx entry inside `got`; unused slots stay negative
+        shift = int((~valid).sum().item())
+        remapped = (inv - shift).reshape(idx.shape)
+        remapped = torch.where(idx >= 0, remapped, torch.full_like(remapped, -1))
+        return self.engine.wrap_rows(got), remapped
+
+    # ------------------------------------------------------------------ the call
+    def score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False):
+        """img, txt: [Q, d]; var: [Q, V, d] (host or device, fp32).  In multi-rank mode every rank passes
+        the SAME full batch and receives the results of its own contiguous slice of the queries.
+        Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim."""
+        var = self._dev(var)
+        q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
+        if v != self.params.n_variants:
+            raise ValueError(f"{v} variants given, params.n_variants = {self.params.n_variants}")
+        lo, hi = slice_bounds(q_total, self.world, self.rank)
+        qs = hi - lo
+        k = self.k
+        rows_all = var.view(q_total * v, d)
+        g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
+        b_sim = b_idx = None
+        if self.bank is not None:
+            b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
+        img_s, txt_s, var_s = self._dev(img)[lo:hi], self._dev(txt)[lo:hi], var[lo:hi]
+        gen_s = self._dev(gen)[lo:hi] if gen is not None else None
+        gcnt_s = self._dev(g_cnt, torch.int32)[lo:hi] if g_cnt is not None else None
+        ret_idx = g_idx.view(qs, v * k)
+        gen_idx = b_idx.view(qs, v * k) if (b_idx is not None and gen is None) else None
+        ret_gal, gen_gal = self.gallery, self.bank
+        if self.world > 1:
+            # (ranks with an empty query slice still take part: the collectives must stay matched)
+            ret_gal, ret_idx = self._fetch_rows(self.gallery, self.n_total, ret_idx)
+            if gen_idx is not None:
+                gen_gal, gen_idx = self._fetch_rows(self.bank, self.b_total, gen_idx)
+        if qs > 0:
+            scores, flags = self.engine.consistency(self.params, img_s, txt_s, var_s, ret_gal, ret_idx, gen_s, gcnt_s,
+                                                    gen_gal if gen_s is None else None, gen_idx)
+        else:
+            scores = torch.empty((0, N.NSCORES), dtype=torch.float32, device=self.device)
+            flags = torch.empty((0,), dtype=torch.uint8, device=self.device)
+        if self.track_hubness:
+            if self.world > 1:
+                local = torch.zeros_like(self.k_occurrence)
+                if qs > 0:
+                    self.engine.k_occurrence(g_idx, self.n_total, local)
+                self.dist.all_reduce(local, group=self.group)
+                self.k_occurrence += local
+            else:
+                self.engine.k_occurrence(g_idx, self.n_total, self.k_occurrence)
+        out = dict(scores=scores, flags=flags, topk_idx=g_idx.view(qs, v, k), topk_sim=g_sim.view(qs, v, k))
+        if b_idx is not None:
+            out.update(bank_idx=b_idx.view(qs, v, k), bank_sim=b_sim.view(qs, v, k))
+        if to_host:
+            host = {}
+            for name, t in out.items():
+                buf = self._pinned(name, t)
+                buf.copy_(t, non_blocking=True)
+                host[name] = buf
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            out = host
+        out["slice"] = (lo, hi)
+        return out
+
+    def reset_hubness(self):
+        if self.k_occurrence is not None:
+            self.k_occurrence.zero_()

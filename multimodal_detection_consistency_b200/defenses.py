@@ -1,0 +1,309 @@
+"""Drop-ins for the experiments-side TVC stack: `ConsistencyChecker`
+(experiments/defenses/consistency_checker.py:31), `DetectionConfig` / `MultiModalDefenseDetector`
+(experiments/defenses/detector.py:19,46) and the retrieval-reference generator front
+(experiments/defenses/retrieval_ref.py:34).
+
+The per-sample arithmetic of `_compute_consistency_scores` (:228-293: <= 19 encoder calls + scalar
+cosines + np.mean / np.std / np.var) and of `make_decision` (voting, stateless adaptive threshold,
+confidence) is kernel (b); retrieval of references (:184-204 -> retrieval_ref.py:246-290) is kernel
+(a).  `detect_batch` / `detect_embeddings` score whole batches per launch.  The one stateful piece —
+the threshold history blend (consistency_checker.py:234-239) — stays on the host, applied to the
+kernel's stateless threshold, as the reference applies it after its own stateless adjustments.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from ._native import Gallery
+
+logger = logging.getLogger(__name__)
+
+_VOTING = {"simple": 0, "weighted": 1, "adaptive": 2}
+_CC_KEYS = ("original_similarity", "text_variant_consistency", "retrieval_consistency", "generative_consistency")
+
+
+def _np(x) -> np.ndarray:
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+
+
+class ConsistencyChecker:
+    """Same constructor, attributes and result dict as the reference (consistency_checker.py:31-117)."""
+
+    def __init__(self, threshold: float = 0.5, adaptive_threshold: bool = True, voting_strategy: str = "weighted",
+                 weights: Optional[Dict[str, float]] = None):
+        if voting_strategy not in _VOTING:
+            raise ValueError(f"unknown voting strategy: {voting_strategy}")
+        self.base_threshold = threshold
+        self.adaptive_threshold = adaptive_threshold
+        self.voting_strategy = voting_strategy
+        self.weights = weights or {k: 0.25 for k in _CC_KEYS}
+        self.detection_history: List[Dict[str, Any]] = []
+        self.threshold_history: List[float] = []
+
+    def params(self, v: int = 5, r: int = 10, g: int = 3, **extra) -> N.DetectorParams:
+        return N.default_params(n_variants=v, n_retrieval=r, n_generative=g, voting=_VOTING[self.voting_strategy],
+                                cc_weights=[float(self.weights.get(k, 0.0)) for k in _CC_KEYS],
+                                cc_base_threshold=float(self.base_threshold), cc_adaptive=int(self.adaptive_threshold),
+                                **extra)
+
+    # -- stateful host part -------------------------------------------------------------------
+    def _blend(self, stateless_thr: float) -> float:
+        """consistency_checker.py:234-242 applied to the kernel's (already adjusted) threshold."""
+        thr = float(stateless_thr)
+        if self.adaptive_threshold and len(self.threshold_history) > 10:
+            thr = 0.7 * thr + 0.3 * float(np.mean(self.threshold_history[-10:]))
+            thr = float(np.clip(thr, 0.1, 0.9))
+        return thr
+
+    def decide_from_kernel(self, score_rows: np.ndarray) -> List[Dict[str, Any]]:
+        """Turn kernel (b) rows [Q, 24] into the reference's decision dicts, in order, maintaining the
+        threshold / detection histories exactly as sequential `make_decision` calls would."""
+        ix = N.SCORE_INDEX
+        out = []
+        for s in np.asarray(score_rows):
+            overall = float(s[ix["overall_score"]])
+            thr = self._blend(float(s[ix["threshold"]]))
+            if thr == float(s[ix["threshold"]]):
+                conf = float(s[ix["confidence"]])
+            else:  # history moved the threshold: redo the distance term (consistency_checker.py:249-271)
+                cmv = float(s[ix["cross_modal_variance"]])
+                valid = [float(s[ix[k]]) for k in _CC_KEYS if float(s[ix[k]]) > 0]
+                cons = 1.0 - float(np.std(valid)) if len(valid) > 1 else 0.5
+                conf = float(np.clip(np.mean([abs(overall - thr) / thr, cons, 1.0 - min(cmv, 1.0)]), 0.0, 1.0))
+            res = {"is_adversarial": bool(overall < thr), "confidence": conf, "overall_score": overall,
+                   "threshold": thr}
+            self.detection_history.append(dict(res))
+            self.threshold_history.append(thr)
+            out.append(res)
+        return out
+
+    def make_decision(self, consistency_scores: Dict[str, float], return_details: bool = False) -> Dict[str, Any]:
+        """consistency_checker.py:74-117 for one score dict.  The dict already holds the means / stds,
+        so it is fed to kernel (b) as two-point similarity lists with exactly those moments."""
+        g = consistency_scores.get
+
+        def pair(mean, std):
+            return np.array([[mean - std, mean + std]], np.float32)
+
+        s0 = np.array([g("original_similarity", 0.0)], np.float32)
+        sv = pair(g("text_variant_consistency", 0.0), g("text_variant_std", 0.0))
+        sr = pair(g("retrieval_consistency", 0.0), g("retrieval_std", 0.0))
+        sg = pair(g("generative_consistency", 0.0), g("generative_std", 0.0))
+        r_cnt = np.array([0 if g("retrieval_consistency", 0.0) == 0 else 2], np.int32)
+        g_cnt = np.array([0 if g("generative_consistency", 0.0) == 0 else 2], np.int32)
+        scores, _ = N.Context.get().consistency_sims(self.params(2, 2, 2), s0, sv, sr, r_cnt, sg, g_cnt)
+        row = scores[0].astype(np.float64)
+        ix = N.SCORE_INDEX
+        # cross_modal_variance is an INPUT of the reference's make_decision: honour the caller's value
+        cmv = float(g("cross_modal_variance", 0.0))
+        thr = float(self.base_threshold)
+        if self.adaptive_threshold:
+            if cmv > 0.1:
+                thr += 0.1
+            if np.mean([g("text_variant_std", 0), g("retrieval_std", 0), g("generative_std", 0)]) > 0.2:
+                thr += 0.05
+            thr = float(np.clip(thr, 0.1, 0.9))
+        row[ix["threshold"]] = thr
+        row[ix["cross_modal_variance"]] = cmv
+        overall = float(row[ix["overall_score"]])
+        valid = [float(g(k, 0.0)) for k in _CC_KEYS if float(g(k, 0.0)) > 0]
+        cons = 1.0 - float(np.std(valid)) if len(valid) > 1 else 0.5
+        row[ix["confidence"]] = float(np.clip(np.mean([abs(overall - thr) / thr, cons, 1.0 - min(cmv, 1.0)]), 0, 1))
+        res = self.decide_from_kernel(row[None])[0]
+        if return_details:
+            res["details"] = {"scores": dict(consistency_scores), "overall_score": res["overall_score"],
+                              "threshold": res["threshold"], "voting_strategy": self.voting_strategy}
+        return res
+
+    def calibrate_threshold(self, validation_scores: List[Dict[str, float]], validation_labels: List[bool]) -> float:
+        """consistency_checker.py:366-409: sweep 81 thresholds in [0.1, 0.9] for the best F1 (one kernel
+        launch scores every validation sample; the sweep itself is a tiny host loop)."""
+        g = [s.get for s in validation_scores]
+
+        def col(k):
+            return np.array([f(k, 0.0) for f in g], np.float32)
+
+        def pair(m, s):
+            return np.stack([col(m) - col(s), col(m) + col(s)], 1)
+
+        scores, _ = N.Context.get().consistency_sims(
+            self.params(2, 2, 2), col("original_similarity"), pair("text_variant_consistency", "text_variant_std"),
+            pair("retrieval_consistency", "retrieval_std"),
+            np.where(col("retrieval_consistency") == 0, 0, 2).astype(np.int32),
+            pair("generative_consistency", "generative_std"),
+            np.where(col("generative_consistency") == 0, 0, 2).astype(np.int32))
+        overall = scores[:, N.SCORE_INDEX["overall_score"]].astype(np.float64)
+        labels = np.asarray(validation_labels, dtype=bool)
+        best_f1, best_thr = -1.0, self.base_threshold
+        for thr in np.linspace(0.1, 0.9, 81):
+            pred = overall < thr
+            tp = int((pred & labels).sum())
+            fp = int((pred & ~labels).sum())
+            fn = int((~pred & labels).sum())
+            prec = tp / (tp + fp) if tp + fp else 0.0
+            rec = tp / (tp + fn) if tp + fn else 0.0
+            f1 = 2 * prec * rec / (prec + rec) if prec + rec else 0.0
+            if f1 > best_f1:
+                best_f1, best_thr = f1, float(thr)
+        self.base_threshold = best_thr
+        return best_thr
+
+    def get_statistics(self) -> Dict[str, Any]:
+        if not self.detection_history:
+            return {"total_detections": 0}
+        adv = sum(1 for d in self.detection_history if d["is_adversarial"])
+        return {"total_detections": len(self.detection_history), "adversarial_detected": adv,
+                "adversarial_rate": adv / len(self.detection_history),
+                "avg_confidence": float(np.mean([d["confidence"] for d in self.detection_history])),
+                "avg_threshold": float(np.mean(self.threshold_history)), "current_threshold": self.base_threshold}
+
+    def reset_history(self):
+        self.detection_history.clear()
+        self.threshold_history.clear()
+
+
+@dataclass
+class DetectionConfig:
+    """experiments/defenses/detector.py:19-43."""
+    use_text_variants: bool = True
+    text_variant_count: int = 5
+    use_retrieval_ref: bool = True
+    retrieval_top_k: int = 10
+    retrieval_weight: float = 0.3
+    use_generative_ref: bool = True
+    generation_count: int = 3
+    generation_weight: float = 0.4
+    consistency_threshold: float = 0.5
+    adaptive_threshold: bool = True
+    voting_strategy: str = "weighted"
+    device: str = "cuda"
+    debug_mode: bool = False
+
+
+class RetrievalReferenceIndex:
+    """The retrieval side of experiments/defenses/retrieval_ref.py (features.npy database, top-
+    `rerank_top_k` inner-product search, similarity floor 0.3, cut to `reference_count`, :173-216,246-290)
+    for whole batches on the GPU."""
+
+    def __init__(self, features, metadata: Optional[Sequence[Dict[str, Any]]] = None, reference_count: int = 5,
+                 similarity_threshold: float = 0.3, rerank_top_k: int = 20, enable_reranking: bool = True):
+        self.reference_features = _np(features)
+        self.reference_metadata = list(metadata) if metadata is not None else []
+        self.reference_count = reference_count
+        self.similarity_threshold = similarity_threshold
+        self.search_k = rerank_top_k if enable_reranking else reference_count
+        self.gallery = Gallery(self.reference_features)
+
+    def retrieve_batch(self, query_features):
+        """[Q, d] or [Q, V, d] -> (sims, idx) [..., reference_count]; entries under the floor are -1."""
+        k = min(self.search_k, max(1, len(self.gallery)))
+        sims, idx = self.gallery.search(query_features, k, threshold=self.similarity_threshold)
+        return sims[..., : self.reference_count], idx[..., : self.reference_count]
+
+    def retrieve_references(self, query_features) -> List[Dict[str, Any]]:
+        """One query row -> the reference's list of dicts (:250-262)."""
+        sims, idx = self.retrieve_batch(_np(query_features).reshape(1, -1))
+        out = []
+        for s, i in zip(sims[0], idx[0]):
+            if i >= 0:
+                out.append({"index": int(i), "similarity": float(s),
+                            "metadata": self.reference_metadata[i] if i < len(self.reference_metadata) else {},
+                            "features": self.reference_features[i]})
+        return out
+
+
+class MultiModalDefenseDetector:
+    """experiments/defenses/detector.py:46-170 with batched scoring.  `clip_model` must provide
+    encode_image / encode_text; `text_variant_generator.generate_variants(text)`,
+    `retrieval_index` (RetrievalReferenceIndex or anything with `.gallery` and `.retrieve_batch`) and
+    `generative_generator.generate_references(text) -> list[image]` are optional, as in the reference."""
+
+    def __init__(self, clip_model=None, qwen_model=None, sd_model=None, config: Optional[DetectionConfig] = None,
+                 text_variant_generator=None, retrieval_index: Optional[RetrievalReferenceIndex] = None,
+                 generative_generator=None):
+        self.clip_model = clip_model
+        self.config = config or DetectionConfig()
+        self.text_variant_generator = text_variant_generator if self.config.use_text_variants else None
+        self.retrieval_generator = retrieval_index if self.config.use_retrieval_ref else None
+        self.generative_generator = generative_generator if self.config.use_generative_ref else None
+        self.consistency_checker = ConsistencyChecker(threshold=self.config.consistency_threshold,
+                                                      adaptive_threshold=self.config.adaptive_threshold,
+                                                      voting_strategy=self.config.voting_strategy)
+
+    # -- embedding entry: everything after the encoders, one launch ------------------------------
+    def detect_embeddings(self, image_emb, text_emb, variant_emb=None, generative_emb=None, generative_counts=None,
+                          return_scores: bool = False):
+        """image_emb/text_emb [Q,d], variant_emb [Q,V,d], generative_emb [Q,G,d].  Retrieval references
+        come from searching every variant row (original text first when no variants) in the retrieval
+        index.  Returns the list of reference-shaped result dicts (and the [Q,24] score matrix)."""
+        img, txt = _np(image_emb), _np(text_emb)
+        var = _np(variant_emb) if variant_emb is not None else None
+        gen = _np(generative_emb) if generative_emb is not None else None
+        q = img.shape[0]
+        v = 0 if var is None else var.shape[1]
+        g = 0 if gen is None else gen.shape[1]
+        ret_gal, ret_idx = None, None
+        if self.retrieval_generator is not None:
+            rows = np.concatenate([txt[:, None, :], var], axis=1) if var is not None else txt[:, None, :]
+            _, idx = self.retrieval_generator.retrieve_batch(rows)          # [Q, 1+V, reference_count]
+            ret_gal, ret_idx = self.retrieval_generator.gallery, idx.reshape(q, -1)
+        params = self.consistency_checker.params(v, self.config.retrieval_top_k if ret_idx is not None else 0, g)
+        scores, _ = N.Context.get().consistency_emb(params, img, txt, var, ret_gallery=ret_gal, ret_idx=ret_idx,
+                                                    gen=gen, g_cnt=generative_counts)
+        decisions = self.consistency_checker.decide_from_kernel(scores)
+        results = [{"is_adversarial": d["is_adversarial"], "confidence": d["confidence"],
+                    "consistency_score": d["overall_score"]} for d in decisions]
+        return (results, scores) if return_scores else results
+
+    # -- reference-shaped entries -----------------------------------------------------------------
+    def _encode(self, image, text):
+        variants = [text]
+        if self.text_variant_generator is not None:
+            try:
+                variants = [text] + list(self.text_variant_generator.generate_variants(text))
+            except Exception as e:  # noqa: BLE001
+                logger.warning("text variant generation failed: %s", e)
+        temb = _np(self.clip_model.encode_text(variants))
+        iemb = _np(self.clip_model.encode_image(image)).reshape(1, -1)
+        gens = []
+        if self.generative_generator is not None:
+            try:
+                for t in variants[: min(len(variants), 3)]:
+                    gens.extend(self.generative_generator.generate_references(t))
+                gens = gens[: self.config.generation_count]
+            except Exception as e:  # noqa: BLE001
+                logger.warning("generative reference generation failed: %s", e)
+                gens = []
+        gemb = np.concatenate([_np(self.clip_model.encode_image(gi)).reshape(1, -1) for gi in gens]) if gens else None
+        return iemb[0], temb[0], temb[1:], gemb, variants
+
+    def detect(self, image, text: str, return_details: bool = False) -> Dict[str, Any]:
+        """experiments/defenses/detector.py:117-170."""
+        return self.batch_detect([image], [text], return_details)[0]
+
+    def batch_detect(self, images, texts: List[str], return_details: bool = False) -> List[Dict[str, Any]]:
+        enc = [self._encode(im, tx) for im, tx in zip(images, texts)]
+        buckets: Dict[Any, List[int]] = {}
+        for i, e in enumerate(enc):
+            buckets.setdefault((e[2].shape[0], 0 if e[3] is None else e[3].shape[0]), []).append(i)
+        out: List[Optional[Dict[str, Any]]] = [None] * len(enc)
+        for (v, g), members in sorted(buckets.items(), key=lambda kv: kv[1][0]):
+            img = np.stack([enc[i][0] for i in members])
+            txt = np.stack([enc[i][1] for i in members])
+            var = np.stack([enc[i][2] for i in members]) if v else None
+            gen = np.stack([enc[i][3] for i in members]) if g else None
+            res, scores = self.detect_embeddings(img, txt, var, gen, return_scores=True)
+            for row, i in enumerate(members):
+                r = res[row]
+                if return_details:
+                    r["details"] = {"text_variants": enc[i][4],
+                                    "consistency_scores": {n: float(scores[row, j]) for j, n in enumerate(N.SCORE_NAMES)}}
+                out[i] = r
+        return out  # type: ignore[return-value]

@@ -1,0 +1,260 @@
+"""The reference-shaped host classes on the GPU, checked against the oracle and against the outputs
+of the reference's own classes (tests/golden/*.npz)."""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import tvc_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+class TableClip:
+    """Encoder stand-in: text / image ids -> rows of seeded embedding tables."""
+
+    def __init__(self, text_table, image_table):
+        self.t, self.i = text_table, image_table
+
+    def encode_text(self, texts, normalize=True):
+        return np.stack([self.t[s] for s in texts])
+
+    def encode_image(self, images, normalize=True):
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        return np.stack([self.i[int(s)] for s in images])
+
+
+def _unit(rng, n, d):
+    return O.l2_normalize(rng.standard_normal((n, d), dtype=np.float32))
+
+
+def test_retriever_drop_in(tmp_path):
+    from multimodal_detection_consistency_b200 import MultiModalRetriever, RetrievalConfig
+    rng = np.random.default_rng(0)
+    n, d = 3000, 128
+    gal = _unit(rng, n, d)
+    texts = {f"caption {i}": O.l2_normalize(gal[i % n][None] + 0.05 * rng.standard_normal((1, d), dtype=np.float32))[0]
+             for i in range(40)}
+    clip = TableClip(texts, {})
+    r = MultiModalRetriever(RetrievalConfig(top_k=10), clip_model=clip)
+    assert r.retrieve_images_by_text("caption 0") == ([], [])        # no index yet: reference error convention
+    paths = [f"img_{i}.jpg" for i in range(n)]
+    r.build_image_index_from_features(gal, paths)
+    q = np.stack(list(texts.values()))
+    ref_s, ref_i = O.search(q, gal, 10)
+    for j, t in enumerate(texts):
+        p, s = r.retrieve_images_by_text(t)
+        assert p == [paths[i] for i in ref_i[j]]
+        assert np.abs(np.array(s) - ref_s[j]).max() <= 1e-5
+        assert r.retrieve(t, k=5)[0] == p[:5] and r.search(t, top_k=5)[0] == p[:5]   # caller-side spellings
+    batch = r.batch_retrieve_images_by_texts(list(texts), top_k=7)
+    assert [b[0] for b in batch] == [[paths[i] for i in ref_i[j][:7]] for j in range(len(texts))]
+    assert r.get_stats()["image_count"] == n and r.get_stats()["retrieval_cache_size"] > 0
+    # _search_index keeps the (indices, scores) order and FAISS -1 padding
+    small = MultiModalRetriever(RetrievalConfig(), clip_model=clip)
+    small.build_image_index_from_features(gal[:4], paths[:4])
+    idx, sc = small._search_index(small.image_index, q[:1], 6)
+    assert idx.tolist()[4:] == [-1, -1] and np.isneginf(sc[4:]).all()
+    # persistence round trip
+    r.save_image_index(str(tmp_path / "idx.pkl"))
+    r2 = MultiModalRetriever(RetrievalConfig(), clip_model=clip)
+    r2.load_image_index(str(tmp_path / "idx.pkl"))
+    assert r2.retrieve_images_by_text("caption 3") == r.retrieve_images_by_text("caption 3")
+    # similarity matrix metrics
+    r.text_features = q
+    for metric, tol in [("dot_product", 2e-3), ("cosine", 2e-3), ("euclidean", 2e-3)]:
+        r.config.similarity_metric = metric
+        assert np.abs(r.compute_similarity_matrix() - O.similarity_matrix(q, gal, metric)).max() <= tol
+
+
+def test_faiss_compat_surface(tmp_path):
+    from multimodal_detection_consistency_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(1)
+    g, q = _unit(rng, 1500, 64), _unit(rng, 20, 64)
+    index = faiss.IndexFlatIP(64)
+    assert index.is_trained and index.ntotal == 0
+    index.add(g[:1000])
+    index.add(g[1000:])
+    assert index.ntotal == 1500
+    D, I = index.search(q, 10)
+    ref_s, ref_i = O.search(q, g, 10)
+    assert np.array_equal(I, ref_i) and np.abs(D - ref_s).max() <= 1e-5
+    faiss.write_index(index, str(tmp_path / "x.faiss"))
+    D2, I2 = faiss.read_index(str(tmp_path / "x.faiss")).search(q, 10)
+    assert np.array_equal(I2, I)
+    assert faiss.index_cpu_to_gpu(faiss.StandardGpuResources(), 0, index) is index and faiss.get_num_gpus() >= 1
+
+
+def test_reference_bank_matches_reference_outputs(tmp_path):
+    """Golden: the reference's ReferenceBank.query_similar on its shipped snapshot and on a random bank."""
+    from multimodal_detection_consistency_b200 import ReferenceBank, ReferenceBankConfig, ReferenceItem
+    z = np.load(GOLD / "ref_bank.npz")
+    for vecs, queries, idx_w, sim_w, cfg_thr, thr_args in [
+            (z["snap_vectors"], z["snap_queries"], z["snap_idx"][None], z["snap_sim"][None], 0.8, [None]),
+            (z["bank"], z["queries"], z["idx"], z["sim"], 0.6, [None, 0.0, 0.3, 0.75])]:
+        bank = ReferenceBank(ReferenceBankConfig(max_size=1000, similarity_threshold=cfg_thr,
+                                                 persistence_enabled=False, save_path=str(tmp_path / "b"),
+                                                 auto_clustering=False, feature_dim=vecs.shape[1]))
+        items = [ReferenceItem(vector=v.copy(), metadata={"i": i}, timestamp=0.0) for i, v in enumerate(vecs)]
+        bank.references.extend(items)
+        bank._dev_append(items)
+        k = idx_w.shape[2]
+        for ti, ta in enumerate(thr_args):
+            for qi, qv in enumerate(queries):
+                got = bank.query_similar(qv, top_k=k, similarity_threshold=ta)
+                n = int((idx_w[ti, qi] >= 0).sum())
+                assert [it.metadata["i"] for it, _ in got] == idx_w[ti, qi, :n].tolist()
+                assert np.abs(np.array([s for _, s in got]) - sim_w[ti, qi, :n]).max(initial=0) <= 1e-5
+            batch = bank.query_similar_batch(queries, top_k=k, similarity_threshold=ta)
+            assert [[it.metadata["i"] for it, _ in row] for row in batch] == \
+                   [idx_w[ti, qi][idx_w[ti, qi] >= 0].tolist() for qi in range(len(queries))]
+    assert sum(it.access_count for it in items) > 0
+
+
+def test_reference_bank_insert_dedup_eviction_persistence(tmp_path):
+    from multimodal_detection_consistency_b200 import ReferenceBank, ReferenceBankConfig
+    rng = np.random.default_rng(2)
+    cfg = ReferenceBankConfig(max_size=50, similarity_threshold=0.9, persistence_enabled=True,
+                              save_path=str(tmp_path / "bank"), auto_clustering=False, feature_dim=32)
+    bank = ReferenceBank(cfg)
+    vecs = rng.standard_normal((80, 32)).astype(np.float32)
+    assert bank.add_reference(vecs[0], {"i": 0})
+    assert not bank.add_reference(vecs[0] * 1.5 + 1e-3, {"i": "dup"})      # cosine > 0.9 -> rejected
+    for i in range(1, 80):
+        assert bank.add_reference(vecs[i], {"i": i})
+    assert len(bank.references) == 50 and bank.stats["total_removed"] == 30   # fifo eviction
+    assert [r.metadata["i"] for r in bank.references] == list(range(30, 80))
+    live = np.stack([r.vector for r in bank.references])
+    for qv in vecs[40:45]:
+        got = bank.query_similar(qv + 0.2 * rng.standard_normal(32).astype(np.float32), top_k=5,
+                                 similarity_threshold=0.5)
+        idx, sim = O.ref_bank_query(live, qv, top_k=5, similarity_threshold=0.5)
+        assert len(got) >= 1 and got[0][0].metadata["i"] == 30 + int(idx[0])
+    sims = bank._compute_similarities(vecs[33])
+    assert np.abs(sims - O.ref_bank_similarities(live, vecs[33])).max() <= 2e-3
+    # reload from the 4-file JSON layout (src/ref_bank.py:505-576)
+    bank2 = ReferenceBank(cfg)
+    assert len(bank2.references) == 50
+    a, b = bank.query_similar(vecs[60], 3, 0.5), bank2.query_similar(vecs[60], 3, 0.5)
+    assert [x[0].metadata for x in a] == [x[0].metadata for x in b]
+    st = bank.get_statistics()
+    assert st["current_size"] == 50 and st["update_strategy"] == "fifo"
+    # similarity eviction removes one member of the closest pair
+    cfg3 = ReferenceBankConfig(max_size=4, similarity_threshold=0.999, update_strategy="similarity",
+                               persistence_enabled=False, save_path=str(tmp_path / "b3"), auto_clustering=False)
+    b3 = ReferenceBank(cfg3)
+    base = rng.standard_normal((4, 32)).astype(np.float32)
+    base[2] = base[1] + 0.05 * rng.standard_normal(32).astype(np.float32)
+    for i in range(4):
+        assert b3.add_reference(base[i], {"i": i})
+    assert b3.add_reference(rng.standard_normal(32).astype(np.float32), {"i": 4})
+    kept = [r.metadata["i"] for r in b3.references]
+    assert len(kept) == 4 and (1 in kept) != (2 in kept)
+
+
+def test_adversarial_detector_matches_reference_outputs():
+    """Golden: the reference's AdversarialDetector.detect_adversarial on the same table encoders."""
+    from multimodal_detection_consistency_b200 import AdversarialDetector, DetectorConfig
+    z = np.load(GOLD / "detectors.npz")
+    img, txt, var, gen, g_cnt = z["img"], z["txt"], z["var"], z["gen"], z["g_cnt"]
+    nq, V = var.shape[0], var.shape[1]
+    for mode_i, mode in enumerate([str(m) for m in z["agg_modes"]]):
+        want = z["det_scores"][mode_i]
+        results = []
+        dets = []
+        for i in range(nq):
+            tt = {"orig": txt[i], **{f"v{v}": var[i, v] for v in range(V)}}
+            it = {0: img[i], **{1 + g: gen[i, g] for g in range(gen.shape[1])}}
+            ng = int(g_cnt[i])
+            det = AdversarialDetector(
+                DetectorConfig(score_aggregation=mode, enable_cache=False), clip_model=TableClip(tt, it),
+                text_augmenter=types.SimpleNamespace(generate_variants=lambda t: [f"v{v}" for v in range(V)]),
+                sd_generator=types.SimpleNamespace(
+                    generate_reference_images=lambda text, num_images, ng=ng: {"images": list(range(1, 1 + ng))}))
+            r = det.detect(0, "orig")
+            assert "error" not in r, r
+            results.append(r)
+            dets.append(det)
+        got = np.array([[r["detection_scores"]["text_variants"], r["detection_scores"]["sd_reference"],
+                         r["detection_scores"]["consistency"], r["aggregated_score"]] for r in results])
+        assert np.abs(got - want[:, :4]).max() <= 1e-5
+        margin = np.abs(want[:, 3] - 0.5) > 1e-5
+        assert np.array_equal(np.array([r["is_adversarial"] for r in results])[margin], want[margin, 4].astype(bool))
+        d0 = results[0]["detection_details"]
+        assert set(d0["text_variants"]) >= {"original_similarity", "variant_similarities", "mean_variant_similarity",
+                                            "std_variant_similarity", "consistency_score", "variability_score",
+                                            "num_variants"}
+        assert abs(d0["text_variants"]["std_variant_similarity"] - want[0, 5]) <= 1e-5
+    # batched embedding entry: one launch for all samples
+    det = AdversarialDetector(DetectorConfig())
+    out = det.detect_embeddings(img, txt, var, gen, g_cnt)
+    assert np.abs(out["aggregated_score"] - z["det_scores"][0][:, 3]).max() <= 1e-5
+    # never-raise convention
+    bad = AdversarialDetector(DetectorConfig()).detect_adversarial(0, "x")
+    assert bad["is_adversarial"] is False and bad["aggregated_score"] == 0.0 and "error" in bad
+
+
+def test_consistency_checker_matches_reference_outputs():
+    from multimodal_detection_consistency_b200 import ConsistencyChecker
+    z = np.load(GOLD / "consistency_checker.npz")
+    keys = [str(k) for k in z["keys"]]
+    S = z["scores"]
+    for voting in ["simple", "weighted", "adaptive"]:
+        for adaptive in [0, 1]:
+            want = z[f"{voting}_{adaptive}"]
+            for i in range(0, 120):
+                chk = ConsistencyChecker(threshold=0.5, adaptive_threshold=bool(adaptive), voting_strategy=voting)
+                r = chk.make_decision({k: float(S[i, j]) for j, k in enumerate(keys)})
+                assert abs(r["overall_score"] - want[i, 0]) <= 1e-5
+                assert abs(r["threshold"] - want[i, 1]) <= 1e-6
+                assert abs(r["confidence"] - want[i, 2]) <= 1e-5
+                if abs(want[i, 0] - want[i, 1]) > 1e-5:
+                    assert r["is_adversarial"] == bool(want[i, 3])
+    chk = ConsistencyChecker(threshold=0.5, adaptive_threshold=True, voting_strategy="weighted")
+    for i in range(z["history"].shape[0]):   # stateful threshold history, 40 sequential decisions
+        r = chk.make_decision({k: float(S[i, j]) for j, k in enumerate(keys)})
+        w = z["history"][i]
+        assert abs(r["threshold"] - w[1]) <= 1e-6 and abs(r["confidence"] - w[2]) <= 1e-5
+        if abs(w[0] - w[1]) > 1e-5:
+            assert r["is_adversarial"] == bool(w[3])
+    assert chk.get_statistics()["total_detections"] == 40
+
+
+def test_defense_detector_batched_matches_oracle():
+    from multimodal_detection_consistency_b200 import DetectionConfig, MultiModalDefenseDetector, RetrievalReferenceIndex
+    d, nq, V = 256, 120, 5
+    g = O.synth_gallery(2500, d, seed=5, clusters=32)
+    img, txt, var = O.synth_queries(g, nq, V, seed=6)
+    rng = np.random.default_rng(7)
+    gen = O.l2_normalize((img[:, None, :] + 0.6 * rng.standard_normal((nq, 3, d), dtype=np.float32)).reshape(-1, d)).reshape(nq, 3, d)
+    idx = RetrievalReferenceIndex(g)
+    det = MultiModalDefenseDetector(clip_model=None, config=DetectionConfig(), retrieval_index=idx)
+    res, scores = det.detect_embeddings(img, txt, var, gen, return_scores=True)
+    rows = np.concatenate([txt[:, None, :], var], 1).reshape(-1, d)
+    rs, ri = O.search(rows, g, 20, threshold=0.3)
+    cand = ri.reshape(nq, V + 1, 20)[:, :, :5].reshape(nq, -1)
+    ref, rflags, _ = O.consistency_emb(img, txt, var, ret_rows=g, ret_idx=cand, gen=gen)
+    assert np.abs(scores - ref).max() <= 1e-4
+    ok = np.abs(ref[:, O.S_CC_OVERALL] - ref[:, O.S_CC_THRESHOLD]) > 1e-5
+    assert np.array_equal(np.array([r["is_adversarial"] for r in res])[ok], ((rflags & O.FLAG_CC_ADV) != 0)[ok])
+    assert set(res[0]) == {"is_adversarial", "confidence", "consistency_score"}
+
+
+def test_hubness_api_matches_reference_outputs():
+    import torch
+    from multimodal_detection_consistency_b200 import compute_hubness, hubness_scores, k_occurrence
+    z = np.load(GOLD / "hubness.npz")
+    for (ni, nq, d) in [(10, 5, 128), (50, 20, 256), (100, 50, 512)]:
+        im, tx = z[f"bench_{ni}_{nq}_{d}_img"], z[f"bench_{ni}_{nq}_{d}_txt"]
+        assert compute_hubness(im, tx, 10) == float(z[f"bench_{ni}_{nq}_{d}_score"])
+        assert compute_hubness(torch.from_numpy(im).cuda(), torch.from_numpy(tx).cuda()) == float(z[f"bench_{ni}_{nq}_{d}_score"])
+        c = k_occurrence(tx, im, 3)
+        _, ri = O.search(tx, im, 3, metric="cosine")
+        assert np.array_equal(c, O.k_occurrence(ri, ni)) and 0 <= c.min() and c.max() <= nq
+    f = z["spec_features"]
+    counts, hub = hubness_scores(f, 10)
+    assert counts.sum() == f.shape[0] * 10
+    assert np.abs(hub - z["spec_hubness"]).sum() <= 0.01 * z["spec_hubness"].sum() + 1e-12

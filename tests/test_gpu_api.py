@@ -143,7 +143,7 @@ def test_reference_bank_insert_dedup_eviction_persistence(tmp_path):
     st = bank.get_statistics()
     assert st["current_size"] == 50 and st["update_strategy"] == "fifo"
     # similarity eviction removes one member of the closest pair
-    cfg3 = ReferenceBankConfig(max_size=4, similarity_threshold=0.999, update_strategy="similarity",
+    cfg3 = ReferenceBankConfig(max_size=4, similarity_threshold=0.99999, update_strategy="similarity",
                                persistence_enabled=False, save_path=str(tmp_path / "b3"), auto_clustering=False)
     b3 = ReferenceBank(cfg3)
     base = rng.standard_normal((4, 32)).astype(np.float32)
@@ -238,8 +238,19 @@ def test_defense_detector_batched_matches_oracle():
     cand = ri.reshape(nq, V + 1, 20)[:, :, :5].reshape(nq, -1)
     ref, rflags, _ = O.consistency_emb(img, txt, var, ret_rows=g, ret_idx=cand, gen=gen)
     assert np.abs(scores - ref).max() <= 1e-4
-    ok = np.abs(ref[:, O.S_CC_OVERALL] - ref[:, O.S_CC_THRESHOLD]) > 1e-5
-    assert np.array_equal(np.array([r["is_adversarial"] for r in res])[ok], ((rflags & O.FLAG_CC_ADV) != 0)[ok])
+    # one checker decides the batch in order, so the reference's threshold history applies (:234-239)
+    hist = []
+    for i in range(nq):
+        s = ref[i]
+        overall, thr, conf, adv = O.consistency_from_scores(
+            s[O.S_ORIGINAL], s[O.S_TV_MEAN], s[O.S_TV_STD], s[O.S_RET_MEAN], s[O.S_RET_STD], s[O.S_GEN_MEAN],
+            s[O.S_GEN_STD], s[O.S_CROSS_MODAL_VAR], threshold_history=hist)
+        hist.append(thr)
+        assert abs(res[i]["consistency_score"] - overall) <= 1e-4 and abs(res[i]["confidence"] - conf) <= 1e-3
+        if abs(overall - thr) > 1e-4:
+            assert res[i]["is_adversarial"] == adv
+    assert det.consistency_checker.threshold_history == pytest.approx(hist, abs=1e-5)
+    del rflags
     assert set(res[0]) == {"is_adversarial", "confidence", "consistency_score"}
 
 

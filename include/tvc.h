@@ -132,6 +132,9 @@ int tvc_ctx_destroy(tvc_ctx* ctx);
 const char* tvc_last_error(tvc_ctx* ctx);
 /* kernels launched through this context since creation (bench.py's gpu_launches) */
 int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
+/* tuning knobs: "pair_min_rows" = query rows from which tvc_search uses the CTA-pair (cta_group::2)
+ * kernel instead of the single-CTA one (default 4096; 0 = always, INT64_MAX = never) */
+int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value);
 /* CUDA-event time in ms of the last gemm_topk launch made with timing enabled (roofline.achieved) */
 int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled);
 int tvc_ctx_last_search_kernel_ms(tvc_ctx* ctx, float* ms, int64_t* launches);

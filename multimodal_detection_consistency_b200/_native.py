@@ -61,6 +61,7 @@ _EXPORTS = {
     "tvc_ctx_destroy": (C.c_int, [C.c_void_p]),
     "tvc_last_error": (C.c_char_p, [C.c_void_p]),
     "tvc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "tvc_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "tvc_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "tvc_ctx_last_search_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "tvc_gallery_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
@@ -217,6 +218,9 @@ class Context:
     # -- bookkeeping ---------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.tvc_ctx_launch_count(self.handle))
+
+    def set_option(self, name: str, value: int):
+        self.check(self.lib.tvc_ctx_set_option(self.handle, name.encode(), int(value)))
 
     def set_timing(self, enabled: bool):
         self.check(self.lib.tvc_ctx_set_timing(self.handle, int(enabled)))

@@ -1,6 +1,7 @@
 // C ABI of libtvc.so (include/tvc.h): contexts, HBM-resident galleries, workspace management and
 // the orchestration of the kernels.  Plain pointers and sizes; no exceptions cross the boundary.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -29,6 +30,8 @@ struct tvc_ctx {
     size_t bytes = 0;
   };
   std::map<cudaStream_t, Ws> ws;
+  int64_t debug_flags = 0;
+  int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
@@ -44,7 +47,8 @@ struct tvc_gallery {
   bool external = false;  // wraps caller-owned fp32 rows (tvc_gallery_wrap_f32): never freed, not searchable
   __nv_bfloat16* bf16 = nullptr;
   float* f32 = nullptr;
-  CUtensorMap tmap;
+  CUtensorMap tmap;      // box [64 x 256]: single-CTA kernel
+  CUtensorMap tmap128;   // box [64 x 128]: CTA-pair kernel (each CTA stages half a gallery tile)
   int64_t tmap_rows = -1;
 };
 
@@ -125,7 +129,8 @@ int make_tmap(tvc_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, int
 
 int gallery_tmap(tvc_gallery* g) {
   if (g->tmap_rows == g->n) return TVC_OK;
-  const int rc = make_tmap(g->ctx, &g->tmap, g->bf16, g->n, g->d_pad, kBN);
+  int rc = make_tmap(g->ctx, &g->tmap, g->bf16, g->n, g->d_pad, kBN);
+  if (rc == TVC_OK) rc = make_tmap(g->ctx, &g->tmap128, g->bf16, g->n, g->d_pad, 128);
   if (rc == TVC_OK) g->tmap_rows = g->n;
   return rc;
 }
@@ -280,6 +285,7 @@ int tvc_ctx_create(int device, tvc_ctx** out) {
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   ctx->launches0 = launches_so_far();
+  if (const char* e = getenv("TVC_PAIR_MIN_ROWS")) ctx->pair_min_rows = atoll(e);
   *out = ctx;
   return TVC_OK;
 }
@@ -307,6 +313,20 @@ int tvc_ctx_destroy(tvc_ctx* ctx) {
 const char* tvc_last_error(tvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int64_t tvc_ctx_launch_count(tvc_ctx* ctx) { return ctx ? launches_so_far() - ctx->launches0 : 0; }
+
+int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return TVC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (strcmp(name, "pair_min_rows") == 0) {
+    ctx->pair_min_rows = value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "debug_flags") == 0) {
+    ctx->debug_flags = value;
+    return TVC_OK;
+  }
+  return fail(ctx, TVC_ERR_INVALID, std::string("unknown option ") + name);
+}
 
 int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled) {
   if (!ctx) return TVC_ERR_INVALID;
@@ -505,7 +525,10 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
                         int64_t m, int64_t row0, int32_t k, float threshold, uint32_t flags,
                         float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev, cudaStream_t st) {
   const int d = g->d, d_pad = g->d_pad;
-  SearchPlan plan = make_search_plan(m, g->n, d_pad, k, ctx->sm_count);
+  // CTA pairs (cta_group::2) pay off once there are enough 256-row query tiles to feed 74 pairs
+  bool pair = m >= ctx->pair_min_rows && (ctx->sm_count % 2) == 0;
+  SearchPlan plan = make_search_plan(m, g->n, d_pad, k, ctx->sm_count, pair);
+  plan.debug = static_cast<int>(ctx->debug_flags);
   plan.skip_self = (flags & TVC_SEARCH_SKIP_SELF) ? 1 : 0;
   plan.self_offset = row0 - g->offset;  // query row i <-> global gallery row i
   const size_t q_in_b = q_dev ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
@@ -550,7 +573,10 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
     }
     TVC_CUDA(ctx, cudaEventRecord(ev.first, st));
   }
-  TVC_CUDA(ctx, launch_gemm_topk(tq, g->tmap, plan, cand_val, cand_idx, st));
+  if (plan.pair)
+    TVC_CUDA(ctx, launch_gemm_topk_pair(tq, g->tmap128, plan, cand_val, cand_idx, st));
+  else
+    TVC_CUDA(ctx, launch_gemm_topk(tq, g->tmap, plan, cand_val, cand_idx, st));
   if (ctx->timing) {
     TVC_CUDA(ctx, cudaEventRecord(ev.second, st));
     ctx->timed.push_back(ev);

@@ -25,13 +25,13 @@
 // in L2 by the others).
 #include "tvc_internal.h"
 #include "tvc_ptx.cuh"
+#include "tvc_topk.cuh"
 
 namespace tvc {
 
 namespace {
 
 constexpr int kEpiWarp0 = 4;                    // first epilogue warp
-constexpr int kStageFloats = 32 * kBM;          // slow-path staging: [32 cols][128 rows] fp32
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + kStages * kABytes;
 constexpr int kSmemStage = kSmemB + kStages * kBBytes;
@@ -45,47 +45,6 @@ struct Barriers {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
-
-template <int KP>
-struct TopList {
-  float v[KP];
-  int id[KP];
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      v[j] = -INFINITY;
-      id[j] = -1;
-    }
-  }
-  __device__ __forceinline__ float kth() const { return v[KP - 1]; }
-  // x must be > kth().  Replace the tail and bubble up; strict '>' keeps earlier (lower index)
-  // entries ahead of equal newcomers, i.e. order (value desc, index asc).
-  __device__ __forceinline__ void insert(float x, int col) {
-    v[KP - 1] = x;
-    id[KP - 1] = col;
-#pragma unroll
-    for (int j = KP - 1; j > 0; --j) {
-      const bool sw = v[j] > v[j - 1];
-      const float a = v[j - 1], b = v[j];
-      const int ia = id[j - 1], ib = id[j];
-      v[j - 1] = sw ? b : a;
-      v[j] = sw ? a : b;
-      id[j - 1] = sw ? ib : ia;
-      id[j] = sw ? ia : ib;
-    }
-  }
-};
-
-__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
-  float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
-  float m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
-#pragma unroll
-  for (int j = 4; j < 32; j += 2) {
-    m0 = fmaxf(m0, __uint_as_float(r[j]));
-    m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
-  }
-  return fmaxf(m0, m1);
-}
 
 template <int KP>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -209,42 +168,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         const uint32_t t_addr =
             tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-#pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
-          tmem_ld_wait();
-          if (max32(r) > thr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) my_stage[j * kBM] = __uint_as_float(r[j]);
-            const int col0 = nt * kBN + c * 32;
-#pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
-              const float x = my_stage[j * kBM];
-              const int col = col0 + j;
-              if (x > thr && col < p.n_rows && col != self_col) {
-                top.insert(x, col);
-                thr = top.kth();
-              }
-            }
-          }
-        }
+        if (!(p.debug & 1)) topk_consume_tile<KP>(top, thr, t_addr, my_stage, nt * kBN, p.n_rows, self_col, p.debug);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (row < p.m_rows) {
-        const size_t base = (static_cast<size_t>(row) * p.splits + split) * KP;
-        float4* vo = reinterpret_cast<float4*>(cand_val + base);
-        int4* io = reinterpret_cast<int4*>(cand_idx + base);
-#pragma unroll
-        for (int j = 0; j < KP / 4; ++j) {
-          vo[j] = make_float4(top.v[4 * j], top.v[4 * j + 1], top.v[4 * j + 2], top.v[4 * j + 3]);
-          io[j] = make_int4(top.id[4 * j], top.id[4 * j + 1], top.id[4 * j + 2], top.id[4 * j + 3]);
-        }
-      }
+      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx, (static_cast<size_t>(row) * p.splits + split) * KP);
     }
   }
 
@@ -407,16 +338,22 @@ cudaError_t launch_kp(const CUtensorMap& tq, const CUtensorMap& tg, const Search
 
 }  // namespace
 
-SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count) {
+SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count, bool pair) {
   SearchPlan p{};
   p.m_rows = static_cast<int>(m);
   p.n_rows = static_cast<int>(n);
   p.kblocks = d_pad / kBK;
-  p.m_tiles = static_cast<int>((m + kBM - 1) / kBM);
+  p.pair = pair ? 1 : 0;
+  const int tile_m = pair ? 2 * kBM : kBM;       // a CTA pair owns 256 query rows
+  const int workers = pair ? sm_count / 2 : sm_count;
+  p.m_tiles = static_cast<int>((m + tile_m - 1) / tile_m);
   p.n_tiles = static_cast<int>((n + kBN - 1) / kBN);
   p.kp = k <= 10 ? 16 : (k <= 26 ? 32 : 64);
-  // Pick the number of gallery ranges: minimise waves * (tiles per range + warm-up), where the
-  // warm-up term charges the threshold-less first tiles of every unit.
+  // Pick the number of gallery ranges: minimise waves * (tiles per range + warm-up).  Every unit
+  // restarts its per-row lists, and until ~1024*KP columns have streamed by nearly every 32x32 chunk
+  // holds a hit for some lane of the warp, which makes the epilogue (not the MMA) the pacing role:
+  // measured, a unit costs about 2.5*KP extra tile-times (106-tile units ran 25 % slower than
+  // 3907-tile units).  Long units win unless M is too small to fill the machine.
   const int max_s = p.n_tiles < 1024 ? p.n_tiles : 1024;
   long long best_cost = -1;
   int best_s = 1, best_tps = p.n_tiles;
@@ -425,8 +362,9 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
     const int s_eff = (p.n_tiles + tps - 1) / tps;
     if (s_eff != s) continue;
     const long long units = static_cast<long long>(p.m_tiles) * s_eff;
-    const long long waves = (units + sm_count - 1) / sm_count;
-    const long long cost = waves * (tps + 2);
+    const long long waves = (units + workers - 1) / workers;
+    const long long warmup = (5 * p.kp) / 2;
+    const long long cost = waves * (tps + (tps < warmup ? tps : warmup));
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best_s = s_eff;
@@ -436,8 +374,9 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
   p.splits = best_s;
   p.tiles_per_split = best_tps;
   const long long units = static_cast<long long>(p.m_tiles) * p.splits;
-  p.grid = static_cast<int>(units < sm_count ? units : sm_count);
+  p.grid = static_cast<int>(units < workers ? units : workers);
   if (p.grid < 1) p.grid = 1;
+  if (pair) p.grid *= 2;
   return p;
 }
 

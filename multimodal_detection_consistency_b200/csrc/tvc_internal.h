@@ -28,16 +28,23 @@ struct SearchPlan {
   int tiles_per_split;
   int kp;               // candidates kept per (row, split): 16 / 32 / 64
   int grid;
+  int pair;             // 1: CTA-pair kernel (256-row query tiles, cta_group::2)
+  int debug;            // profiling only: bit0 = skip the top-k epilogue (results are garbage)
   int skip_self;        // drop candidate == query row (+ self_offset)
   int64_t self_offset;  // global row of query 0 minus global row of gallery row 0
 };
 
 // plans the unit decomposition for `sm_count` persistent CTAs
-SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count);
+SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count, bool pair);
 
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g,
                              const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
                              cudaStream_t stream);
+
+// CTA-pair revision (tvc_gemm_topk_pair.cu); tmap_g128 has a 128-row box (each CTA stages half a tile)
+cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
+                                  const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                                  cudaStream_t stream);
 
 cudaError_t launch_gemm_store(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g, int m, int n,
                               int kblocks, float* out, int64_t ld_out, int sm_count,

@@ -151,3 +151,29 @@ def test_skip_self_hubness_knn(tvc_ctx):
     ref_s, ref_i = O.search(f, f, 10, skip_self=True)
     _check_topk(sims, idx, ref_s, ref_i, f @ f.T)
     assert (idx != np.arange(1500)[:, None]).all()
+
+
+@pytest.mark.parametrize("m,n,d,k", [(256, 256, 64, 10), (300, 1000, 128, 10), (1000, 5000, 768, 10),
+                                     (2500, 9000, 512, 20), (513, 70000, 128, 10), (640, 3000, 96, 50)])
+def test_pair_kernel_matches_oracle(tvc_ctx, m, n, d, k):
+    """The CTA-pair (cta_group::2) kernel, forced for every size, against the oracle and against the
+    single-CTA kernel (bit-identical outputs: same candidates, same fp32 re-rank)."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(m + n)
+    g, q = _unit(rng, n, d), _unit(rng, m, d)
+    g[n // 2] = g[3]                                   # a tie
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    try:
+        tvc_ctx.set_option("pair_min_rows", 0)
+        sims, idx = gal.search(q, k)
+        sims_self, idx_self = (gal.search(g[:m], k, skip_self=True) if m <= n else (None, None))
+        tvc_ctx.set_option("pair_min_rows", 1 << 62)
+        sims1, idx1 = gal.search(q, k)
+    finally:
+        tvc_ctx.set_option("pair_min_rows", 4096)
+    ref_s, ref_i = O.search(q, g, k)
+    _check_topk(sims, idx, ref_s, ref_i, q @ g.T)
+    assert np.array_equal(idx, idx1) and np.array_equal(sims, sims1)
+    if idx_self is not None:
+        rs, ri = O.search(g[:m], g, k, skip_self=True)
+        _check_topk(sims_self, idx_self, rs, ri, g[:m] @ g.T)

@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="also print per-phase CUDA-event times (stderr)")
     return ap.parse_args()
 
 
@@ -287,6 +288,14 @@ def main():
     k_ms, k_n = ctx.search_kernel_ms()
     ctx.set_timing(False)
     value = args.queries * args.steps / (total_ms / 1e3)
+
+    if args.phases:
+        scorer.profile = True
+        for _ in range(3):
+            scorer.score_batch(img, txt, var)
+        ph = scorer.phase_times()
+        scorer.profile = False
+        print(f"[rank {rank}] phase ms/step: " + ", ".join(f"{k}={v / 3:.3f}" for k, v in ph.items()), file=sys.stderr)
 
     # ---- end-to-end arm: pinned host inputs, H2D + D2H inside the timed region --------------
     e2e = None

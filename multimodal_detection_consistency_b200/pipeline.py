@@ -109,8 +109,27 @@ class TVCScorer:
         self.track_hubness = track_hubness
         self.k_occurrence = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
         self._host: Dict[str, torch.Tensor] = {}
+        self.profile = False            # True: CUDA-event time per phase, read with phase_times()
+        self._marks = []
 
     # ------------------------------------------------------------------ helpers
+    def _mark(self, name: str):
+        if self.profile and self.device.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def phase_times(self) -> Dict[str, float]:
+        """ms per phase accumulated since the last call (profile=True only)."""
+        out: Dict[str, float] = {}
+        if self._marks:
+            torch.cuda.synchronize(self.device)
+            for (n0, e0), (n1, e1) in zip(self._marks, self._marks[1:]):
+                if n1 != "begin":
+                    out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._marks = []
+        return out
+
     def _dev(self, x, dtype=torch.float32):
         if x is None:
             return None
@@ -181,6 +200,7 @@ class TVCScorer:
         """img, txt: [Q, d]; var: [Q, V, d] (host or device, fp32).  In multi-rank mode every rank passes
         the SAME full batch and receives the results of its own contiguous slice of the queries.
         Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim."""
+        self._mark("begin")
         var = self._dev(var)
         q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
         if v != self.params.n_variants:
@@ -190,9 +210,11 @@ class TVCScorer:
         k = self.k
         rows_all = var.view(q_total * v, d)
         g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
+        self._mark("search_gallery")
         b_sim = b_idx = None
         if self.bank is not None:
             b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
+            self._mark("search_bank")
         img_s, txt_s, var_s = self._dev(img)[lo:hi], self._dev(txt)[lo:hi], var[lo:hi]
         gen_s = self._dev(gen)[lo:hi] if gen is not None else None
         gcnt_s = self._dev(g_cnt, torch.int32)[lo:hi] if g_cnt is not None else None
@@ -204,12 +226,14 @@ class TVCScorer:
             ret_gal, ret_idx = self._fetch_rows(self.gallery, self.n_total, ret_idx)
             if gen_idx is not None:
                 gen_gal, gen_idx = self._fetch_rows(self.bank, self.b_total, gen_idx)
+        self._mark("fetch_rows")
         if qs > 0:
             scores, flags = self.engine.consistency(self.params, img_s, txt_s, var_s, ret_gal, ret_idx, gen_s, gcnt_s,
                                                     gen_gal if gen_s is None else None, gen_idx)
         else:
             scores = torch.empty((0, N.NSCORES), dtype=torch.float32, device=self.device)
             flags = torch.empty((0,), dtype=torch.uint8, device=self.device)
+        self._mark("consistency")
         if self.track_hubness:
             if self.world > 1:
                 local = torch.zeros_like(self.k_occurrence)
@@ -219,6 +243,7 @@ class TVCScorer:
                 self.k_occurrence += local
             else:
                 self.engine.k_occurrence(g_idx, self.n_total, self.k_occurrence)
+        self._mark("hubness")
         out = dict(scores=scores, flags=flags, topk_idx=g_idx.view(qs, v, k), topk_sim=g_sim.view(qs, v, k))
         if b_idx is not None:
             out.update(bank_idx=b_idx.view(qs, v, k), bank_sim=b_sim.view(qs, v, k))
@@ -231,6 +256,7 @@ class TVCScorer:
             if self.device.type == "cuda":
                 torch.cuda.current_stream(self.device).synchronize()
             out = host
+            self._mark("to_host")
         out["slice"] = (lo, hi)
         return out
 

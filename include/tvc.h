@@ -163,6 +163,18 @@ int tvc_gallery_destroy(tvc_gallery* g);
 int tvc_gallery_wrap_f32(tvc_ctx* ctx, const float* device_rows, int64_t n, int32_t d,
                          int64_t global_row_offset, tvc_gallery** out);
 
+/* Row-sharded galleries across the GPUs of one box (one process per GPU).  A rank exports its fp32
+ * master as a CUDA IPC handle, peers import it as a view, and a GROUP of [own shard + peer views]
+ * is passed as ret_gallery / gen_gallery of tvc_consistency_emb, whose kernel then reads the
+ * referenced rows of other shards directly from peer HBM over NVLink (no staging collective).
+ * Exchange the 64-byte handles with any host channel (torch.distributed.all_gather_object). */
+#define TVC_IPC_HANDLE_BYTES 64
+int tvc_gallery_export_ipc(tvc_gallery* g, void* handle /* TVC_IPC_HANDLE_BYTES */);
+int tvc_gallery_import_ipc(tvc_ctx* ctx, const void* handle, int64_t n, int32_t d, int64_t global_row_offset,
+                           tvc_gallery** out);
+/* group of up to 16 plain galleries / views with disjoint global index ranges; owns nothing */
+int tvc_gallery_group_create(tvc_ctx* ctx, tvc_gallery** parts, int32_t n_parts, tvc_gallery** out);
+
 /* Exact top-k of every query row against the gallery: out_sim [m, k] f32, out_idx [m, k] i64.
  * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K. */
 int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,

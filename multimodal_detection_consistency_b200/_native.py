@@ -77,6 +77,10 @@ _EXPORTS = {
     "tvc_gallery_destroy": (C.c_int, [C.c_void_p]),
     "tvc_gallery_wrap_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
                                        C.POINTER(C.c_void_p)]),
+    "tvc_gallery_export_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tvc_gallery_import_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                         C.POINTER(C.c_void_p)]),
+    "tvc_gallery_group_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
     "tvc_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int32,
                              C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tvc_similarity_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32,
@@ -387,6 +391,40 @@ class Gallery:
                                                          int(global_row_offset), C.byref(h)))
         self.handle = h
         self.global_row_offset = int(global_row_offset)
+        return self
+
+    # -- row shards across the GPUs of one box ---------------------------------------------------
+    def export_ipc(self) -> bytes:
+        """64-byte CUDA IPC handle of the fp32 master (send it to the peer ranks)."""
+        buf = C.create_string_buffer(64)
+        self.ctx.check(self.ctx.lib.tvc_gallery_export_ipc(self.handle, buf))
+        return buf.raw
+
+    @classmethod
+    def import_ipc(cls, handle: bytes, n: int, dim: int, global_row_offset: int, ctx: Context) -> "Gallery":
+        """View over a PEER rank's fp32 master (read over NVLink by kernel (b)); not searchable."""
+        self = cls.__new__(cls)
+        self.ctx, self.dim, self.flags = ctx, int(dim), 0
+        h = C.c_void_p()
+        ctx.check(ctx.lib.tvc_gallery_import_ipc(ctx.handle, C.create_string_buffer(handle, 64), int(n), int(dim),
+                                                 int(global_row_offset), C.byref(h)))
+        self.handle = h
+        self.global_row_offset = int(global_row_offset)
+        return self
+
+    @classmethod
+    def group(cls, parts) -> "Gallery":
+        """Group of row shards with disjoint global index ranges, usable as ret_gallery / gen_gallery."""
+        parts = list(parts)
+        ctx = parts[0].ctx
+        arr = (C.c_void_p * len(parts))(*[p.handle for p in parts])
+        self = cls.__new__(cls)
+        self.ctx, self.dim, self.flags = ctx, parts[0].dim, 0
+        self._keepalive = parts
+        h = C.c_void_p()
+        ctx.check(ctx.lib.tvc_gallery_group_create(ctx.handle, arr, len(parts), C.byref(h)))
+        self.handle = h
+        self.global_row_offset = 0
         return self
 
     def __len__(self) -> int:

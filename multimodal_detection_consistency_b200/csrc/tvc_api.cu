@@ -45,6 +45,8 @@ struct tvc_gallery {
   int64_t offset = 0;
   uint32_t flags = 0;
   bool external = false;  // wraps caller-owned fp32 rows (tvc_gallery_wrap_f32): never freed, not searchable
+  bool ipc = false;       // f32 was opened from a peer process (cudaIpcOpenMemHandle): closed on destroy
+  std::vector<tvc_gallery*> parts;  // non-empty: a group of row shards (tvc_gallery_group_create)
   __nv_bfloat16* bf16 = nullptr;
   float* f32 = nullptr;
   CUtensorMap tmap;      // box [64 x 256]: single-CTA kernel
@@ -490,7 +492,10 @@ int tvc_gallery_destroy(tvc_gallery* g) {
   if (!g) return TVC_OK;
   {
     DeviceGuard guard(g->ctx->device);
-    if (!g->external) {
+    if (g->ipc) {
+      cudaDeviceSynchronize();
+      if (g->f32) cudaIpcCloseMemHandle(g->f32);
+    } else if (!g->external) {
       cudaDeviceSynchronize();
       if (g->bf16) cudaFree(g->bf16);
       if (g->f32) cudaFree(g->f32);
@@ -518,6 +523,74 @@ int tvc_gallery_wrap_f32(tvc_ctx* ctx, const float* device_rows, int64_t n, int3
   g->f32 = const_cast<float*>(device_rows);
   *out = g;
   return TVC_OK;
+}
+
+int tvc_gallery_export_ipc(tvc_gallery* g, void* handle) {
+  if (!g || !handle || g->external || !g->f32 || !g->parts.empty())
+    return fail(g ? g->ctx : nullptr, TVC_ERR_INVALID, "tvc_gallery_export_ipc: needs an owned gallery with an fp32 master");
+  static_assert(sizeof(cudaIpcMemHandle_t) == TVC_IPC_HANDLE_BYTES, "handle size");
+  DeviceGuard guard(g->ctx->device);
+  TVC_CUDA(g->ctx, cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle), g->f32));
+  return TVC_OK;
+}
+
+int tvc_gallery_import_ipc(tvc_ctx* ctx, const void* handle, int64_t n, int32_t d, int64_t global_row_offset,
+                           tvc_gallery** out) {
+  if (!ctx || !handle || !out || n < 0 || d <= 0) return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_import_ipc: bad argument");
+  DeviceGuard guard(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  TVC_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  tvc_gallery* g = new (std::nothrow) tvc_gallery();
+  if (!g) return TVC_ERR_OOM;
+  g->ctx = ctx;
+  g->n = g->cap = n;
+  g->d = d;
+  g->d_pad = (d + kBK - 1) / kBK * kBK;
+  g->offset = global_row_offset;
+  g->external = true;
+  g->ipc = true;
+  g->f32 = static_cast<float*>(p);
+  *out = g;
+  return TVC_OK;
+}
+
+int tvc_gallery_group_create(tvc_ctx* ctx, tvc_gallery** parts, int32_t n_parts, tvc_gallery** out) {
+  if (!ctx || !parts || !out || n_parts < 1 || n_parts > kMaxParts)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_group_create: 1..16 parts");
+  for (int i = 0; i < n_parts; ++i)
+    if (!parts[i] || parts[i]->ctx != ctx || parts[i]->d != parts[0]->d || !parts[i]->parts.empty())
+      return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_group_create: parts must be plain galleries of one dimension");
+  tvc_gallery* g = new (std::nothrow) tvc_gallery();
+  if (!g) return TVC_ERR_OOM;
+  g->ctx = ctx;
+  g->d = parts[0]->d;
+  g->d_pad = parts[0]->d_pad;
+  g->external = true;  // owns nothing: the parts stay alive with their owners
+  g->parts.assign(parts, parts + n_parts);
+  *out = g;
+  return TVC_OK;
+}
+
+static void fill_row_source(RowSource* rs, const tvc_gallery* g) {
+  memset(rs, 0, sizeof(*rs));
+  rs->d_pad = g->d_pad;
+  if (g->parts.empty()) {
+    rs->nparts = 1;
+    rs->f32[0] = g->f32;
+    rs->bf16[0] = g->bf16;
+    rs->off[0] = g->offset;
+    rs->n[0] = g->n;
+    return;
+  }
+  rs->nparts = static_cast<int>(g->parts.size());
+  for (int i = 0; i < rs->nparts; ++i) {
+    rs->f32[i] = g->parts[i]->f32;
+    rs->bf16[i] = g->parts[i]->bf16;
+    rs->off[i] = g->parts[i]->offset;
+    rs->n[i] = g->parts[i]->n;
+  }
 }
 
 // ------------------------------------------------------------------------------- search
@@ -596,7 +669,7 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
   if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad handle");
   if (m < 0 || (m > 0 && (!queries || !out_sim || !out_idx)) || q_dtype < 0 || q_dtype > TVC_F16)
     return fail(ctx, TVC_ERR_INVALID, "tvc_search: bad argument");
-  if (g->external) return fail(ctx, TVC_ERR_INVALID, "tvc_search: wrapped row views are not searchable");
+  if (g->external) return fail(ctx, TVC_ERR_INVALID, "tvc_search: row views / groups are not searchable");
   if (d != g->d) return fail(ctx, TVC_ERR_INVALID, "tvc_search: query dimension != gallery dimension");
   if (k < 1) return fail(ctx, TVC_ERR_INVALID, "tvc_search: k < 1");
   if (k > TVC_MAX_K) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search: k > TVC_MAX_K");
@@ -803,21 +876,13 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
   if (V == 0) a.var = nullptr;
   if (G == 0) a.gen = nullptr;
   if (ret_gallery && ret_idx && R > 0 && n_ret_cand > 0) {
-    a.ret_rows = ret_gallery->f32;
-    a.ret_rows_bf16 = ret_gallery->bf16;
-    a.ret_dpad = ret_gallery->d_pad;
-    a.ret_n = ret_gallery->n;
-    a.ret_offset = ret_gallery->offset;
+    fill_row_source(&a.ret, ret_gallery);
     a.n_ret_cand = n_ret_cand;
   } else {
     a.ret_idx = nullptr;
   }
   if (!a.gen && gen_gallery && gen_idx && G > 0 && n_gen_cand > 0) {
-    a.gen_rows = gen_gallery->f32;
-    a.gen_rows_bf16 = gen_gallery->bf16;
-    a.gen_dpad = gen_gallery->d_pad;
-    a.gen_n = gen_gallery->n;
-    a.gen_offset = gen_gallery->offset;
+    fill_row_source(&a.genr, gen_gallery);
     a.n_gen_cand = n_gen_cand;
   } else {
     a.gen_idx = nullptr;

@@ -635,19 +635,21 @@ __device__ __forceinline__ void load_row_to_smem(float* dst, const float* g_f32,
 // Greedy reference selection (experiments/defenses/detector.py:184-204, 302-325): walk the
 // candidate list in order, drop repeated indices and rows whose cosine to an already kept row
 // exceeds dedup_threshold, stop at `cap` kept rows; sims[j] = cos(image, kept row j).
-__device__ int select_refs(const float* s_img, float* s_rows, int d, const float* g_f32,
-                           const __nv_bfloat16* g_bf16, int d_pad, long long g_n, long long g_off,
+__device__ int select_refs(const float* s_img, float* s_rows, int d, const RowSource& src,
                            const long long* cand, int ncand, int cap, float dedup_thr, float* sims,
                            long long* kept_idx) {
   int kept = 0;
   for (int c = 0; c < ncand && kept < cap; ++c) {
-    const long long gi = cand[c] - g_off;
-    if (gi < 0 || gi >= g_n) continue;
+    const long long gi = cand[c];
+    int part = -1;
+    for (int p = 0; p < src.nparts; ++p)
+      if (gi >= src.off[p] && gi < src.off[p] + src.n[p]) part = p;
+    if (part < 0) continue;  // unused slot (-1) or an index no shard owns
     bool dup = false;
     for (int j = 0; j < kept; ++j) dup |= (kept_idx[j] == gi);
     if (dup) continue;
     float* row = s_rows + static_cast<size_t>(kept) * d;
-    load_row_to_smem(row, g_f32, g_bf16, d, d_pad, gi);
+    load_row_to_smem(row, src.f32[part], src.bf16[part], d, src.d_pad, gi - src.off[part]);
     if (dedup_thr > -1.0f) {
       for (int j = 0; j < kept && !dup; ++j) {
         const CosAcc a = warp_cos_acc(s_rows + static_cast<size_t>(j) * d, row, d);
@@ -712,10 +714,9 @@ __global__ void consistency_emb_kernel(const tvc_detector_params p, long long nq
         ++nx;
       }
     int nr = 0;
-    if (a.ret_idx && (a.ret_rows || a.ret_rows_bf16))
-      nr = select_refs(s_img, s_rows, d, a.ret_rows, a.ret_rows_bf16, a.ret_dpad, a.ret_n,
-                       a.ret_offset, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand, a.n_ret_cand, min(R, rows_cap),
-                       p.dedup_threshold, l_sr, l_kept);
+    if (a.ret_idx && a.ret.nparts > 0)
+      nr = select_refs(s_img, s_rows, d, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
+                       a.n_ret_cand, min(R, rows_cap), p.dedup_threshold, l_sr, l_kept);
     int ng = 0;
     if (a.gen) {
       ng = a.g_cnt ? max(0, min(G, a.g_cnt[q])) : G;
@@ -723,10 +724,9 @@ __global__ void consistency_emb_kernel(const tvc_detector_params p, long long nq
         const CosAcc c = warp_cos_acc(s_img, a.gen + (q * G + g) * d, d);
         if (lane == 0) l_sg[g] = cos_from(c);
       }
-    } else if (a.gen_idx && (a.gen_rows || a.gen_rows_bf16)) {
-      ng = select_refs(s_img, s_rows, d, a.gen_rows, a.gen_rows_bf16, a.gen_dpad, a.gen_n,
-                       a.gen_offset, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand, a.n_gen_cand, min(G, rows_cap),
-                       p.dedup_threshold, l_sg, l_kept);
+    } else if (a.gen_idx && a.genr.nparts > 0) {
+      ng = select_refs(s_img, s_rows, d, a.genr, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand,
+                       a.n_gen_cand, min(G, rows_cap), p.dedup_threshold, l_sg, l_kept);
     }
     __syncwarp();
     if (lane == 0) {

@@ -71,24 +71,28 @@ cudaError_t launch_gather_rows(const float* g_f32, const __nv_bfloat16* g_bf16, 
                                const int64_t* idx, int64_t n, int64_t n_rows, float* out,
                                cudaStream_t stream);
 
+// Where the rows behind global indices live: up to kMaxParts row shards, each resident in this GPU's
+// HBM or in a PEER GPU's HBM mapped through CUDA IPC (read over NVLink by the kernel itself).
+constexpr int kMaxParts = 16;
+struct RowSource {
+  int nparts;
+  int d_pad;
+  const float* f32[kMaxParts];            // fp32 master of shard p (or null)
+  const __nv_bfloat16* bf16[kMaxParts];   // bf16 rows of shard p (used when there is no master)
+  long long off[kMaxParts];               // global index of the shard's first row
+  long long n[kMaxParts];                 // rows in the shard
+};
+
 struct ConsistencyEmbArgs {
   const float* img;
   const float* txt;
   const float* var;
-  const float* ret_rows;  // fp32 master of the retrieval gallery (or null)
-  const __nv_bfloat16* ret_rows_bf16;
-  int ret_dpad;
-  int64_t ret_n;
-  int64_t ret_offset;
+  RowSource ret;          // retrieval gallery shards
   const int64_t* ret_idx;
   int n_ret_cand;
   const float* gen;  // direct generative embeddings [Q,G,d] (or null)
   const int32_t* g_cnt;
-  const float* gen_rows;
-  const __nv_bfloat16* gen_rows_bf16;
-  int gen_dpad;
-  int64_t gen_n;
-  int64_t gen_offset;
+  RowSource genr;         // generative (bank) shards
   const int64_t* gen_idx;
   int n_gen_cand;
   float* out_sv;

@@ -57,6 +57,16 @@ class CudaEngine:
     def k_occurrence(self, idx, n_bins, counts):
         return self.ctx.k_occurrence(idx, n_bins, 0, counts)
 
+    def peer_group(self, gallery, total_rows, dist, group, world, rank):
+        """[own shard + CUDA-IPC views of every peer's fp32 master]: kernel (b) then reads rows of other
+        shards straight from peer HBM over NVLink instead of staging them with collectives."""
+        info = [None] * world
+        dist.all_gather_object(info, (gallery.export_ipc(), len(gallery), gallery.global_row_offset), group=group)
+        parts = []
+        for r, (handle, n, off) in enumerate(info):
+            parts.append(gallery if r == rank else N.Gallery.import_ipc(handle, n, gallery.dim, off, self.ctx))
+        return N.Gallery.group(parts)
+
 
 def shard_bounds(n: int, world: int, rank: int):
     """Contiguous row shard of rank `rank`: rows [lo, hi) with ceil(n / world) rows per rank."""
@@ -106,6 +116,16 @@ class TVCScorer:
             if self.b_hi - self.b_lo != b_local:
                 raise ValueError(f"rank {self.rank}: bank shard has {b_local} rows, expected {self.b_hi - self.b_lo}")
             self.bank = engine.make_gallery(bank_rows, self.b_lo)
+        # multi-rank: rows referenced by kernel (b) live on other shards.  With the CUDA engine they are
+        # read in place through CUDA IPC peer mappings; engines without peer memory (the CPU test
+        # engine) stage them with index + row all-to-alls (_fetch_rows).
+        self._gallery_group = self._bank_group = None
+        if self.world > 1 and hasattr(engine, "peer_group"):
+            self._gallery_group = engine.peer_group(self.gallery, self.n_total, self.dist, self.group, self.world,
+                                                    self.rank)
+            if self.bank is not None:
+                self._bank_group = engine.peer_group(self.bank, self.b_total, self.dist, self.group, self.world,
+                                                     self.rank)
         self.track_hubness = track_hubness
         self.k_occurrence = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
         self._host: Dict[str, torch.Tensor] = {}
@@ -221,7 +241,9 @@ class TVCScorer:
         ret_idx = g_idx.view(qs, v * k)
         gen_idx = b_idx.view(qs, v * k) if (b_idx is not None and gen is None) else None
         ret_gal, gen_gal = self.gallery, self.bank
-        if self.world > 1:
+        if self._gallery_group is not None:
+            ret_gal, gen_gal = self._gallery_group, self._bank_group
+        elif self.world > 1:
             # (ranks with an empty query slice still take part: the collectives must stay matched)
             ret_gal, ret_idx = self._fetch_rows(self.gallery, self.n_total, ret_idx)
             if gen_idx is not None:

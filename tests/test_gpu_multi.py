@@ -1,0 +1,78 @@
+"""Two-GPU run of the sharded TVCScorer (NCCL candidate all-to-all, merge kernel, kernel (b) reading
+peer shards over CUDA IPC / NVLink, histogram all-reduce) against the single-GPU result.
+Skipped on boxes with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _data():
+    sys.path.insert(0, str(ROOT))
+    from oracle import tvc_oracle as O
+    g = O.synth_gallery(20000, 256, seed=3, clusters=128, dup_rate=1e-3)
+    bank = O.synth_gallery(3000, 256, seed=4, clusters=128)
+    img, txt, var = O.synth_queries(g, 1500, 5, seed=5)
+    return g, bank, img, txt, var
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    sys.path.insert(0, str(ROOT))
+    from multimodal_detection_consistency_b200.pipeline import TVCScorer, shard_bounds
+    g, bank, img, txt, var = _data()
+    glo, ghi = shard_bounds(len(g), world, rank)
+    blo, bhi = shard_bounds(len(bank), world, rank)
+    sc = TVCScorer(g[glo:ghi], bank[blo:bhi], k=10, total_gallery_rows=len(g), total_bank_rows=len(bank),
+                   device=f"cuda:{rank}")
+    assert sc._gallery_group is not None          # the peer-memory path, not the staged fetch
+    out = sc.score_batch(img, txt, var, to_host=True)
+    lo, hi = out["slice"]
+    torch.cuda.synchronize()
+    np.savez(Path(out_dir) / f"r{rank}.npz", lo=lo, hi=hi, scores=out["scores"].numpy(), flags=out["flags"].numpy(),
+             topk_idx=out["topk_idx"].numpy(), topk_sim=out["topk_sim"].numpy(), bank_idx=out["bank_idx"].numpy(),
+             hub=sc.k_occurrence.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_equals_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    from multimodal_detection_consistency_b200.pipeline import TVCScorer
+    g, bank, img, txt, var = _data()
+    ref = TVCScorer(g, bank, k=10, device="cuda:0")
+    want = ref.score_batch(img, txt, var, to_host=True)
+    want = {k: (v.numpy().copy() if hasattr(v, "numpy") else v) for k, v in want.items()}
+    hub = ref.k_occurrence.cpu().numpy()
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    covered = 0
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        lo, hi = int(z["lo"]), int(z["hi"])
+        covered += hi - lo
+        assert np.array_equal(z["topk_idx"], want["topk_idx"][lo:hi])
+        assert np.array_equal(z["bank_idx"], want["bank_idx"][lo:hi])
+        assert np.abs(z["topk_sim"] - want["topk_sim"][lo:hi]).max() <= 1e-6
+        assert np.abs(z["scores"] - want["scores"][lo:hi]).max() <= 1e-5
+        assert np.array_equal(z["flags"], want["flags"][lo:hi])
+        assert np.array_equal(z["hub"], hub)
+    assert covered == len(img)

@@ -349,11 +349,10 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
   p.m_tiles = static_cast<int>((m + tile_m - 1) / tile_m);
   p.n_tiles = static_cast<int>((n + kBN - 1) / kBN);
   p.kp = k <= 10 ? 16 : (k <= 26 ? 32 : 64);
-  // Pick the number of gallery ranges: minimise waves * (tiles per range + warm-up).  Every unit
-  // restarts its per-row lists, and until ~1024*KP columns have streamed by nearly every 32x32 chunk
-  // holds a hit for some lane of the warp, which makes the epilogue (not the MMA) the pacing role:
-  // measured, a unit costs about 2.5*KP extra tile-times (106-tile units ran 25 % slower than
-  // 3907-tile units).  Long units win unless M is too small to fill the machine.
+  // Pick the number of gallery ranges S: minimise waves * (unit time) where a unit costs its tiles plus
+  // ~4 tile-times of fixed work (pipeline fill/drain, candidate store, its share of the re-rank) plus a
+  // quarter tile for each of the first 2*KP tiles, during which nearly every 32x32 chunk takes the
+  // epilogue's slow path.  (In quarter-tile units; ties go to fewer ranges.)
   const int max_s = p.n_tiles < 1024 ? p.n_tiles : 1024;
   long long best_cost = -1;
   int best_s = 1, best_tps = p.n_tiles;
@@ -363,8 +362,8 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
     if (s_eff != s) continue;
     const long long units = static_cast<long long>(p.m_tiles) * s_eff;
     const long long waves = (units + workers - 1) / workers;
-    const long long warmup = (5 * p.kp) / 2;
-    const long long cost = waves * (tps + (tps < warmup ? tps : warmup));
+    const long long warm = tps < 2 * p.kp ? tps : 2 * p.kp;
+    const long long cost = waves * (4ll * tps + 16 + warm) * 64 + s_eff;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best_s = s_eff;

@@ -221,13 +221,25 @@ class TVCScorer:
         the SAME full batch and receives the results of its own contiguous slice of the queries.
         Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim."""
         self._mark("begin")
-        var = self._dev(var)
         q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
         if v != self.params.n_variants:
             raise ValueError(f"{v} variants given, params.n_variants = {self.params.n_variants}")
         lo, hi = slice_bounds(q_total, self.world, self.rank)
         qs = hi - lo
         k = self.k
+        host_var = not (isinstance(var, torch.Tensor) and var.device.type == self.device.type == "cuda")
+        if self.world > 1 and host_var and self.device.type == "cuda":
+            # every rank holds the same host batch: upload only this rank's slice over PCIe and
+            # all-gather the rest over NVLink (1/world of the host->device traffic per GPU)
+            per = -(-q_total // self.world)
+            piece = torch.zeros((per, v, d), dtype=torch.float32, device=self.device)
+            if qs > 0:
+                piece[:qs].copy_(torch.as_tensor(var[lo:hi]), non_blocking=True)
+            full = torch.empty((self.world * per, v, d), dtype=torch.float32, device=self.device)
+            self.dist.all_gather_into_tensor(full, piece, group=self.group)
+            var = full[:q_total]
+        else:
+            var = self._dev(var)
         rows_all = var.view(q_total * v, d)
         g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
         self._mark("search_gallery")
@@ -235,9 +247,9 @@ class TVCScorer:
         if self.bank is not None:
             b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
             self._mark("search_bank")
-        img_s, txt_s, var_s = self._dev(img)[lo:hi], self._dev(txt)[lo:hi], var[lo:hi]
-        gen_s = self._dev(gen)[lo:hi] if gen is not None else None
-        gcnt_s = self._dev(g_cnt, torch.int32)[lo:hi] if g_cnt is not None else None
+        img_s, txt_s, var_s = self._dev(img[lo:hi]), self._dev(txt[lo:hi]), var[lo:hi]
+        gen_s = self._dev(gen[lo:hi]) if gen is not None else None
+        gcnt_s = self._dev(g_cnt[lo:hi], torch.int32) if g_cnt is not None else None
         ret_idx = g_idx.view(qs, v * k)
         gen_idx = b_idx.view(qs, v * k) if (b_idx is not None and gen is None) else None
         ret_gal, gen_gal = self.gallery, self.bank

@@ -325,9 +325,20 @@ def main():
     # gallery and the bank launch of a step; achieved = those FLOPs / the launches' CUDA-event time.
     shard_flops = 2.0 * args.queries * args.variants * ((ghi - glo) + (bhi - blo)) * args.dim
     achieved = shard_flops * args.steps / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
+    traffic = None
+    try:  # DRAM bytes of the dominant launch from the committed ncu --set full capture, same workload only
+        tj = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())
+        w = tj["workload"]
+        if (w["queries"], w["variants"], w["gallery"], w["bank"], w["dim"], w["n_gpus"]) == \
+                (args.queries, args.variants, args.gallery, args.bank, args.dim, world):
+            traffic = tj["traffic_bytes"]
+    except Exception:
+        pass
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
-                    frac=(achieved / peaks["bf16_sustained"]) if achieved else None, traffic=None,
-                    kernel="gemm_topk_kernel<16> (tcgen05 GEMM + top-k epilogue)",
+                    frac=(achieved / peaks["bf16_sustained"]) if achieved else None, traffic=traffic,
+                    traffic_note="DRAM bytes of the gallery launch (ncu, profiles/roofline_traffic.json); algorithmic "
+                                 "bytes 1.69e9 - each of the 13 waves of query tiles re-streams its gallery range",
+                    kernel="gemm_topk_pair_kernel<16> (tcgen05 cta_group::2 GEMM + in-register top-k epilogue)",
                     kernel_ms_per_step=k_ms / args.steps, kernel_launches=k_n,
                     kernel_share_of_step=k_ms / total_ms, peak_source=f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                     frac_of_burst_peak=(achieved / peaks["bf16"]) if achieved else None)

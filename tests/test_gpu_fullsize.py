@@ -65,7 +65,7 @@ def test_c3_hubness_coco_train_scale(tvc_ctx):
     gen = torch.Generator(device="cuda").manual_seed(7)
     g = torch.nn.functional.normalize(torch.randn(n, d, device="cuda", generator=gen), dim=1)
     hub = torch.nn.functional.normalize(torch.randn(d, device="cuda", generator=gen), dim=0)
-    q = torch.nn.functional.normalize(torch.randn(m, d, device="cuda", generator=gen) + 2.0 * hub, dim=1)
+    q = torch.nn.functional.normalize(torch.randn(m, d, device="cuda", generator=gen) / d ** 0.5 + 0.6 * hub, dim=1)
     g[777] = hub                                       # an adversarial hub: near every query
     gal = tvc.Gallery(g, ctx=tvc_ctx)
     sims, idx = gal.search(q, k)
@@ -121,9 +121,11 @@ def test_1m_gallery_properties(tvc_ctx):
     torch.cuda.synchronize()
     assert torch.equal(mi, idx) and torch.equal(ms, sims)
     # sampled rows against a plain torch fp32 reference (full row of similarities)
-    sel = torch.randperm(m, device="cuda", generator=gen)[:256]
+    sel = torch.randperm(m, device="cuda", generator=gen)
+    sel = sel[sel % 10 != 0][:256]          # planted rows tie exactly; torch.topk's tie order is unspecified
     ref = torch.topk(q[sel] @ g.T, k, dim=1)
     same = ref.indices == idx[sel]
     assert float(same.float().mean()) > 0.995
     assert float((ref.values - sims[sel]).abs().max()) <= 1e-3
-    assert float((ref.values - sims[sel]).abs()[~same].max(initial=0) if (~same).any() else 0.0) <= 1e-3
+    diff = (ref.values - sims[sel]).abs()
+    assert (not bool((~same).any())) or float(diff[~same].max()) <= 1e-3

@@ -915,10 +915,12 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
   const bool idx_dev = m == 0 || is_device_ptr(idx), cnt_dev = is_device_ptr(counts);
   const size_t ib = up256(static_cast<size_t>(m) * k * 8), cb = up256(static_cast<size_t>(n_bins) * 4);
   uint8_t* ws = nullptr;
-  if (!idx_dev || !cnt_dev) {
-    int rc = get_ws(ctx, st, ib + cb, &ws);
+  {
+    int rc = get_ws(ctx, st, 256 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
     if (rc != TVC_OK) return rc;
   }
+  int* flag_scratch = reinterpret_cast<int*>(ws);
+  ws += 256;
   const int64_t* d_idx = idx;
   if (!idx_dev) {
     TVC_CUDA(ctx, cudaMemcpyAsync(ws, idx, static_cast<size_t>(m) * k * 8, cudaMemcpyHostToDevice, st));
@@ -931,7 +933,7 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
       TVC_CUDA(ctx, cudaMemcpyAsync(d_cnt, counts, static_cast<size_t>(n_bins) * 4, cudaMemcpyHostToDevice, st));
   }
   if (zero_first) TVC_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, static_cast<size_t>(n_bins) * 4, st));
-  TVC_CUDA(ctx, launch_k_occurrence(d_idx, m, k, idx_base, n_bins, d_cnt, ctx->sm_count, st));
+  TVC_CUDA(ctx, launch_k_occurrence(d_idx, m, k, idx_base, n_bins, d_cnt, ctx->sm_count, flag_scratch, st));
   if (!cnt_dev)
     TVC_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, static_cast<size_t>(n_bins) * 4, cudaMemcpyDeviceToHost, st));
   if (!idx_dev || !cnt_dev) TVC_CUDA(ctx, cudaStreamSynchronize(st));

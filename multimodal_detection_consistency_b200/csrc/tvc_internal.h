@@ -65,7 +65,8 @@ cudaError_t launch_merge_topk(const float* in_sim, const int64_t* in_idx, int64_
                               float* out_sim, int64_t* out_idx, cudaStream_t stream);
 
 cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t idx_base,
-                                int64_t n_bins, int32_t* counts, int sm_count, cudaStream_t stream);
+                                int64_t n_bins, int32_t* counts, int sm_count, int* flag_scratch,
+                                cudaStream_t stream);
 
 cudaError_t launch_gather_rows(const float* g_f32, const __nv_bfloat16* g_bf16, int d, int d_pad,
                                const int64_t* idx, int64_t n, int64_t n_rows, float* out,

@@ -32,6 +32,7 @@ struct tvc_ctx {
   std::map<cudaStream_t, Ws> ws;
   int64_t debug_flags = 0;
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
+  int64_t emb_generic = 0;       // 1: kernel (b) embedding mode always takes the one-warp-per-query kernel
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
@@ -319,6 +320,10 @@ int64_t tvc_ctx_launch_count(tvc_ctx* ctx) { return ctx ? launches_so_far() - ct
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return TVC_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (strcmp(name, "emb_generic") == 0) {
+    ctx->emb_generic = value;
+    return TVC_OK;
+  }
   if (strcmp(name, "pair_min_rows") == 0) {
     ctx->pair_min_rows = value;
     return TVC_OK;
@@ -893,7 +898,7 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
   a.out_sv = sg_.out_buf(out_sv, Q * V, &s2_);
   a.out_sr = sg_.out_buf(out_sr, Q * R, &s3_);
   a.out_sg = sg_.out_buf(out_sg, Q * G, &s4_);
-  TVC_CUDA(ctx, launch_consistency_emb(*p, q, d, a, d_scores, d_flags, st));
+  TVC_CUDA(ctx, launch_consistency_emb(*p, q, d, a, d_scores, d_flags, ctx->sm_count, ctx->emb_generic != 0, st));
   if (s0_) TVC_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, Q * TVC_NSCORES * 4, cudaMemcpyDeviceToHost, st));
   if (s1_) TVC_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, Q, cudaMemcpyDeviceToHost, st));
   if (s2_) TVC_CUDA(ctx, cudaMemcpyAsync(out_sv, a.out_sv, Q * V * 4, cudaMemcpyDeviceToHost, st));
@@ -916,11 +921,11 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
   const size_t ib = up256(static_cast<size_t>(m) * k * 8), cb = up256(static_cast<size_t>(n_bins) * 4);
   uint8_t* ws = nullptr;
   {
-    int rc = get_ws(ctx, st, 256 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
+    int rc = get_ws(ctx, st, 4096 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
     if (rc != TVC_OK) return rc;
   }
   int* flag_scratch = reinterpret_cast<int*>(ws);
-  ws += 256;
+  ws += 4096;
   const int64_t* d_idx = idx;
   if (!idx_dev) {
     TVC_CUDA(ctx, cudaMemcpyAsync(ws, idx, static_cast<size_t>(m) * k * 8, cudaMemcpyHostToDevice, st));

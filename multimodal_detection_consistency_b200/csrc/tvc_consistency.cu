@@ -1,0 +1,1064 @@
+// Kernel (b): the variant-consistency reduction.  Per query it turns similarities (or the embedding
+// rows themselves) into the statistics and decisions of the reference's three scoring stacks:
+//   AdversarialDetector            src/detector.py:441-590, 643-682, 399
+//   MultiModalDefenseDetector      experiments/defenses/detector.py:228-325
+//   ConsistencyChecker             experiments/defenses/consistency_checker.py:119-272
+//   README sigma rule              README.md:474-482, 846
+// Statistics are fp64 on fp32 similarities like the reference's Python floats -> np.mean/np.std.
+//
+// Both modes are HBM-bound by design:
+//   * similarity-fed  - a block stages the contiguous similarity slabs of its queries through shared
+//     memory with 128-bit loads, one thread reduces one query, results leave as coalesced stores;
+//   * embedding-fed   - a persistent, warp-specialised CTA per SM: one producer warp walks the
+//     candidate lists and pulls the ~20 rows a query needs (image, text, V variants, the first R
+//     distinct retrieval candidates, G generative rows) from HBM - or a PEER GPU's HBM over NVLink -
+//     into a 3-stage shared-memory ring with cp.async.bulk (TMA) completing on mbarriers; eight
+//     consumer warps split the query's ~75 dot products into register-blocked tasks (one A row against
+//     up to 5 B rows) on the resident rows; a rotating finisher warp runs the greedy de-duplication on
+//     the resulting cosine matrix, the fp64 statistics and the stores while the others move on.
+#include <math.h>
+
+#include "tvc_internal.h"
+#include "tvc_ptx.cuh"
+
+namespace tvc {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------- fp64 statistics
+// Division of a double by a small positive integer with a tabulated correctly rounded reciprocal and
+// two FMA-residual refinements (Markstein): the result is the correctly rounded quotient, i.e. what
+// IEEE division (np.mean / np.var) returns, for a fraction of the cost of the DP division sequence.
+constexpr int kRcpN = 128;   // covers every count: V, R, G <= 16, V(V-1)/2 <= 120, R+G <= 32
+
+__device__ __forceinline__ void fill_rcp_table(double* rcp, int tid, int nthreads) {
+  for (int i = tid; i < kRcpN; i += nthreads) rcp[i] = i > 0 ? 1.0 / static_cast<double>(i) : 0.0;
+}
+__device__ __forceinline__ double div_n(double s, int n, const double* rcp) {
+  const double r = rcp[n], dn = static_cast<double>(n);
+  double q = s * r;
+  q = fma(fma(-q, dn, s), r, q);
+  q = fma(fma(-q, dn, s), r, q);
+  return q;
+}
+
+struct Stats {
+  double sum, mean, ss, var, sd;   // ss = sum of squared deviations, var = ss / n (ddof = 0)
+  float mn, mx;
+};
+
+// x[0..n): MAXN <= 16 keeps the converted values in registers between the two passes
+template <int MAXN>
+__device__ __forceinline__ Stats stats_of(const float* x, int n, const double* rcp, bool want_sd) {
+  Stats s{0., 0., 0., 0., 0., 0.f, 0.f};
+  if (n <= 0) return s;
+  float mn = x[0], mx = x[0];
+  double sum = 0., ss = 0.;
+  if constexpr (MAXN <= 16) {
+    double v[MAXN];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+      v[i] = 0.;
+      if (i < n) {
+        const float f = x[i];
+        mn = fminf(mn, f);
+        mx = fmaxf(mx, f);
+        v[i] = static_cast<double>(f);
+        sum += v[i];
+      }
+    }
+    s.mean = div_n(sum, n, rcp);
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i)
+      if (i < n) {
+        const double dlt = v[i] - s.mean;
+        ss = fma(dlt, dlt, ss);
+      }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const float f = x[i];
+      mn = fminf(mn, f);
+      mx = fmaxf(mx, f);
+      sum += static_cast<double>(f);
+    }
+    s.mean = div_n(sum, n, rcp);
+    for (int i = 0; i < n; ++i) {
+      const double dlt = static_cast<double>(x[i]) - s.mean;
+      ss = fma(dlt, dlt, ss);
+    }
+  }
+  s.sum = sum;
+  s.ss = ss;
+  s.var = div_n(ss, n, rcp);
+  s.sd = want_sd ? sqrt(s.var) : 0.;
+  s.mn = mn;
+  s.mx = mx;
+  return s;
+}
+
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// sv/sr/sg/sx point at this query's similarity lists (shared memory).  VM/RM/GM bound the counts.
+template <int VM, int RM, int GM>
+__device__ __forceinline__ void finish_scores(const tvc_detector_params& p, const double* rcp, float s0f,
+                                              const float* sv, int nv, const float* sr, int nr,
+                                              const float* sg, int ng, const float* sx, int nx,
+                                              float* out, int out_stride, uint8_t* flag) {
+  const double s0 = s0f;
+  const Stats tv = stats_of<VM>(sv, nv, rcp, true);
+  const Stats rt = stats_of<RM>(sr, nr, rcp, true);
+  const Stats gn = stats_of<GM>(sg, ng, rcp, true);
+  const Stats xv = stats_of<VM*(VM - 1) / 2>(sx, nx, rcp, false);
+
+  // --- AdversarialDetector (src/detector.py:441-590, 643-682, 399)
+  double det_tv = 0.0;
+  if (nv > 0) {
+    const double consistency = 1.0 - fabs(s0 - tv.mean);
+    const double variability = 1.0 - tv.sd;
+    det_tv = 1.0 - (consistency * 0.7 + variability * 0.3);
+  }
+  const double det_sd = ng > 0 ? 1.0 - gn.mean : 0.0;
+  const double det_c = 1.0 - s0;
+  double agg = 0.0;
+  {
+    const double sc[3] = {det_tv, det_sd, det_c};
+    const double wt[3] = {p.w_text_variants, p.w_sd_reference, p.w_consistency};
+    double wsum = 0., tw = 0., sum = 0., mx = -INFINITY, mn = INFINITY;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (!(p.methods & (1u << i))) continue;
+      wsum += sc[i] * wt[i];
+      tw += wt[i];
+      sum += sc[i];
+      mx = sc[i] > mx ? sc[i] : mx;
+      mn = sc[i] < mn ? sc[i] : mn;
+      ++cnt;
+    }
+    if (cnt > 0) {
+      if (p.aggregation == 0)
+        agg = tw > 0. ? wsum / tw : 0.0;
+      else if (p.aggregation == 2)
+        agg = mx;
+      else if (p.aggregation == 3)
+        agg = mn;
+      else
+        agg = div_n(sum, cnt, rcp);
+    }
+  }
+  const bool det_adv = agg > static_cast<double>(p.detection_threshold);
+
+  // --- MultiModalDefenseDetector scores (experiments/defenses/detector.py:228-300)
+  const double tv_c = nv > 0 ? tv.mean : s0;
+  const double tv_s = nv > 0 ? tv.sd : 0.0;
+  const double rt_c = nr > 0 ? rt.mean : 0.0, rt_s = nr > 0 ? rt.sd : 0.0;
+  const double gn_c = ng > 0 ? gn.mean : 0.0, gn_s = ng > 0 ? gn.sd : 0.0;
+  const double four[4] = {s0, tv_c, rt_c, gn_c};
+  int nvalid = 0;
+  double vsum = 0.;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (four[i] > 0.) {
+      vsum += four[i];
+      ++nvalid;
+    }
+  double vmean = 0., vvar = 0.;
+  if (nvalid > 0) {
+    vmean = div_n(vsum, nvalid, rcp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (four[i] > 0.) vvar = fma(four[i] - vmean, four[i] - vmean, vvar);
+    vvar = div_n(vvar, nvalid, rcp);
+  }
+  const double cmv = nvalid < 2 ? 0.0 : vvar;
+
+  // --- ConsistencyChecker (experiments/defenses/consistency_checker.py:119-272)
+  double overall = 0.0;
+  if (p.voting == 0) {
+    overall = nvalid > 0 ? vmean : 0.0;
+  } else {
+    double w[4];
+    if (p.voting == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = p.cc_weights[i];
+    } else {
+      w[0] = 1.0;
+      w[1] = 1.0 / (1.0 + tv_s);
+      w[2] = 1.0 / (1.0 + rt_s);
+      w[3] = 1.0 / (1.0 + gn_s);
+      const double t = w[0] + w[1] + w[2] + w[3];
+      if (t > 0.) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] /= t;
+      }
+    }
+    double ws = 0., tw = 0.;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (four[i] > 0.) {
+        ws += four[i] * w[i];
+        tw += w[i];
+      }
+    overall = tw == 0. ? 0.0 : ws / tw;
+  }
+  double thr = p.cc_base_threshold;
+  if (p.cc_adaptive) {
+    if (cmv > 0.1) thr += 0.1;
+    const double avg_std = div_n(tv_s + rt_s + gn_s, 3, rcp);
+    if (avg_std > 0.2) thr += 0.05;
+    thr = clipd(thr, 0.1, 0.9);
+  }
+  const bool cc_adv = overall < thr;
+  const double dist_conf = fabs(overall - thr) / thr;
+  const double cons_conf = nvalid > 1 ? 1.0 - sqrt(vvar) : 0.5;
+  const double var_conf = 1.0 - (cmv < 1.0 ? cmv : 1.0);
+  const double conf = clipd(div_n(dist_conf + cons_conf + var_conf, 3, rcp), 0.0, 1.0);
+
+  // --- README sigma rule over all references (README.md:474-482, 846): population std of the
+  // retrieval and generative similarities together, from the two groups' moments
+  double sigma = 0.0;
+  {
+    const int n = nr + ng;
+    if (n > 0) {
+      const double mu = div_n(rt.sum + gn.sum, n, rcp);
+      double acc = rt.ss + gn.ss;
+      acc = fma(static_cast<double>(nr) * (rt.mean - mu), rt.mean - mu, acc);
+      acc = fma(static_cast<double>(ng) * (gn.mean - mu), gn.mean - mu, acc);
+      sigma = sqrt(div_n(acc, n, rcp));
+    }
+  }
+  const bool sig_adv = sigma > static_cast<double>(p.sigma_threshold);
+
+  auto put = [&](int col, double v) { out[col * out_stride] = static_cast<float>(v); };
+  out[TVC_S_ORIGINAL * out_stride] = s0f;
+  put(TVC_S_TV_MEAN, tv_c);
+  put(TVC_S_TV_STD, tv_s);
+  out[TVC_S_TV_MIN * out_stride] = nv > 0 ? tv.mn : s0f;
+  put(TVC_S_TV_VAR, nv > 0 ? tv.var : 0.0);
+  put(TVC_S_RET_MEAN, rt_c);
+  put(TVC_S_RET_STD, rt_s);
+  put(TVC_S_GEN_MEAN, gn_c);
+  put(TVC_S_GEN_STD, gn_s);
+  out[TVC_S_GEN_MAX * out_stride] = ng > 0 ? gn.mx : 0.f;
+  put(TVC_S_CROSS_MODAL_VAR, cmv);
+  put(TVC_S_XV_MEAN, xv.mean);
+  out[TVC_S_XV_MIN * out_stride] = xv.mn;
+  put(TVC_S_XV_VAR, xv.var);
+  put(TVC_S_DET_TV, det_tv);
+  put(TVC_S_DET_SD, det_sd);
+  put(TVC_S_DET_C, det_c);
+  put(TVC_S_DET_AGG, agg);
+  put(TVC_S_CC_OVERALL, overall);
+  put(TVC_S_CC_THRESHOLD, thr);
+  put(TVC_S_CC_CONFIDENCE, conf);
+  out[TVC_S_N_RET * out_stride] = static_cast<float>(nr);
+  out[TVC_S_N_GEN * out_stride] = static_cast<float>(ng);
+  put(TVC_S_REF_SIGMA, sigma);
+  *flag = static_cast<uint8_t>((det_adv ? TVC_FLAG_DET_ADV : 0u) | (cc_adv ? TVC_FLAG_CC_ADV : 0u) |
+                               (sig_adv ? TVC_FLAG_SIGMA_ADV : 0u));
+}
+
+// runtime dispatch on the configured widths: the common (V<=5, R<=10, G<=4) build keeps every list in
+// registers; the wide build serves anything up to TVC_MAX_*
+__device__ __forceinline__ void finish_scores_any(const tvc_detector_params& p, const double* rcp, float s0,
+                                                  const float* sv, int nv, const float* sr, int nr,
+                                                  const float* sg, int ng, const float* sx, int nx,
+                                                  float* out, int out_stride, uint8_t* flag) {
+  if (p.n_variants <= 5 && p.n_retrieval <= 10 && p.n_generative <= 4)
+    finish_scores<5, 10, 4>(p, rcp, s0, sv, nv, sr, nr, sg, ng, sx, nx, out, out_stride, flag);
+  else
+    finish_scores<TVC_MAX_VARIANTS, TVC_MAX_REFS, TVC_MAX_REFS>(p, rcp, s0, sv, nv, sr, nr, sg, ng, sx, nx, out,
+                                                                 out_stride, flag);
+}
+
+// ------------------------------------------------------------------------------- similarity-fed
+constexpr int kSimsBlock = 128;
+constexpr int kOutStride = kSimsBlock + 1;   // column-major result tile, conflict-free both ways
+
+__device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__ src, long long q0,
+                                           int nq, int width) {
+  if (src == nullptr || width == 0) return;
+  const long long base = q0 * width;
+  const int total = nq * width;
+  const float* s = src + base;
+  if (((reinterpret_cast<uintptr_t>(s) & 15u) == 0)) {
+    const int n4 = total >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      reinterpret_cast<float4*>(dst)[i] = __ldcs(reinterpret_cast<const float4*>(s) + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < total; i += blockDim.x) dst[i] = s[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = s[i];
+  }
+}
+
+__global__ void __launch_bounds__(kSimsBlock)
+consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const float* __restrict__ s0,
+                        const float* __restrict__ sv, const float* __restrict__ sr,
+                        const int32_t* __restrict__ r_cnt, const float* __restrict__ sg,
+                        const int32_t* __restrict__ g_cnt, const float* __restrict__ sxv,
+                        float* __restrict__ scores, uint8_t* __restrict__ flags) {
+  extern __shared__ __align__(16) float s_buf[];
+  __shared__ double s_rcp[kRcpN];
+  const int V = p.n_variants, R = p.n_retrieval, G = p.n_generative;
+  const int X = sxv ? V * (V - 1) / 2 : 0;
+  const int pad4 = 4;  // keep every slab 16-byte aligned
+  auto up4 = [](int x) { return (x + 3) & ~3; };
+  float* b_sv = s_buf;
+  float* b_sr = b_sv + up4(kSimsBlock * V) + pad4;
+  float* b_sg = b_sr + up4(kSimsBlock * R) + pad4;
+  float* b_sx = b_sg + up4(kSimsBlock * G) + pad4;
+  float* b_out = b_sx + up4(kSimsBlock * X) + pad4;
+  fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
+  const long long q0 = static_cast<long long>(blockIdx.x) * kSimsBlock;
+  const int nq = static_cast<int>(min(static_cast<long long>(kSimsBlock), nq_total - q0));
+  stage_slab(b_sv, sv, q0, nq, V);
+  stage_slab(b_sr, sr, q0, nq, R);
+  stage_slab(b_sg, sg, q0, nq, G);
+  stage_slab(b_sx, sxv, q0, nq, X);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < nq) {
+    const long long q = q0 + t;
+    const int nr = sr ? (r_cnt ? max(0, min(R, r_cnt[q])) : R) : 0;
+    const int ng = sg ? (g_cnt ? max(0, min(G, g_cnt[q])) : G) : 0;
+    const int nv = sv ? V : 0;
+    uint8_t flag = 0;
+    finish_scores_any(p, s_rcp, s0[q], b_sv + t * V, nv, b_sr + t * R, nr, b_sg + t * G, ng, b_sx + t * X, X,
+                      b_out + t, kOutStride, &flag);
+    flags[q] = flag;
+  }
+  __syncthreads();
+  float* dst = scores + q0 * TVC_NSCORES;
+  const int total = nq * TVC_NSCORES;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int qq = i / TVC_NSCORES, col = i - qq * TVC_NSCORES;
+    __stcs(dst + i, b_out[col * kOutStride + qq]);
+  }
+}
+
+// ------------------------------------------------------------------------------- embedding-fed
+// torch.cosine_similarity: x.y / max(|x||y|, eps), eps = 1e-8
+__device__ __forceinline__ float cos_of(float dot, float na, float nb) {
+  return dot / fmaxf(sqrtf(na) * sqrtf(nb), 1e-8f);
+}
+
+struct CosAcc {
+  float dot, na, nb;
+};
+// one warp, rows anywhere (generic loads); used by the generic kernel and by the finisher's slow path
+__device__ __forceinline__ CosAcc warp_cos_acc(const float* __restrict__ a, const float* __restrict__ b, int d) {
+  const int lane = threadIdx.x & 31;
+  float dot = 0.f, na = 0.f, nb = 0.f;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int i = lane; i < (d >> 2); i += 32) {
+      const float4 x = a4[i], y = b4[i];
+      dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot);
+      dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
+      na = fmaf(x.x, x.x, na); na = fmaf(x.y, x.y, na);
+      na = fmaf(x.z, x.z, na); na = fmaf(x.w, x.w, na);
+      nb = fmaf(y.x, y.x, nb); nb = fmaf(y.y, y.y, nb);
+      nb = fmaf(y.z, y.z, nb); nb = fmaf(y.w, y.w, nb);
+    }
+  } else {
+    for (int i = lane; i < d; i += 32) {
+      const float x = a[i], y = b[i];
+      dot = fmaf(x, y, dot);
+      na = fmaf(x, x, na);
+      nb = fmaf(y, y, nb);
+    }
+  }
+  CosAcc r;
+  r.dot = warp_sum(dot);
+  r.na = warp_sum(na);
+  r.nb = warp_sum(nb);
+  return r;
+}
+__device__ __forceinline__ float cos_from(const CosAcc& c) { return cos_of(c.dot, c.na, c.nb); }
+
+__device__ __forceinline__ int find_part(const RowSource& src, long long gi) {
+  int part = -1;
+  for (int p = 0; p < src.nparts; ++p)
+    if (gi >= src.off[p] && gi < src.off[p] + src.n[p]) part = p;
+  return part;
+}
+
+__device__ __forceinline__ void load_row_to_smem(float* dst, const float* g_f32, const __nv_bfloat16* g_bf16,
+                                                 int d, int d_pad, long long gi) {
+  const int lane = threadIdx.x & 31;
+  if (g_f32) {
+    const float* src = g_f32 + gi * d;
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      for (int i = lane; i < (d >> 2); i += 32)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    } else {
+      for (int i = lane; i < d; i += 32) dst[i] = src[i];
+    }
+  } else {
+    const __nv_bfloat16* src = g_bf16 + gi * d_pad;
+    for (int i = lane; i < d; i += 32) dst[i] = __bfloat162float(src[i]);
+  }
+  __syncwarp();
+}
+
+// ---- generic kernel (any d / alignment, bf16-only galleries): one warp per query -----------------
+// Greedy reference selection (experiments/defenses/detector.py:184-204, 302-325): walk the
+// candidate list in order, drop repeated indices and rows whose cosine to an already kept row
+// exceeds dedup_threshold, stop at `cap` kept rows; sims[j] = cos(image, kept row j).
+__device__ int select_refs(const float* s_img, float* s_rows, int d, const RowSource& src,
+                           const long long* cand, int ncand, int cap, float dedup_thr, float* sims,
+                           long long* kept_idx) {
+  int kept = 0;
+  for (int c = 0; c < ncand && kept < cap; ++c) {
+    const long long gi = cand[c];
+    const int part = find_part(src, gi);
+    if (part < 0) continue;  // unused slot (-1) or an index no shard owns
+    bool dup = false;
+    for (int j = 0; j < kept; ++j) dup |= (kept_idx[j] == gi);
+    if (dup) continue;
+    float* row = s_rows + static_cast<size_t>(kept) * d;
+    load_row_to_smem(row, src.f32[part], src.bf16[part], d, src.d_pad, gi - src.off[part]);
+    if (dedup_thr > -1.0f) {
+      for (int j = 0; j < kept && !dup; ++j) {
+        const CosAcc a = warp_cos_acc(s_rows + static_cast<size_t>(j) * d, row, d);
+        dup = cos_from(a) > dedup_thr;
+      }
+      if (dup) continue;
+    }
+    const CosAcc a = warp_cos_acc(s_img, row, d);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      sims[kept] = cos_from(a);
+      kept_idx[kept] = gi;
+    }
+    __syncwarp();
+    ++kept;
+  }
+  return kept;
+}
+
+constexpr int kXMax = TVC_MAX_VARIANTS * (TVC_MAX_VARIANTS - 1) / 2;
+constexpr int kListFloats = TVC_MAX_VARIANTS + 2 * TVC_MAX_REFS + kXMax + TVC_NSCORES;
+
+__global__ void consistency_emb_generic_kernel(const tvc_detector_params p, long long nq, int d,
+                                               const ConsistencyEmbArgs a, float* __restrict__ scores,
+                                               uint8_t* __restrict__ flags, int rows_cap) {
+  extern __shared__ __align__(16) float s_dyn[];
+  __shared__ double s_rcp[kRcpN];
+  fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  // per warp: image row + rows_cap kept rows, then small lists
+  const size_t row_floats = (static_cast<size_t>(1 + rows_cap) * d + 3) & ~static_cast<size_t>(3);
+  float* s_img = s_dyn + static_cast<size_t>(w) * row_floats;
+  float* s_rows = s_img + d;
+  float* s_lists = s_dyn + static_cast<size_t>(warps) * row_floats;
+  float* l_sv = s_lists + static_cast<size_t>(w) * (kListFloats + 2 * TVC_MAX_REFS);
+  float* l_sr = l_sv + TVC_MAX_VARIANTS;
+  float* l_sg = l_sr + TVC_MAX_REFS;
+  float* l_sx = l_sg + TVC_MAX_REFS;
+  float* l_out = l_sx + kXMax;
+  long long* l_kept = reinterpret_cast<long long*>(l_out + TVC_NSCORES);  // TVC_MAX_REFS entries
+
+  const int V = p.n_variants, R = p.n_retrieval, G = p.n_generative;
+  for (long long q = static_cast<long long>(blockIdx.x) * warps + w; q < nq;
+       q += static_cast<long long>(gridDim.x) * warps) {
+    load_row_to_smem(s_img, a.img, nullptr, d, d, q);
+    float s0 = 0.f;
+    {
+      const CosAcc c = warp_cos_acc(s_img, a.txt + q * d, d);
+      s0 = cos_from(c);
+    }
+    const float* var_q = a.var ? a.var + q * V * d : nullptr;
+    const int nv = var_q ? V : 0;
+    for (int v = 0; v < nv; ++v) {
+      const CosAcc c = warp_cos_acc(s_img, var_q + static_cast<size_t>(v) * d, d);
+      if (lane == 0) l_sv[v] = cos_from(c);
+    }
+    int nx = 0;
+    for (int i = 0; i < nv; ++i)
+      for (int j = i + 1; j < nv; ++j) {
+        const CosAcc c = warp_cos_acc(var_q + static_cast<size_t>(i) * d,
+                                      var_q + static_cast<size_t>(j) * d, d);
+        if (lane == 0) l_sx[nx] = cos_from(c);
+        ++nx;
+      }
+    int nr = 0;
+    if (a.ret_idx && a.ret.nparts > 0)
+      nr = select_refs(s_img, s_rows, d, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
+                       a.n_ret_cand, min(R, rows_cap), p.dedup_threshold, l_sr, l_kept);
+    int ng = 0;
+    if (a.gen) {
+      ng = a.g_cnt ? max(0, min(G, a.g_cnt[q])) : G;
+      for (int g = 0; g < ng; ++g) {
+        const CosAcc c = warp_cos_acc(s_img, a.gen + (q * G + g) * d, d);
+        if (lane == 0) l_sg[g] = cos_from(c);
+      }
+    } else if (a.gen_idx && a.genr.nparts > 0) {
+      ng = select_refs(s_img, s_rows, d, a.genr, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand,
+                       a.n_gen_cand, min(G, rows_cap), p.dedup_threshold, l_sg, l_kept);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint8_t flag;
+      finish_scores_any(p, s_rcp, s0, l_sv, nv, l_sr, nr, l_sg, ng, l_sx, nx, l_out, 1, &flag);
+      flags[q] = flag;
+    }
+    __syncwarp();
+    if (lane < TVC_NSCORES) scores[q * TVC_NSCORES + lane] = l_out[lane];
+    if (a.out_sv && lane < V) a.out_sv[q * V + lane] = lane < nv ? l_sv[lane] : 0.f;
+    if (a.out_sr && lane < R) a.out_sr[q * R + lane] = lane < nr ? l_sr[lane] : 0.f;
+    if (a.out_sg && lane < G) a.out_sg[q * G + lane] = lane < ng ? l_sg[lane] : 0.f;
+    __syncwarp();
+  }
+}
+
+// ---- pipelined kernel -----------------------------------------------------------------------------
+constexpr int kEmbConsumers = 8;                        // consumer warps
+constexpr int kEmbThreads = (kEmbConsumers + 1) * 32;   // + one producer warp
+constexpr int kEmbMaxStages = 4;
+constexpr int kJB = 5;                                  // B rows per task (register block)
+constexpr int kMaxTasks = 224;
+constexpr int kMaxStageRows = 2 + TVC_MAX_VARIANTS + 2 * TVC_MAX_REFS;   // 50
+
+// global -> shared bulk copy (TMA, no tensor map), completion bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One task = dots of row A against rows B0 .. B0+nb-1 of the stage (+ squared norms for the image
+// group).  Groups: 0 = image/text/variants (always resident), 1 = retrieval rows, 2 = generative rows.
+struct EmbTask {
+  short a_row, b_row0;      // stage row numbers
+  unsigned char nb, norms;  // B rows, 1 = also write |A|^2 and |B|^2
+  unsigned char ga, gb;     // validity groups of A and of the B rows
+  short ia, ib0;            // index of A / first B inside its group
+  short out;                // result offset of (A, B0); consecutive B -> consecutive floats
+  short pad;
+};
+
+// per-stage control block and results (shared memory)
+struct EmbStage {
+  long long q;
+  long long pf_idx[2][TVC_MAX_REFS];   // global indices of the prefetched rows (0 retrieval, 1 generative)
+  int pf_n[2];                         // rows prefetched
+  int pf_end[2];                       // candidate position after the last prefetched one
+  int n_gen_direct;                    // valid direct generative rows (g_cnt)
+  int task_ctr;
+  // results: squared norms and image dots per stage row, pair dots per group
+  float nrm2[kMaxStageRows];
+  float d_img[kMaxStageRows];
+  float d_var[TVC_MAX_VARIANTS * TVC_MAX_VARIANTS];
+  float d_ref[2][TVC_MAX_REFS * TVC_MAX_REFS];
+};
+
+// finisher scratch (per consumer warp)
+struct EmbLists {
+  float sv[TVC_MAX_VARIANTS];
+  float sr[TVC_MAX_REFS];
+  float sg[TVC_MAX_REFS];
+  float sx[kXMax];
+  float out[TVC_NSCORES];
+  long long kept_idx[TVC_MAX_REFS];
+  int kept_slot[TVC_MAX_REFS];
+  int info[4];   // kept, need_slow
+};
+
+// Sums N per-lane values over the warp with N-1 + log2(32/N) shuffles instead of 5 N: at every level
+// half of the values go to the partner lane, which is the same addition tree as the xor butterfly
+// (bit-identical results).  Returns the total of value number bitrev-ish index `multi_index<N>(lane)`.
+template <int N>
+__device__ __forceinline__ float warp_sum_multi(float (&v)[N], int lane) {
+  static_assert(N == 8 || N == 16, "N");
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[2 * i] : v[2 * i + 1];
+      const float keep = upper ? v[2 * i + 1] : v[2 * i];
+      v[i] = keep + __shfl_xor_sync(kFull, send, off);
+    }
+  }
+  float r = v[0];
+  for (; off > 0; off >>= 1) r += __shfl_xor_sync(kFull, r, off);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ int multi_index(int lane) {
+  if (N == 16) return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2) | (((lane >> 1) & 1) << 3);
+  return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2);
+}
+
+template <bool NORMS>
+__device__ __forceinline__ void run_task(const EmbTask& t, int nb, const float* rows, int d, EmbStage* st,
+                                         float* out) {
+  const int lane = threadIdx.x & 31;
+  const float4* A = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.a_row) * d);
+  const float4* B = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.b_row0) * d);
+  const int d4 = d >> 2;
+  constexpr int NV = NORMS ? 16 : 8;     // dot[0..4] | nbn[0..4] at 5..9, |A|^2 at 10
+  float v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = 0.f;
+  for (int c = lane; c < d4; c += 32) {
+    const float4 x = A[c];
+    if (NORMS) {
+      v[10] = fmaf(x.x, x.x, v[10]); v[10] = fmaf(x.y, x.y, v[10]);
+      v[10] = fmaf(x.z, x.z, v[10]); v[10] = fmaf(x.w, x.w, v[10]);
+    }
+#pragma unroll
+    for (int j = 0; j < kJB; ++j)
+      if (j < nb) {
+        const float4 y = B[static_cast<size_t>(j) * d4 + c];
+        v[j] = fmaf(x.x, y.x, v[j]); v[j] = fmaf(x.y, y.y, v[j]);
+        v[j] = fmaf(x.z, y.z, v[j]); v[j] = fmaf(x.w, y.w, v[j]);
+        if (NORMS) {
+          v[5 + j] = fmaf(y.x, y.x, v[5 + j]); v[5 + j] = fmaf(y.y, y.y, v[5 + j]);
+          v[5 + j] = fmaf(y.z, y.z, v[5 + j]); v[5 + j] = fmaf(y.w, y.w, v[5 + j]);
+        }
+      }
+  }
+  const float r = warp_sum_multi<NV>(v, lane);
+  const int idx = multi_index<NV>(lane);
+  if ((lane & (NORMS ? 1 : 3)) == 0) {   // one lane per value
+    if (idx < kJB) {
+      if (idx < nb) out[t.out + idx] = r;
+    } else if (NORMS) {
+      if (idx < 2 * kJB) {
+        if (idx - kJB < nb) st->nrm2[t.b_row0 + idx - kJB] = r;
+      } else if (idx == 10) {
+        st->nrm2[t.a_row] = r;
+      }
+    }
+  }
+}
+
+// Greedy selection over the prefetched rows using the pair dots of the stage (one lane per row, the
+// order-dependent part resolved with shuffles); falls back to walking the rest of the candidate list
+// with synchronous loads when de-duplication dropped a row.  Returns the number kept; sims[j] =
+// cos(image, kept j).  Warp-cooperative (all 32 lanes call it).
+__device__ int select_from_stage(const tvc_detector_params& p, EmbStage* st, int grp, float* rows, int d,
+                                 int row_base /* stage row of the group's slot 0 */, const RowSource& src,
+                                 const long long* cand, int ncand, int cap, float* sims, EmbLists* L) {
+  const int lane = threadIdx.x & 31;
+  const float thr = p.dedup_threshold;
+  const int pf_n = st->pf_n[grp];
+  const float* pd = st->d_ref[grp];
+  // lane s owns prefetched row s: its cosine to the image and the set of earlier rows it duplicates
+  unsigned dup_of = 0;
+  float sim = 0.f;
+  if (lane < pf_n) {
+    const float ns = sqrtf(st->nrm2[row_base + lane]);
+    sim = st->d_img[row_base + lane] / fmaxf(sqrtf(st->nrm2[0]) * ns, 1e-8f);
+    if (thr > -1.0f)
+      for (int j = 0; j < lane; ++j) {
+        const float c = pd[j * TVC_MAX_REFS + lane] / fmaxf(sqrtf(st->nrm2[row_base + j]) * ns, 1e-8f);
+        if (c > thr) dup_of |= 1u << j;
+      }
+  }
+  // greedy resolution in list order (every lane computes the same kept set)
+  unsigned kept_mask = 0;
+  int kept = 0;
+  for (int s = 0; s < pf_n; ++s) {
+    const unsigned m = __shfl_sync(kFull, dup_of, s);
+    if (kept < cap && (m & kept_mask) == 0) {
+      kept_mask |= 1u << s;
+      ++kept;
+    }
+  }
+  if (lane < pf_n && ((kept_mask >> lane) & 1u)) {
+    const int pos = __popc(kept_mask & ((1u << lane) - 1u));
+    sims[pos] = sim;
+    L->kept_slot[pos] = lane;
+    L->kept_idx[pos] = st->pf_idx[grp][lane];
+  }
+  __syncwarp();
+  if (!(kept < cap && kept < pf_n && st->pf_end[grp] < ncand)) return kept;
+  // slow path: a prefetched row was dropped, so later candidates may still qualify
+  const float* s_img = rows;
+  for (int c = st->pf_end[grp]; c < ncand && kept < cap; ++c) {
+    const long long gi = cand[c];
+    const int part = find_part(src, gi);
+    if (part < 0) continue;
+    bool dup = false;
+    for (int j = 0; j < kept; ++j) dup |= (L->kept_idx[j] == gi);
+    if (dup) continue;
+    // a free slot: lowest slot not used by a kept row (kept < cap <= slots)
+    unsigned used = 0;
+    for (int j = 0; j < kept; ++j) used |= 1u << L->kept_slot[j];
+    const int slot = __ffs(~used) - 1;
+    float* row = rows + static_cast<size_t>(row_base + slot) * d;
+    load_row_to_smem(row, src.f32[part], src.bf16[part], d, src.d_pad, gi - src.off[part]);
+    if (thr > -1.0f) {
+      for (int j = 0; j < kept && !dup; ++j) {
+        const CosAcc a = warp_cos_acc(rows + static_cast<size_t>(row_base + L->kept_slot[j]) * d, row, d);
+        dup = cos_from(a) > thr;
+      }
+      if (dup) continue;
+    }
+    const CosAcc a = warp_cos_acc(s_img, row, d);
+    __syncwarp();
+    if (lane == 0) {
+      sims[kept] = cos_from(a);
+      L->kept_idx[kept] = gi;
+      L->kept_slot[kept] = slot;
+    }
+    __syncwarp();
+    ++kept;
+  }
+  return kept;
+}
+
+// producer side: take the first `cap` distinct valid indices of a candidate list, start their copies
+__device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const RowSource& src,
+                                                   const long long* cand, int ncand, int cap, float* rows_grp,
+                                                   int d, uint64_t* bar) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t row_bytes = static_cast<uint32_t>(d) * 4u;
+  int n = 0, end = 0;
+  for (int c0 = 0; c0 < ncand && n < cap; c0 += 32) {
+    const int c = c0 + lane;
+    long long gi = -1;
+    int part = -1;
+    if (c < ncand) {
+      gi = cand[c];
+      part = find_part(src, gi);
+    }
+    bool take = part >= 0;
+    if (take)
+      for (int j = 0; j < n; ++j) take &= (st->pf_idx[grp][j] != gi);
+    const unsigned vmask = __ballot_sync(kFull, take);
+    if (take) {
+      const unsigned same = __match_any_sync(vmask, static_cast<unsigned long long>(gi));
+      take = (__ffs(same) - 1) == lane;   // first occurrence inside this chunk
+    }
+    const unsigned keep = __ballot_sync(kFull, take);
+    const int slot = n + __popc(keep & ((1u << lane) - 1u));
+    if (take && slot < cap) {
+      st->pf_idx[grp][slot] = gi;
+      bulk_g2s(rows_grp + static_cast<size_t>(slot) * d, src.f32[part] + (gi - src.off[part]) * d, row_bytes, bar);
+    }
+    const int taken = min(cap - n, __popc(keep));
+    if (taken > 0) {
+      // candidate position after the last one taken in this chunk
+      unsigned k2 = keep;
+      for (int i = 1; i < taken; ++i) k2 &= k2 - 1;   // drop the lowest taken-1 bits
+      end = c0 + __ffs(k2);
+    }
+    n += taken;
+    __syncwarp();
+  }
+  if (n < cap) end = ncand;   // list exhausted
+  if (lane == 0) {
+    st->pf_n[grp] = n;
+    st->pf_end[grp] = end;
+  }
+  return static_cast<uint32_t>(n) * row_bytes;
+}
+
+__global__ void __launch_bounds__(kEmbThreads, 1)
+consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, const ConsistencyEmbArgs a,
+                            float* __restrict__ scores, uint8_t* __restrict__ flags, int n_stages,
+                            int stage_rows) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) uint64_t s_full[kEmbMaxStages], s_done[kEmbMaxStages], s_empty[kEmbMaxStages];
+  __shared__ double s_rcp[kRcpN];
+  __shared__ EmbTask s_tasks[kMaxTasks];
+  __shared__ int s_ntasks;
+  __shared__ EmbStage s_stage[kEmbMaxStages];
+  __shared__ EmbLists s_lists[kEmbConsumers];
+  float* s_rows = reinterpret_cast<float*>(s_raw);
+  const size_t stage_floats = static_cast<size_t>(stage_rows) * d;
+
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int V = a.var ? p.n_variants : 0;
+  const bool has_ret = a.ret_idx != nullptr && a.ret.nparts > 0;
+  const bool gen_direct = a.gen != nullptr;
+  const bool gen_idx = !gen_direct && a.gen_idx != nullptr && a.genr.nparts > 0;
+  const int R = has_ret ? p.n_retrieval : 0;
+  const int G = (gen_direct || gen_idx) ? p.n_generative : 0;
+  const int row_var = 2, row_ret = 2 + V, row_gen = 2 + V + R;
+
+  fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_done[s], kEmbConsumers);
+      mbar_init(&s_empty[s], 1);
+    }
+    fence_mbar_init();
+    // task table (the same for every query): image group, variant pairs, reference pairs
+    int nt = 0;
+    auto add = [&](int a_row, int b_row0, int nb, int norms, int ga, int gb, int ia, int ib0, int out) {
+      EmbTask t;
+      t.a_row = static_cast<short>(a_row); t.b_row0 = static_cast<short>(b_row0);
+      t.nb = static_cast<unsigned char>(nb); t.norms = static_cast<unsigned char>(norms);
+      t.ga = static_cast<unsigned char>(ga); t.gb = static_cast<unsigned char>(gb);
+      t.ia = static_cast<short>(ia); t.ib0 = static_cast<short>(ib0);
+      t.out = static_cast<short>(out); t.pad = 0;
+      s_tasks[nt++] = t;
+    };
+    // image (row 0) against every other row; d_img[row]
+    for (int b = 1; b < 2 + V; b += kJB) add(0, b, min(kJB, 2 + V - b), 1, 0, 0, 0, b, b);
+    for (int b = 0; b < R; b += kJB) add(0, row_ret + b, min(kJB, R - b), 1, 0, 1, 0, b, row_ret + b);
+    for (int b = 0; b < G; b += kJB)
+      add(0, row_gen + b, min(kJB, G - b), 1, 0, gen_direct ? 3 : 2, 0, b, row_gen + b);
+    for (int i = 0; i < V; ++i)
+      for (int b = i + 1; b < V; b += kJB)
+        add(row_var + i, row_var + b, min(kJB, V - b), 0, 0, 0, i, b, i * TVC_MAX_VARIANTS + b);
+    if (p.dedup_threshold > -1.0f) {
+      for (int i = 0; i < R; ++i)
+        for (int b = i + 1; b < R; b += kJB)
+          add(row_ret + i, row_ret + b, min(kJB, R - b), 0, 1, 1, i, b, i * TVC_MAX_REFS + b);
+      if (gen_idx)
+        for (int i = 0; i < G; ++i)
+          for (int b = i + 1; b < G; b += kJB)
+            add(row_gen + i, row_gen + b, min(kJB, G - b), 0, 2, 2, i, b, i * TVC_MAX_REFS + b);
+    }
+    s_ntasks = nt;
+  }
+  __syncthreads();
+  const int ntasks = s_ntasks;
+  const long long my_n = nq > blockIdx.x ? (nq - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (w == kEmbConsumers) {
+    // ===== producer warp
+    const uint32_t row_bytes = static_cast<uint32_t>(d) * 4u;
+    for (long long i = 0; i < my_n; ++i) {
+      const int s = static_cast<int>(i % n_stages);
+      const uint32_t round = static_cast<uint32_t>(i / n_stages);
+      if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1u);
+      const long long q = blockIdx.x + i * static_cast<long long>(gridDim.x);
+      EmbStage* st = &s_stage[s];
+      float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
+      uint64_t* bar = &s_full[s];
+      // rows addressed directly by q: image, text, variants, direct generative rows
+      const int ndirect = 2 + V + (gen_direct ? G : 0);
+      if (lane < ndirect) {
+        const float* srcp;
+        int row;
+        if (lane == 0) { srcp = a.img + q * d; row = 0; }
+        else if (lane == 1) { srcp = a.txt + q * d; row = 1; }
+        else if (lane < 2 + V) { srcp = a.var + (q * V + (lane - 2)) * d; row = lane; }
+        else { srcp = a.gen + (q * G + (lane - 2 - V)) * d; row = row_gen + (lane - 2 - V); }
+        bulk_g2s(rows + static_cast<size_t>(row) * d, srcp, row_bytes, bar);
+      }
+      if (ndirect > 32)   // V = G = 16: the last rows
+        for (int r = 32 + lane; r < ndirect; r += 32)
+          bulk_g2s(rows + static_cast<size_t>(row_gen + (r - 2 - V)) * d, a.gen + (q * G + (r - 2 - V)) * d, row_bytes, bar);
+      uint32_t bytes = static_cast<uint32_t>(ndirect) * row_bytes;
+      if (has_ret)
+        bytes += prefetch_group(st, 0, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
+                                a.n_ret_cand, R, rows + static_cast<size_t>(row_ret) * d, d, bar);
+      if (gen_idx)
+        bytes += prefetch_group(st, 1, a.genr, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand,
+                                a.n_gen_cand, G, rows + static_cast<size_t>(row_gen) * d, d, bar);
+      if (lane == 0) {
+        st->q = q;
+        if (!has_ret) { st->pf_n[0] = 0; st->pf_end[0] = 0; }
+        if (!gen_idx) { st->pf_n[1] = 0; st->pf_end[1] = 0; }
+        st->n_gen_direct = gen_direct ? (a.g_cnt ? max(0, min(G, a.g_cnt[q])) : G) : 0;
+        st->task_ctr = 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+    }
+    return;
+  }
+
+  // ===== consumer warps
+  EmbLists* L = &s_lists[w];
+  bool skip_next = false;
+  for (long long i = 0; i < my_n; ++i) {
+    const int s = static_cast<int>(i % n_stages);
+    const uint32_t par = static_cast<uint32_t>(i / n_stages) & 1u;
+    EmbStage* st = &s_stage[s];
+    float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
+    if (skip_next) {   // finished the previous query: already checked in for this one
+      skip_next = false;
+      continue;
+    }
+    mbar_wait(&s_full[s], par);
+    const int valid1 = st->pf_n[0], valid2 = st->pf_n[1], valid3 = st->n_gen_direct;
+    while (true) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&st->task_ctr, 1);
+      t = __shfl_sync(kFull, t, 0);
+      if (t >= ntasks) break;
+      const EmbTask tk = s_tasks[t];
+      const int va = tk.ga == 0 ? 1 << 20 : (tk.ga == 1 ? valid1 : valid2);
+      const int vb = tk.gb == 0 ? 1 << 20 : (tk.gb == 1 ? valid1 : (tk.gb == 2 ? valid2 : valid3));
+      const int nb = min(static_cast<int>(tk.nb), vb - tk.ib0);
+      if (tk.ia >= va || nb <= 0) continue;
+      if (tk.norms)
+        run_task<true>(tk, nb, rows, d, st, st->d_img);
+      else
+        run_task<false>(tk, nb, rows, d, st, tk.ga == 0 ? st->d_var : st->d_ref[tk.ga - 1]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_done[s]);
+    if (static_cast<int>(i % kEmbConsumers) != w) continue;
+
+    // ===== finisher for this query
+    mbar_wait(&s_done[s], par);
+    // This warp is about to be busy: it sits out the next query's tasks and checks in on that
+    // query's done barrier now (legal: all eight arrivals of the barrier's previous phase happened
+    // before this query's did), so consecutive finishers overlap instead of waiting for each other.
+    if (i + 1 < my_n && lane == 0) mbar_arrive(&s_done[(i + 1) % n_stages]);
+    skip_next = true;
+    const long long q = st->q;
+    const float n_img = st->nrm2[0];
+    float s0 = cos_of(st->d_img[1], n_img, st->nrm2[1]);
+    if (lane < V) L->sv[lane] = cos_of(st->d_img[row_var + lane], n_img, st->nrm2[row_var + lane]);
+    int nx = 0;
+    for (int ii = 0; ii < V; ++ii) {
+      const int cnt = V - 1 - ii;   // pairs (ii, ii+1 .. V-1) are consecutive in sx
+      if (lane < cnt) {
+        const int jj = ii + 1 + lane;
+        L->sx[nx + lane] = cos_of(st->d_var[ii * TVC_MAX_VARIANTS + jj], st->nrm2[row_var + ii], st->nrm2[row_var + jj]);
+      }
+      nx += cnt;
+    }
+    __syncwarp();
+    int nr = 0;
+    if (has_ret)
+      nr = select_from_stage(p, st, 0, rows, d, row_ret, a.ret,
+                             reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand, a.n_ret_cand, R,
+                             L->sr, L);
+    int ng = 0;
+    if (gen_direct) {
+      ng = st->n_gen_direct;
+      if (lane < ng) L->sg[lane] = cos_of(st->d_img[row_gen + lane], n_img, st->nrm2[row_gen + lane]);
+    } else if (gen_idx) {
+      ng = select_from_stage(p, st, 1, rows, d, row_gen, a.genr,
+                             reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand, a.n_gen_cand, G,
+                             L->sg, L);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint8_t flag;
+      finish_scores_any(p, s_rcp, s0, L->sv, V, L->sr, nr, L->sg, ng, L->sx, nx, L->out, 1, &flag);
+      flags[q] = flag;
+    }
+    __syncwarp();
+    if (lane < TVC_NSCORES) scores[q * TVC_NSCORES + lane] = L->out[lane];
+    const int Vp = p.n_variants, Rp = p.n_retrieval, Gp = p.n_generative;
+    if (a.out_sv && lane < Vp) a.out_sv[q * Vp + lane] = lane < V ? L->sv[lane] : 0.f;
+    if (a.out_sr && lane < Rp) a.out_sr[q * Rp + lane] = lane < nr ? L->sr[lane] : 0.f;
+    if (a.out_sg && lane < Gp) a.out_sg[q * Gp + lane] = lane < ng ? L->sg[lane] : 0.f;
+    // the slow path may have written rows with ordinary stores; the next use of the stage is a bulk copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+}
+
+}  // namespace
+
+// =============================================================================== launchers
+cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, const float* s0,
+                                    const float* sv, const float* sr, const int32_t* r_cnt,
+                                    const float* sg, const int32_t* g_cnt, const float* sxv,
+                                    float* scores, uint8_t* flags, cudaStream_t stream) {
+  if (q <= 0) return cudaSuccess;
+  const int V = p.n_variants, R = p.n_retrieval, G = p.n_generative;
+  const int X = sxv ? V * (V - 1) / 2 : 0;
+  auto up4 = [](int x) { return (x + 3) & ~3; };
+  const size_t floats = up4(kSimsBlock * V) + up4(kSimsBlock * R) + up4(kSimsBlock * G) +
+                        up4(kSimsBlock * X) + 16 + kOutStride * TVC_NSCORES;
+  const size_t smem = floats * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(consistency_sims_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = static_cast<int>((q + kSimsBlock - 1) / kSimsBlock);
+  consistency_sims_kernel<<<grid, kSimsBlock, smem, stream>>>(p, q, s0, sv, sr, r_cnt, sg, g_cnt, sxv,
+                                                              scores, flags);
+  note_launch();
+  return cudaGetLastError();
+}
+
+static bool rows_f32_aligned(const RowSource& s) {
+  for (int i = 0; i < s.nparts; ++i)
+    if (s.f32[i] == nullptr || (reinterpret_cast<uintptr_t>(s.f32[i]) & 15u) != 0) return false;
+  return true;
+}
+
+cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int d,
+                                   const ConsistencyEmbArgs& a, float* scores, uint8_t* flags,
+                                   int sm_count, int force_generic, cudaStream_t stream) {
+  if (q <= 0) return cudaSuccess;
+  // ---- pipelined kernel: fp32 rows, 16-byte aligned, at least two stages of rows in shared memory
+  const int V = a.var ? p.n_variants : 0;
+  const bool has_ret = a.ret_idx != nullptr && a.ret.nparts > 0;
+  const bool gen_direct = a.gen != nullptr;
+  const bool gen_idx = !gen_direct && a.gen_idx != nullptr && a.genr.nparts > 0;
+  const int R = has_ret ? p.n_retrieval : 0;
+  const int G = (gen_direct || gen_idx) ? p.n_generative : 0;
+  const int stage_rows = 2 + V + R + G;
+  const size_t stage_bytes = static_cast<size_t>(stage_rows) * d * 4;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  bool pipe = !force_generic && (d % 4) == 0 && al16(a.img) && al16(a.txt) && (!a.var || al16(a.var)) &&
+              (!a.gen || al16(a.gen)) && (!has_ret || rows_f32_aligned(a.ret)) &&
+              (!gen_idx || rows_f32_aligned(a.genr));
+  const size_t smem_budget = 196 * 1024;   // dynamic; the static part (stages, tasks, lists) is ~28 KB
+  int n_stages = static_cast<int>(smem_budget / stage_bytes);
+  if (n_stages > kEmbMaxStages) n_stages = kEmbMaxStages;
+  if (n_stages < 2) pipe = false;
+  if (pipe) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(consistency_emb_pipe_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_budget));
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    long long blocks = q < sm_count ? q : sm_count;
+    consistency_emb_pipe_kernel<<<static_cast<int>(blocks), kEmbThreads, n_stages * stage_bytes, stream>>>(
+        p, q, d, a, scores, flags, n_stages, stage_rows);
+    note_launch();
+    return cudaGetLastError();
+  }
+  // ---- generic kernel
+  int rows_cap = p.n_retrieval > p.n_generative ? p.n_retrieval : p.n_generative;
+  if (rows_cap < 1) rows_cap = 1;
+  const size_t row_floats = (static_cast<size_t>(1 + rows_cap) * d + 3) & ~static_cast<size_t>(3);
+  const size_t per_warp = (row_floats + kListFloats + 2 * TVC_MAX_REFS) * 4;
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  if (per_warp * warps > 220 * 1024) return cudaErrorInvalidValue;
+  static bool configured_g = false;
+  if (!configured_g) {
+    cudaError_t e = cudaFuncSetAttribute(consistency_emb_generic_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    configured_g = true;
+  }
+  long long blocks = (q + warps - 1) / warps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  consistency_emb_generic_kernel<<<static_cast<int>(blocks), warps * 32, per_warp * warps, stream>>>(
+      p, q, d, a, scores, flags, rows_cap);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace tvc

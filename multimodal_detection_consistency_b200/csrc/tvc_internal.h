@@ -108,7 +108,7 @@ cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, con
 
 cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int d,
                                    const ConsistencyEmbArgs& a, float* scores, uint8_t* flags,
-                                   cudaStream_t stream);
+                                   int sm_count, int force_generic, cudaStream_t stream);
 
 // counts every kernel launch made by the library (reported through tvc_ctx_launch_count)
 void note_launch(int n = 1);

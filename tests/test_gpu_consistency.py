@@ -137,3 +137,72 @@ def test_checker_golden(tvc_ctx):
         assert np.abs(scores[:, O.S_CC_OVERALL] - want[:, 0]).max() <= 1e-5
         margin = np.abs(want[:, 0] - 0.5) > 1e-5
         assert np.array_equal((flags & O.FLAG_CC_ADV).astype(bool)[margin], want[margin, 3].astype(bool))
+
+
+def _emb_case(tvc_ctx, d, nq, V, R, G, k, n_gal, noise, dup_rate, seed, gen_mode, dedup=0.95, generic=False):
+    """Runs tvc_consistency_emb on a synthetic case and returns (got, want) triples."""
+    import multimodal_detection_consistency_b200 as tvc
+    g = O.synth_gallery(n_gal, d, seed=seed, clusters=32, noise=noise, dup_rate=dup_rate)
+    bank = O.synth_gallery(max(64, n_gal // 4), d, seed=seed + 1, clusters=32, noise=noise, dup_rate=dup_rate)
+    img, txt, var = O.synth_queries(g, nq, V, seed=seed + 2)
+    gal, bnk = tvc.Gallery(g, ctx=tvc_ctx), tvc.Gallery(bank, global_row_offset=1000, ctx=tvc_ctx)
+    _, ridx = gal.search(var, k)
+    ridx = ridx.reshape(nq, V * k)
+    rng = np.random.default_rng(seed)
+    ridx[rng.uniform(size=ridx.shape) < 0.05] = -1                  # unused slots inside the lists
+    over = dict(n_variants=V, n_retrieval=R, n_generative=G, dedup_threshold=dedup)
+    params = tvc.default_params(**over)
+    kw, okw = {}, {}
+    if gen_mode == "idx":
+        _, gidx = bnk.search(var, k)
+        gidx = gidx.reshape(nq, V * k)
+        kw = dict(gen_gallery=bnk, gen_idx=gidx)
+        okw = dict(gen_rows=bank, gen_idx=gidx, gen_offset=1000)
+    elif gen_mode == "direct":
+        gen = O.l2_normalize(rng.standard_normal((nq * G, d)).astype(np.float32)).reshape(nq, G, d)
+        g_cnt = rng.integers(0, G + 1, nq).astype(np.int32)
+        kw = dict(gen=gen, g_cnt=g_cnt)
+        okw = dict(gen=gen, g_cnt=g_cnt)
+    tvc_ctx.set_option("emb_generic", 1 if generic else 0)
+    try:
+        got = tvc_ctx.consistency_emb(params, img, txt, var if V else None, ret_gallery=gal, ret_idx=ridx,
+                                      return_sims=True, **kw)
+    finally:
+        tvc_ctx.set_option("emb_generic", 0)
+    want = O.consistency_emb(img, txt, var if V else None, ret_rows=g, ret_idx=ridx, params=over, **okw)
+    return got, want, over
+
+
+@pytest.mark.parametrize("d,nq,V,R,G,k,noise,dup,gen_mode", [
+    (768, 700, 5, 10, 3, 10, 0.35, 1e-4, "idx"),      # bench shape: no de-duplication hits
+    (768, 500, 5, 10, 3, 10, 0.10, 0.2, "idx"),       # tight clusters + 20 % exact duplicates: slow path
+    (512, 300, 5, 10, 3, 10, 0.05, 0.3, "direct"),    # nearly every candidate is a near-duplicate
+    (256, 260, 16, 16, 16, 3, 0.2, 0.05, "idx"),      # widest configuration
+    (256, 150, 16, 16, 16, 3, 0.2, 0.05, "direct"),
+    (64, 129, 3, 4, 2, 5, 0.3, 0.0, "none"),
+    (100, 77, 5, 10, 3, 10, 0.3, 0.01, "idx"),        # d % 4 == 0 but rows only 16-byte aligned every 4th
+    (101, 64, 5, 10, 3, 10, 0.3, 0.01, "idx"),        # odd d: generic kernel
+    (768, 3, 5, 10, 3, 10, 0.35, 0.0, "idx"),         # fewer queries than stages
+])
+def test_emb_mode_pipelined_kernel(tvc_ctx, d, nq, V, R, G, k, noise, dup, gen_mode):
+    (scores, flags, (sv, sr, sg)), (ref, rflags, (rsv, rsr, rsg)), over = _emb_case(
+        tvc_ctx, d, nq, V, R, G, k, 3000, noise, dup, 11, gen_mode)
+    assert np.array_equal(scores[:, O.S_N_RET], ref[:, O.S_N_RET])
+    assert np.array_equal(scores[:, O.S_N_GEN], ref[:, O.S_N_GEN])
+    assert np.abs(scores - ref).max() <= TIGHT
+    for i in range(nq):
+        assert np.abs(sr[i, :len(rsr[i])] - np.array(rsr[i], np.float32)).max(initial=0) <= TIGHT
+        assert np.abs(sg[i, :len(rsg[i])] - np.array(rsg[i], np.float32)).max(initial=0) <= TIGHT
+    _decisions_match(flags, rflags, ref, over)
+
+
+def test_emb_mode_pipelined_equals_generic(tvc_ctx):
+    """The two embedding-mode kernels sum in the same order: identical bits, including on the
+    de-duplication slow path and with de-duplication switched off."""
+    for dedup, dup in [(0.95, 0.2), (-2.0, 0.2), (0.95, 0.0)]:
+        a, _, _ = _emb_case(tvc_ctx, 768, 400, 5, 10, 3, 10, 3000, 0.1, dup, 5, "idx", dedup=dedup)
+        b, _, _ = _emb_case(tvc_ctx, 768, 400, 5, 10, 3, 10, 3000, 0.1, dup, 5, "idx", dedup=dedup, generic=True)
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1], b[1])
+        for x, y in zip(a[2], b[2]):
+            assert np.array_equal(x, y)

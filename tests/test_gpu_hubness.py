@@ -78,3 +78,19 @@ def test_merge_topk(tvc_ctx, m, parts, k):
     ref_s, ref_i = O.merge_topk(sims, idx, k)
     assert np.array_equal(got_i, ref_i)
     assert np.array_equal(got_s, ref_s)
+
+
+@pytest.mark.parametrize("m,k,n_bins,hub_share", [(30000, 10, 200000, 0.5), (30000, 10, 200000, 0.1),
+                                                  (200000, 10, 1000000, 0.02), (100000, 10, 1500, 0.3)])
+def test_k_occurrence_hot_bins(tvc_ctx, m, k, n_bins, hub_share):
+    """Hub-dominated streams (the hot-bin table) and streams that take the shared-memory histogram."""
+    rng = np.random.default_rng(m)
+    idx = rng.integers(0, n_bins, (m, k)).astype(np.int64)
+    hubs = rng.integers(0, n_bins, 40)
+    hot = rng.uniform(size=(m, k)) < hub_share
+    idx[hot] = hubs[(rng.uniform(size=int(hot.sum())) ** 3 * 40).astype(np.int64)]
+    import torch
+    t = torch.from_numpy(idx).cuda()
+    got = tvc_ctx.k_occurrence(t, n_bins)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), O.k_occurrence(idx, n_bins))

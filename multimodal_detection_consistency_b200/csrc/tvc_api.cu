@@ -32,6 +32,7 @@ struct tvc_ctx {
   std::map<cudaStream_t, Ws> ws;
   int64_t debug_flags = 0;
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
+  int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
   int64_t emb_generic = 0;       // 1: kernel (b) embedding mode always takes the one-warp-per-query kernel
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -320,6 +321,10 @@ int64_t tvc_ctx_launch_count(tvc_ctx* ctx) { return ctx ? launches_so_far() - ct
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return TVC_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (strcmp(name, "emb_trace_ptr") == 0) {
+    ctx->emb_trace_ptr = value;
+    return TVC_OK;
+  }
   if (strcmp(name, "emb_generic") == 0) {
     ctx->emb_generic = value;
     return TVC_OK;
@@ -867,11 +872,25 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
                        is_device_ptr(scores) && is_device_ptr(flags) &&
                        (!out_sv || is_device_ptr(out_sv)) && (!out_sr || is_device_ptr(out_sr)) &&
                        (!out_sg || is_device_ptr(out_sg));
+  // similarity lists handed from the gather/dot kernel to the statistics kernel
+  const size_t X = V * (V > 0 ? V - 1 : 0) / 2;
+  const size_t lists = 3 * up256(Q * 4) + up256(Q * V * 4) + up256(Q * R * 4) + up256(Q * G * 4) + up256(Q * X * 4);
+  const size_t stage_bytes = all_dev ? 4096 : need;
   uint8_t* ws;
-  rc = get_ws(ctx, st, all_dev ? 4096 : need, &ws);
+  rc = get_ws(ctx, st, stage_bytes + lists, &ws);
   if (rc != TVC_OK) return rc;
   Stager sg_{ctx, st, ws};
   ConsistencyEmbArgs a{};
+  {
+    uint8_t* w = ws + stage_bytes;
+    a.w_s0 = reinterpret_cast<float*>(w); w += up256(Q * 4);
+    a.w_rcnt = reinterpret_cast<int32_t*>(w); w += up256(Q * 4);
+    a.w_gcnt = reinterpret_cast<int32_t*>(w); w += up256(Q * 4);
+    a.w_sv = reinterpret_cast<float*>(w); w += up256(Q * V * 4);
+    a.w_sr = reinterpret_cast<float*>(w); w += up256(Q * R * 4);
+    a.w_sg = reinterpret_cast<float*>(w); w += up256(Q * G * 4);
+    a.w_sx = reinterpret_cast<float*>(w);
+  }
   if ((rc = sg_.in(img, Q * D, &a.img)) || (rc = sg_.in(txt, Q * D, &a.txt)) ||
       (rc = sg_.in(var, Q * V * D, &a.var)) ||
       (rc = sg_.in(ret_idx, Q * static_cast<size_t>(n_ret_cand), &a.ret_idx)) ||
@@ -898,6 +917,7 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
   a.out_sv = sg_.out_buf(out_sv, Q * V, &s2_);
   a.out_sr = sg_.out_buf(out_sr, Q * R, &s3_);
   a.out_sg = sg_.out_buf(out_sg, Q * G, &s4_);
+  a.trace = reinterpret_cast<unsigned long long*>(ctx->emb_trace_ptr);
   TVC_CUDA(ctx, launch_consistency_emb(*p, q, d, a, d_scores, d_flags, ctx->sm_count, ctx->emb_generic != 0, st));
   if (s0_) TVC_CUDA(ctx, cudaMemcpyAsync(scores, d_scores, Q * TVC_NSCORES * 4, cudaMemcpyDeviceToHost, st));
   if (s1_) TVC_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, Q, cudaMemcpyDeviceToHost, st));

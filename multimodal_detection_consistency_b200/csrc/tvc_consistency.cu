@@ -9,13 +9,17 @@
 // Both modes are HBM-bound by design:
 //   * similarity-fed  - a block stages the contiguous similarity slabs of its queries through shared
 //     memory with 128-bit loads, one thread reduces one query, results leave as coalesced stores;
-//   * embedding-fed   - a persistent, warp-specialised CTA per SM: one producer warp walks the
-//     candidate lists and pulls the ~20 rows a query needs (image, text, V variants, the first R
-//     distinct retrieval candidates, G generative rows) from HBM - or a PEER GPU's HBM over NVLink -
-//     into a 3-stage shared-memory ring with cp.async.bulk (TMA) completing on mbarriers; eight
-//     consumer warps split the query's ~75 dot products into register-blocked tasks (one A row against
-//     up to 5 B rows) on the resident rows; a rotating finisher warp runs the greedy de-duplication on
-//     the resulting cosine matrix, the fp64 statistics and the stores while the others move on.
+//   * embedding-fed   - a persistent, warp-specialised CTA per SM.  One producer warp per stage of a
+//     3-stage shared-memory ring walks the candidate lists and pulls the ~20 rows a query needs
+//     (image, text, V variants, the first R distinct retrieval candidates, G generative rows) from
+//     HBM - or a PEER GPU's HBM over NVLink - with cp.async.bulk (TMA) completing on mbarriers.
+//     Sixteen consumer warps draw (query, task) units from one CTA-wide queue: a task is one resident
+//     row A against up to 5 rows B, register-blocked, so the query's ~75 dot products cost ~20 units.
+//     The warp that draws a query's last unit waits for the rest, runs the greedy de-duplication on
+//     the resulting cosine matrix (one lane per candidate), releases the stage and writes the
+//     similarity lists; the similarity-fed kernel then turns them into statistics and decisions.
+//     Measured limits (scripts/trace_emb.py): the kernel is bound by per-stage latency (index load ->
+//     bulk copies -> tasks -> selection ~ 9 us) over the 3 stages that fit in 227 KB, not by HBM.
 #include <math.h>
 
 #include "tvc_internal.h"
@@ -107,17 +111,13 @@ __device__ __forceinline__ double clipd(double x, double lo, double hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
 
-// sv/sr/sg/sx point at this query's similarity lists (shared memory).  VM/RM/GM bound the counts.
-template <int VM, int RM, int GM>
-__device__ __forceinline__ void finish_scores(const tvc_detector_params& p, const double* rcp, float s0f,
-                                              const float* sv, int nv, const float* sr, int nr,
-                                              const float* sg, int ng, const float* sx, int nx,
-                                              float* out, int out_stride, uint8_t* flag) {
+// Scores and decisions of one query from the four groups' statistics (text variants, retrieval
+// references, generative references, variant pairs).
+__device__ __forceinline__ void combine_scores(const tvc_detector_params& p, const double* rcp, float s0f,
+                                               const Stats& tv, int nv, const Stats& rt, int nr,
+                                               const Stats& gn, int ng, const Stats& xv, float* out,
+                                               int out_stride, uint8_t* flag) {
   const double s0 = s0f;
-  const Stats tv = stats_of<VM>(sv, nv, rcp, true);
-  const Stats rt = stats_of<RM>(sr, nr, rcp, true);
-  const Stats gn = stats_of<GM>(sg, ng, rcp, true);
-  const Stats xv = stats_of<VM*(VM - 1) / 2>(sx, nx, rcp, false);
 
   // --- AdversarialDetector (src/detector.py:441-590, 643-682, 399)
   double det_tv = 0.0;
@@ -265,6 +265,19 @@ __device__ __forceinline__ void finish_scores(const tvc_detector_params& p, cons
   put(TVC_S_REF_SIGMA, sigma);
   *flag = static_cast<uint8_t>((det_adv ? TVC_FLAG_DET_ADV : 0u) | (cc_adv ? TVC_FLAG_CC_ADV : 0u) |
                                (sig_adv ? TVC_FLAG_SIGMA_ADV : 0u));
+}
+
+// sv/sr/sg/sx point at this query's similarity lists (shared memory).  VM/RM/GM bound the counts.
+template <int VM, int RM, int GM>
+__device__ __forceinline__ void finish_scores(const tvc_detector_params& p, const double* rcp, float s0f,
+                                              const float* sv, int nv, const float* sr, int nr,
+                                              const float* sg, int ng, const float* sx, int nx,
+                                              float* out, int out_stride, uint8_t* flag) {
+  const Stats tv = stats_of<VM>(sv, nv, rcp, true);
+  const Stats rt = stats_of<RM>(sr, nr, rcp, true);
+  const Stats gn = stats_of<GM>(sg, ng, rcp, true);
+  const Stats xv = stats_of<VM*(VM - 1) / 2>(sx, nx, rcp, false);
+  combine_scores(p, rcp, s0f, tv, nv, rt, nr, gn, ng, xv, out, out_stride, flag);
 }
 
 // runtime dispatch on the configured widths: the common (V<=5, R<=10, G<=4) build keeps every list in
@@ -525,12 +538,24 @@ __global__ void consistency_emb_generic_kernel(const tvc_detector_params p, long
 }
 
 // ---- pipelined kernel -----------------------------------------------------------------------------
-constexpr int kEmbConsumers = 8;                        // consumer warps
-constexpr int kEmbThreads = (kEmbConsumers + 1) * 32;   // + one producer warp
+constexpr int kEmbConsumers = 16;                       // consumer warps
 constexpr int kEmbMaxStages = 4;
+constexpr int kEmbProducers = kEmbMaxStages;            // producer warps: one per stage of the ring
+constexpr int kEmbThreads = (kEmbConsumers + kEmbProducers) * 32;
 constexpr int kJB = 5;                                  // B rows per task (register block)
 constexpr int kMaxTasks = 224;
 constexpr int kMaxStageRows = 2 + TVC_MAX_VARIANTS + 2 * TVC_MAX_REFS;   // 50
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// optional tracing of block 0 (a.trace != null): 8 timestamps per query, see scripts/trace_emb.py
+#define TVC_TRACE(i, k)                                                                              \
+  do {                                                                                               \
+    if (a.trace != nullptr && blockIdx.x == 0 && (i) < 512) atomicMin(a.trace + (i)*8 + (k), gtime_ns()); \
+  } while (0)
 
 // global -> shared bulk copy (TMA, no tensor map), completion bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -558,7 +583,6 @@ struct EmbStage {
   int pf_n[2];                         // rows prefetched
   int pf_end[2];                       // candidate position after the last prefetched one
   int n_gen_direct;                    // valid direct generative rows (g_cnt)
-  int task_ctr;
   // results: squared norms and image dots per stage row, pair dots per group
   float nrm2[kMaxStageRows];
   float d_img[kMaxStageRows];
@@ -572,7 +596,7 @@ struct EmbLists {
   float sr[TVC_MAX_REFS];
   float sg[TVC_MAX_REFS];
   float sx[kXMax];
-  float out[TVC_NSCORES];
+  float sq[kMaxStageRows];   // |row| of every stage row
   long long kept_idx[TVC_MAX_REFS];
   int kept_slot[TVC_MAX_REFS];
   int info[4];   // kept, need_slow
@@ -605,9 +629,8 @@ __device__ __forceinline__ int multi_index(int lane) {
   return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2);
 }
 
-template <bool NORMS>
-__device__ __forceinline__ void run_task(const EmbTask& t, int nb, const float* rows, int d, EmbStage* st,
-                                         float* out) {
+template <bool NORMS, int NB>
+__device__ __forceinline__ void run_task_nb(const EmbTask& t, const float* rows, int d, EmbStage* st, float* out) {
   const int lane = threadIdx.x & 31;
   const float4* A = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.a_row) * d);
   const float4* B = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.b_row0) * d);
@@ -616,36 +639,61 @@ __device__ __forceinline__ void run_task(const EmbTask& t, int nb, const float* 
   float v[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] = 0.f;
+#pragma unroll 2
   for (int c = lane; c < d4; c += 32) {
     const float4 x = A[c];
-    if (NORMS) {
-      v[10] = fmaf(x.x, x.x, v[10]); v[10] = fmaf(x.y, x.y, v[10]);
-      v[10] = fmaf(x.z, x.z, v[10]); v[10] = fmaf(x.w, x.w, v[10]);
-    }
+    float4 y[NB];
 #pragma unroll
-    for (int j = 0; j < kJB; ++j)
-      if (j < nb) {
-        const float4 y = B[static_cast<size_t>(j) * d4 + c];
-        v[j] = fmaf(x.x, y.x, v[j]); v[j] = fmaf(x.y, y.y, v[j]);
-        v[j] = fmaf(x.z, y.z, v[j]); v[j] = fmaf(x.w, y.w, v[j]);
-        if (NORMS) {
-          v[5 + j] = fmaf(y.x, y.x, v[5 + j]); v[5 + j] = fmaf(y.y, y.y, v[5 + j]);
-          v[5 + j] = fmaf(y.z, y.z, v[5 + j]); v[5 + j] = fmaf(y.w, y.w, v[5 + j]);
-        }
-      }
+    for (int j = 0; j < NB; ++j) y[j] = B[static_cast<size_t>(j) * d4 + c];
+    // component-major order: NB (or 2 NB + 1) independent chains advance together
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v[j] = fmaf(x.x, y[j].x, v[j]);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v[j] = fmaf(x.y, y[j].y, v[j]);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v[j] = fmaf(x.z, y[j].z, v[j]);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v[j] = fmaf(x.w, y[j].w, v[j]);
+    if (NORMS) {
+      v[10] = fmaf(x.x, x.x, v[10]);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[5 + j] = fmaf(y[j].x, y[j].x, v[5 + j]);
+      v[10] = fmaf(x.y, x.y, v[10]);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[5 + j] = fmaf(y[j].y, y[j].y, v[5 + j]);
+      v[10] = fmaf(x.z, x.z, v[10]);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[5 + j] = fmaf(y[j].z, y[j].z, v[5 + j]);
+      v[10] = fmaf(x.w, x.w, v[10]);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[5 + j] = fmaf(y[j].w, y[j].w, v[5 + j]);
+    }
   }
   const float r = warp_sum_multi<NV>(v, lane);
   const int idx = multi_index<NV>(lane);
   if ((lane & (NORMS ? 1 : 3)) == 0) {   // one lane per value
     if (idx < kJB) {
-      if (idx < nb) out[t.out + idx] = r;
+      if (idx < NB) out[t.out + idx] = r;
     } else if (NORMS) {
       if (idx < 2 * kJB) {
-        if (idx - kJB < nb) st->nrm2[t.b_row0 + idx - kJB] = r;
+        if (idx - kJB < NB) st->nrm2[t.b_row0 + idx - kJB] = r;
       } else if (idx == 10) {
         st->nrm2[t.a_row] = r;
       }
     }
+  }
+}
+
+template <bool NORMS>
+__device__ __forceinline__ void run_task(const EmbTask& t, int nb, const float* rows, int d, EmbStage* st,
+                                         float* out) {
+  static_assert(kJB == 5, "dispatch below covers 1..5");
+  switch (nb) {
+    case 5: run_task_nb<NORMS, 5>(t, rows, d, st, out); break;
+    case 4: run_task_nb<NORMS, 4>(t, rows, d, st, out); break;
+    case 3: run_task_nb<NORMS, 3>(t, rows, d, st, out); break;
+    case 2: run_task_nb<NORMS, 2>(t, rows, d, st, out); break;
+    default: run_task_nb<NORMS, 1>(t, rows, d, st, out); break;
   }
 }
 
@@ -664,11 +712,11 @@ __device__ int select_from_stage(const tvc_detector_params& p, EmbStage* st, int
   unsigned dup_of = 0;
   float sim = 0.f;
   if (lane < pf_n) {
-    const float ns = sqrtf(st->nrm2[row_base + lane]);
-    sim = st->d_img[row_base + lane] / fmaxf(sqrtf(st->nrm2[0]) * ns, 1e-8f);
+    const float ns = L->sq[row_base + lane];
+    sim = st->d_img[row_base + lane] / fmaxf(L->sq[0] * ns, 1e-8f);
     if (thr > -1.0f)
       for (int j = 0; j < lane; ++j) {
-        const float c = pd[j * TVC_MAX_REFS + lane] / fmaxf(sqrtf(st->nrm2[row_base + j]) * ns, 1e-8f);
+        const float c = pd[j * TVC_MAX_REFS + lane] / fmaxf(L->sq[row_base + j] * ns, 1e-8f);
         if (c > thr) dup_of |= 1u << j;
       }
   }
@@ -774,13 +822,13 @@ __device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const 
 
 __global__ void __launch_bounds__(kEmbThreads, 1)
 consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, const ConsistencyEmbArgs a,
-                            float* __restrict__ scores, uint8_t* __restrict__ flags, int n_stages,
-                            int stage_rows) {
+                            int n_stages, int stage_rows) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) uint64_t s_full[kEmbMaxStages], s_done[kEmbMaxStages], s_empty[kEmbMaxStages];
   __shared__ double s_rcp[kRcpN];
   __shared__ EmbTask s_tasks[kMaxTasks];
   __shared__ int s_ntasks;
+  __shared__ unsigned s_next;
   __shared__ EmbStage s_stage[kEmbMaxStages];
   __shared__ EmbLists s_lists[kEmbConsumers];
   float* s_rows = reinterpret_cast<float*>(s_raw);
@@ -797,12 +845,6 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
 
   fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_done[s], kEmbConsumers);
-      mbar_init(&s_empty[s], 1);
-    }
-    fence_mbar_init();
     // task table (the same for every query): image group, variant pairs, reference pairs
     int nt = 0;
     auto add = [&](int a_row, int b_row0, int nb, int norms, int ga, int gb, int ia, int ib0, int out) {
@@ -832,36 +874,41 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
             add(row_gen + i, row_gen + b, min(kJB, G - b), 0, 2, 2, i, b, i * TVC_MAX_REFS + b);
     }
     s_ntasks = nt;
+    s_next = 0u;
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_done[s], static_cast<uint32_t>(nt));   // one arrival per task
+      mbar_init(&s_empty[s], 1);
+    }
+    fence_mbar_init();
   }
   __syncthreads();
   const int ntasks = s_ntasks;
   const long long my_n = nq > blockIdx.x ? (nq - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (w == kEmbConsumers) {
-    // ===== producer warp
+  if (w >= kEmbConsumers) {
+    // ===== producer warps: a query costs its producer two dependent global loads of latency, so
+    // every stage has its own producer (which also keeps each stage's barrier phases in order)
     const uint32_t row_bytes = static_cast<uint32_t>(d) * 4u;
-    for (long long i = 0; i < my_n; ++i) {
-      const int s = static_cast<int>(i % n_stages);
-      const uint32_t round = static_cast<uint32_t>(i / n_stages);
-      if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1u);
+    if (w - kEmbConsumers >= n_stages) return;
+    const int s = w - kEmbConsumers;     // this producer's stage
+    uint32_t round = 0;
+    for (long long i = s; i < my_n; i += n_stages, ++round) {
+      if (round > 0) mbar_wait_parked(&s_empty[s], (round - 1) & 1u);
       const long long q = blockIdx.x + i * static_cast<long long>(gridDim.x);
       EmbStage* st = &s_stage[s];
       float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
       uint64_t* bar = &s_full[s];
-      // rows addressed directly by q: image, text, variants, direct generative rows
+      if (lane == 0) TVC_TRACE(i, 0);
+      // rows addressed directly by q: image, text, the V variants (contiguous) and the direct
+      // generative rows (contiguous): four bulk copies
       const int ndirect = 2 + V + (gen_direct ? G : 0);
-      if (lane < ndirect) {
-        const float* srcp;
-        int row;
-        if (lane == 0) { srcp = a.img + q * d; row = 0; }
-        else if (lane == 1) { srcp = a.txt + q * d; row = 1; }
-        else if (lane < 2 + V) { srcp = a.var + (q * V + (lane - 2)) * d; row = lane; }
-        else { srcp = a.gen + (q * G + (lane - 2 - V)) * d; row = row_gen + (lane - 2 - V); }
-        bulk_g2s(rows + static_cast<size_t>(row) * d, srcp, row_bytes, bar);
-      }
-      if (ndirect > 32)   // V = G = 16: the last rows
-        for (int r = 32 + lane; r < ndirect; r += 32)
-          bulk_g2s(rows + static_cast<size_t>(row_gen + (r - 2 - V)) * d, a.gen + (q * G + (r - 2 - V)) * d, row_bytes, bar);
+      if (lane == 0) bulk_g2s(rows, a.img + q * d, row_bytes, bar);
+      if (lane == 1) bulk_g2s(rows + d, a.txt + q * d, row_bytes, bar);
+      if (lane == 2 && V > 0)
+        bulk_g2s(rows + static_cast<size_t>(row_var) * d, a.var + q * V * d, row_bytes * V, bar);
+      if (lane == 3 && gen_direct && G > 0)
+        bulk_g2s(rows + static_cast<size_t>(row_gen) * d, a.gen + q * G * d, row_bytes * G, bar);
       uint32_t bytes = static_cast<uint32_t>(ndirect) * row_bytes;
       if (has_ret)
         bytes += prefetch_group(st, 0, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
@@ -874,68 +921,69 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
         if (!has_ret) { st->pf_n[0] = 0; st->pf_end[0] = 0; }
         if (!gen_idx) { st->pf_n[1] = 0; st->pf_end[1] = 0; }
         st->n_gen_direct = gen_direct ? (a.g_cnt ? max(0, min(G, a.g_cnt[q])) : G) : 0;
-        st->task_ctr = 0;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+      if (lane == 0) TVC_TRACE(i, 1);
     }
     return;
   }
 
-  // ===== consumer warps
+  // ===== consumer warps: one CTA-wide queue of (query, task) units in query order
   EmbLists* L = &s_lists[w];
-  bool skip_next = false;
-  for (long long i = 0; i < my_n; ++i) {
-    const int s = static_cast<int>(i % n_stages);
-    const uint32_t par = static_cast<uint32_t>(i / n_stages) & 1u;
+  const unsigned total_units = static_cast<unsigned>(my_n) * static_cast<unsigned>(ntasks);   // < 2^31 (launcher)
+  while (true) {
+    unsigned g = 0;
+    if (lane == 0) g = atomicAdd(&s_next, 1u);
+    g = __shfl_sync(kFull, g, 0);
+    if (g >= total_units) break;
+    const unsigned iu = g / static_cast<unsigned>(ntasks);      // 32-bit divisions only
+    const int t = static_cast<int>(g - iu * static_cast<unsigned>(ntasks));
+    const unsigned round = iu / static_cast<unsigned>(n_stages);
+    const int s = static_cast<int>(iu - round * static_cast<unsigned>(n_stages));
+    const uint32_t par = round & 1u;
+    const long long i = iu;
     EmbStage* st = &s_stage[s];
     float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
-    if (skip_next) {   // finished the previous query: already checked in for this one
-      skip_next = false;
-      continue;
-    }
-    mbar_wait(&s_full[s], par);
-    const int valid1 = st->pf_n[0], valid2 = st->pf_n[1], valid3 = st->n_gen_direct;
-    while (true) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(&st->task_ctr, 1);
-      t = __shfl_sync(kFull, t, 0);
-      if (t >= ntasks) break;
+    mbar_wait_parked(&s_full[s], par);
+    if (lane == 0) TVC_TRACE(i, 2);
+    {
       const EmbTask tk = s_tasks[t];
+      const int valid1 = st->pf_n[0], valid2 = st->pf_n[1], valid3 = st->n_gen_direct;
       const int va = tk.ga == 0 ? 1 << 20 : (tk.ga == 1 ? valid1 : valid2);
       const int vb = tk.gb == 0 ? 1 << 20 : (tk.gb == 1 ? valid1 : (tk.gb == 2 ? valid2 : valid3));
       const int nb = min(static_cast<int>(tk.nb), vb - tk.ib0);
-      if (tk.ia >= va || nb <= 0) continue;
-      if (tk.norms)
-        run_task<true>(tk, nb, rows, d, st, st->d_img);
-      else
-        run_task<false>(tk, nb, rows, d, st, tk.ga == 0 ? st->d_var : st->d_ref[tk.ga - 1]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_done[s]);
-    if (static_cast<int>(i % kEmbConsumers) != w) continue;
-
-    // ===== finisher for this query
-    mbar_wait(&s_done[s], par);
-    // This warp is about to be busy: it sits out the next query's tasks and checks in on that
-    // query's done barrier now (legal: all eight arrivals of the barrier's previous phase happened
-    // before this query's did), so consecutive finishers overlap instead of waiting for each other.
-    if (i + 1 < my_n && lane == 0) mbar_arrive(&s_done[(i + 1) % n_stages]);
-    skip_next = true;
-    const long long q = st->q;
-    const float n_img = st->nrm2[0];
-    float s0 = cos_of(st->d_img[1], n_img, st->nrm2[1]);
-    if (lane < V) L->sv[lane] = cos_of(st->d_img[row_var + lane], n_img, st->nrm2[row_var + lane]);
-    int nx = 0;
-    for (int ii = 0; ii < V; ++ii) {
-      const int cnt = V - 1 - ii;   // pairs (ii, ii+1 .. V-1) are consecutive in sx
-      if (lane < cnt) {
-        const int jj = ii + 1 + lane;
-        L->sx[nx + lane] = cos_of(st->d_var[ii * TVC_MAX_VARIANTS + jj], st->nrm2[row_var + ii], st->nrm2[row_var + jj]);
+      if (tk.ia < va && nb > 0) {
+        if (tk.norms)
+          run_task<true>(tk, nb, rows, d, st, st->d_img);
+        else
+          run_task<false>(tk, nb, rows, d, st, tk.ga == 0 ? st->d_var : st->d_ref[tk.ga - 1]);
       }
-      nx += cnt;
     }
     __syncwarp();
+    if (lane == 0) mbar_arrive(&s_done[s]);     // one arrival per unit, executed or skipped
+    if (t != ntasks - 1) continue;
+
+    // ===== the warp that drew a query's last unit finishes it (the others keep drawing units)
+    mbar_wait_parked(&s_done[s], par);
+    if (lane == 0) TVC_TRACE(i, 3);
+    const long long q = st->q;
+    for (int r = lane; r < stage_rows; r += 32) L->sq[r] = sqrtf(st->nrm2[r]);
+    __syncwarp();
+    const float sq_img = L->sq[0];
+    const float s0 = st->d_img[1] / fmaxf(sq_img * L->sq[1], 1e-8f);
+    if (lane < V) L->sv[lane] = st->d_img[row_var + lane] / fmaxf(sq_img * L->sq[row_var + lane], 1e-8f);
+    const int nx = V * (V - 1) / 2;
+    for (int e = lane; e < nx; e += 32) {
+      // e-th pair (ii < jj) in row-major order of the upper triangle
+      int ii = 0, rem = e;
+      while (rem >= V - 1 - ii) {
+        rem -= V - 1 - ii;
+        ++ii;
+      }
+      const int jj = ii + 1 + rem;
+      L->sx[e] = st->d_var[ii * TVC_MAX_VARIANTS + jj] / fmaxf(L->sq[row_var + ii] * L->sq[row_var + jj], 1e-8f);
+    }
     int nr = 0;
     if (has_ret)
       nr = select_from_stage(p, st, 0, rows, d, row_ret, a.ret,
@@ -944,28 +992,43 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     int ng = 0;
     if (gen_direct) {
       ng = st->n_gen_direct;
-      if (lane < ng) L->sg[lane] = cos_of(st->d_img[row_gen + lane], n_img, st->nrm2[row_gen + lane]);
+      if (lane < ng) L->sg[lane] = st->d_img[row_gen + lane] / fmaxf(sq_img * L->sq[row_gen + lane], 1e-8f);
     } else if (gen_idx) {
       ng = select_from_stage(p, st, 1, rows, d, row_gen, a.genr,
                              reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand, a.n_gen_cand, G,
                              L->sg, L);
     }
-    __syncwarp();
-    if (lane == 0) {
-      uint8_t flag;
-      finish_scores_any(p, s_rcp, s0, L->sv, V, L->sr, nr, L->sg, ng, L->sx, nx, L->out, 1, &flag);
-      flags[q] = flag;
-    }
-    __syncwarp();
-    if (lane < TVC_NSCORES) scores[q * TVC_NSCORES + lane] = L->out[lane];
-    const int Vp = p.n_variants, Rp = p.n_retrieval, Gp = p.n_generative;
-    if (a.out_sv && lane < Vp) a.out_sv[q * Vp + lane] = lane < V ? L->sv[lane] : 0.f;
-    if (a.out_sr && lane < Rp) a.out_sr[q * Rp + lane] = lane < nr ? L->sr[lane] : 0.f;
-    if (a.out_sg && lane < Gp) a.out_sg[q * Gp + lane] = lane < ng ? L->sg[lane] : 0.f;
-    // the slow path may have written rows with ordinary stores; the next use of the stage is a bulk copy
+    // everything still needed lives in this warp's lists: hand the stage back
+    // (the slow path may have written rows with ordinary stores; the next writer is a bulk copy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);
+    if (lane == 0) TVC_TRACE(i, 4);
+    // similarity lists -> global; the statistics kernel (consistency_sims_kernel) takes it from there
+    const int Vp = p.n_variants, Rp = p.n_retrieval, Gp = p.n_generative;
+    if (lane == 0) {
+      a.w_s0[q] = s0;
+      a.w_rcnt[q] = nr;
+      a.w_gcnt[q] = ng;
+    }
+    if (lane < Vp) {
+      const float x = lane < V ? L->sv[lane] : 0.f;
+      a.w_sv[q * Vp + lane] = x;
+      if (a.out_sv) a.out_sv[q * Vp + lane] = x;
+    }
+    if (lane < Rp) {
+      const float x = lane < nr ? L->sr[lane] : 0.f;
+      a.w_sr[q * Rp + lane] = x;
+      if (a.out_sr) a.out_sr[q * Rp + lane] = x;
+    }
+    if (lane < Gp) {
+      const float x = lane < ng ? L->sg[lane] : 0.f;
+      a.w_sg[q * Gp + lane] = x;
+      if (a.out_sg) a.out_sg[q * Gp + lane] = x;
+    }
+    for (int e = lane; e < nx; e += 32) a.w_sx[q * nx + e] = L->sx[e];
+    __syncwarp();
+    if (lane == 0) TVC_TRACE(i, 5);
   }
 }
 
@@ -1020,23 +1083,33 @@ cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int 
   bool pipe = !force_generic && (d % 4) == 0 && al16(a.img) && al16(a.txt) && (!a.var || al16(a.var)) &&
               (!a.gen || al16(a.gen)) && (!has_ret || rows_f32_aligned(a.ret)) &&
               (!gen_idx || rows_f32_aligned(a.genr));
-  const size_t smem_budget = 196 * 1024;   // dynamic; the static part (stages, tasks, lists) is ~28 KB
+  // dynamic shared memory left for the stage ring after the kernel's static tables
+  static size_t smem_budget = 0;
+  if (smem_budget == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, consistency_emb_pipe_kernel);
+    if (e != cudaSuccess) return e;
+    const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+    e = cudaFuncSetAttribute(consistency_emb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(budget));
+    if (e != cudaSuccess) return e;
+    smem_budget = budget;
+  }
   int n_stages = static_cast<int>(smem_budget / stage_bytes);
   if (n_stages > kEmbMaxStages) n_stages = kEmbMaxStages;
   if (n_stages < 2) pipe = false;
+  if (q / (sm_count > 0 ? sm_count : 1) + 1 >= (1ll << 31) / kMaxTasks) pipe = false;   // 32-bit unit counter
   if (pipe) {
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(consistency_emb_pipe_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_budget));
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
     long long blocks = q < sm_count ? q : sm_count;
     consistency_emb_pipe_kernel<<<static_cast<int>(blocks), kEmbThreads, n_stages * stage_bytes, stream>>>(
-        p, q, d, a, scores, flags, n_stages, stage_rows);
+        p, q, d, a, n_stages, stage_rows);
     note_launch();
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // statistics + decisions from the similarity lists the kernel left in the workspace
+    return launch_consistency_sims(p, q, a.w_s0, V > 0 ? a.w_sv : nullptr, has_ret ? a.w_sr : nullptr, a.w_rcnt,
+                                   G > 0 ? a.w_sg : nullptr, a.w_gcnt, V > 1 ? a.w_sx : nullptr, scores, flags,
+                                   stream);
   }
   // ---- generic kernel
   int rows_cap = p.n_retrieval > p.n_generative ? p.n_retrieval : p.n_generative;

@@ -99,6 +99,15 @@ struct ConsistencyEmbArgs {
   float* out_sv;
   float* out_sr;
   float* out_sg;
+  // similarity lists written by the pipelined kernel for the statistics kernel (device workspace)
+  float* w_s0;
+  float* w_sv;
+  float* w_sr;
+  int32_t* w_rcnt;
+  float* w_sg;
+  int32_t* w_gcnt;
+  float* w_sx;
+  unsigned long long* trace;   // debugging: per-query timestamps of block 0 (null = off)
 };
 
 cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, const float* s0,

@@ -21,6 +21,8 @@
  *   tvc_k_occurrence               hubness_counts[j] += 1 double loop            references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:43-57
  *                                  (top1 == 0).sum()                             src/attacks/hubness_attack.py:492-496
  *   tvc_merge_topk                 (new) merge of per-shard top-k candidates after the NCCL all-gather
+ *   tvc_search_candidates /        (new) sharded search: candidates written into the owner's HBM over NVLink,
+ *   tvc_rerank_candidates                re-ranked there from local + peer fp32 masters
  *
  * Conventions
  *   - plain pointers and sizes only; every function returns a tvc_status (0 = ok) and never throws.
@@ -63,6 +65,8 @@ typedef enum { TVC_F32 = 0, TVC_BF16 = 1, TVC_F16 = 2 } tvc_dtype;
 /* search flags */
 #define TVC_SEARCH_NORMALIZE_Q 1u  /* L2-normalise query rows (cosine metric) */
 #define TVC_SEARCH_SKIP_SELF 2u    /* query set == gallery: drop candidate idx == query row (hubness spec [:,1:k+1]) */
+#define TVC_SEARCH_PREPARED_Q 4u   /* tvc_search_candidates only: `queries` is the bf16 [m, tvc_query_row_bytes(d)/2]
+                                      operand written by tvc_prepare_queries (q_dtype is ignored) */
 
 #define TVC_MAX_K 56               /* largest k served by the in-register top-k epilogue */
 #define TVC_MAX_VARIANTS 16
@@ -180,6 +184,49 @@ int tvc_gallery_group_create(tvc_ctx* ctx, tvc_gallery** parts, int32_t n_parts,
 int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
                int32_t k, float threshold, uint32_t flags, float* out_sim, int64_t* out_idx,
                void* stream);
+
+/* ---- Sharded exact search (gallery row-sharded over the GPUs of one box, one process per GPU) ----
+ * Phase 1, every rank, all query rows: GEMM + per-range top-KP on this rank's shard; the KP =
+ * tvc_candidate_width(k) best candidates of each row by GEMM score (global indices, -1 = unused) go
+ * either to the local lists cand_val/cand_idx [m, KP] or - with `scatter` - straight into the receive
+ * buffers of the ranks that own the query slices: row r belongs to slice j = r / rows_per_slice and is
+ * written at val[j][(slot * rows_in_slice_j + r - j*rows_per_slice) * KP ...].  val[j] / idx[j] are
+ * device pointers of THIS process: the rank's own buffer or a peer's buffer opened with tvc_peer_open,
+ * so the exchange is the kernel's own store stream over NVLink (no collective).  The caller orders
+ * phase 2 after every rank's phase 1 (a barrier on the stream) and double-buffers the receive buffers.
+ * Phase 2, the owner of a slice: merge the `parts` lists of each of its rows ([parts, m, KP]), re-score
+ * the KP best in fp32 from the masters behind `g` (a gallery or a group with peer views) and emit the
+ * top-k (score desc, index asc, `threshold` filter) - bit-identical to tvc_search on the unsharded
+ * gallery.  Device pointers only. */
+/* Query operand of the GEMM, prepared once per batch and BROADCAST over peer memory: the rows
+ * (device, any dtype, optionally L2-normalised) are converted to the bf16 zero-padded row format
+ * (tvc_query_row_bytes(d) bytes per row) and written at row `dst_row0` of each of the n_dst buffers -
+ * the rank's own query buffer and its peers' (tvc_peer_alloc / tvc_peer_open).  A rank that holds only
+ * its slice of the batch thereby hands the operand to the whole box; pass the filled buffer to
+ * tvc_search_candidates with TVC_SEARCH_PREPARED_Q (after a barrier when peers wrote into it). */
+int tvc_query_row_bytes(int32_t d);
+int tvc_prepare_queries(tvc_ctx* ctx, const void* rows, int dtype, int64_t m, int32_t d, uint32_t flags,
+                        int32_t n_dst, void* const* dst, int64_t dst_row0, void* stream);
+
+typedef struct {
+  int32_t n_slices;
+  int32_t slot;
+  int64_t rows_per_slice;
+  float* val[16];
+  int64_t* idx[16];
+} tvc_scatter;
+int tvc_candidate_width(int32_t k);
+int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
+                          int32_t k, uint32_t flags, const tvc_scatter* scatter, float* cand_val,
+                          int64_t* cand_idx, void* stream);
+int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, int64_t m, int32_t d,
+                          int32_t parts, int32_t kp, const float* cand_val, const int64_t* cand_idx, int32_t k,
+                          float threshold, float* out_sim, int64_t* out_idx, void* stream);
+/* device buffers shareable with the other ranks of the box (cudaMalloc + CUDA IPC; zero-filled) */
+int tvc_peer_alloc(tvc_ctx* ctx, int64_t bytes, void** ptr, void* handle /* TVC_IPC_HANDLE_BYTES */);
+int tvc_peer_open(tvc_ctx* ctx, const void* handle, void** ptr);
+int tvc_peer_close(tvc_ctx* ctx, void* ptr);
+int tvc_peer_free(tvc_ctx* ctx, void* ptr);
 
 /* Dense [m, N] fp32 similarity matrix (tcgen05 GEMM, plain store epilogue). Only for sizes that
  * fit; the search path never materialises it. */

@@ -16,7 +16,7 @@ LIB_PATH = PKG_DIR / "libtvc.so"
 TVC_OK, TVC_ERR_INVALID, TVC_ERR_CUDA, TVC_ERR_NO_DEVICE, TVC_ERR_UNSUPPORTED, TVC_ERR_OOM = range(6)
 TVC_F32, TVC_BF16, TVC_F16 = 0, 1, 2
 GALLERY_NORMALIZE, GALLERY_NO_MASTER = 1, 2
-SEARCH_NORMALIZE_Q, SEARCH_SKIP_SELF = 1, 2
+SEARCH_NORMALIZE_Q, SEARCH_SKIP_SELF, SEARCH_PREPARED_Q = 1, 2, 4
 MAX_K, MAX_VARIANTS, MAX_REFS, NSCORES = 56, 16, 16, 24
 FLAG_DET_ADV, FLAG_CC_ADV, FLAG_SIGMA_ADV = 1, 2, 4
 
@@ -28,6 +28,12 @@ SCORE_NAMES = (
     "det_consistency", "aggregated_score", "overall_score", "threshold", "confidence",
     "n_retrieval", "n_generative", "reference_sigma")
 SCORE_INDEX = {n: i for i, n in enumerate(SCORE_NAMES)}
+
+
+class Scatter(C.Structure):
+    """tvc_scatter: where the candidates of a sharded search go (include/tvc.h)."""
+    _fields_ = [("n_slices", C.c_int32), ("slot", C.c_int32), ("rows_per_slice", C.c_int64),
+                ("val", C.c_void_p * 16), ("idx", C.c_void_p * 16)]
 
 
 class TvcError(RuntimeError):
@@ -94,6 +100,19 @@ _EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,  # gen g_cnt gen_gallery gen_idx ncand
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,  # scores flags sv sr sg
                                       C.c_void_p]),
+    "tvc_candidate_width": (C.c_int, [C.c_int32]),
+    "tvc_query_row_bytes": (C.c_int, [C.c_int32]),
+    "tvc_prepare_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_uint32, C.c_int32,
+                                      C.POINTER(C.c_void_p), C.c_int64, C.c_void_p]),
+    "tvc_search_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tvc_rerank_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "tvc_peer_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "tvc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tvc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tvc_k_occurrence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_int, C.c_void_p]),
 }
@@ -252,6 +271,53 @@ class Context:
         self.check(self.lib.tvc_merge_topk(self.handle, _ptr(sims), _ptr(idx), m, parts, k, _ptr(out_s),
                                            _ptr(out_i), _stream_of(sims)))
         return out_s, out_i
+
+    # -- sharded search (peer memory) --------------------------------------------------------
+    def peer_alloc(self, nbytes: int) -> Tuple[int, bytes]:
+        """Zero-filled device buffer shareable with the other ranks: (device pointer, 64-byte IPC handle)."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.check(self.lib.tvc_peer_alloc(self.handle, int(nbytes), C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.check(self.lib.tvc_peer_open(self.handle, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self.check(self.lib.tvc_peer_close(self.handle, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self.check(self.lib.tvc_peer_free(self.handle, C.c_void_p(ptr)))
+
+    def query_row_bytes(self, d: int) -> int:
+        return int(self.lib.tvc_query_row_bytes(int(d)))
+
+    def prepare_queries(self, rows, dst_ptrs, dst_row0: int = 0, normalize: bool = False):
+        """rows [m, d] cuda tensor -> bf16 GEMM operand rows written at row dst_row0 of every buffer in
+        dst_ptrs (device pointers: own or peer query buffers)."""
+        q = _rows(rows)
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+        self.check(self.lib.tvc_prepare_queries(self.handle, _ptr(q), _dtype_code(q), int(q.shape[0]), int(q.shape[1]),
+                                                SEARCH_NORMALIZE_Q if normalize else 0, len(dst_ptrs), arr,
+                                                int(dst_row0), _stream_of(q)))
+
+    def candidate_width(self, k: int) -> int:
+        return int(self.lib.tvc_candidate_width(int(k)))
+
+    def rerank_candidates(self, gallery, queries, cand_val: int, cand_idx: int, parts: int, kp: int, k: int,
+                          threshold: float = -math.inf):
+        """Phase 2 of the sharded search: queries [m, d] fp32 cuda; cand_val / cand_idx are device
+        pointers of the [parts, m, kp] receive buffers.  Returns (sims [m,k], idx [m,k]) cuda tensors."""
+        import torch
+        q = queries.contiguous().to(torch.float32)
+        m = int(q.shape[0])
+        sims = torch.empty((m, k), dtype=torch.float32, device=q.device)
+        idx = torch.empty((m, k), dtype=torch.int64, device=q.device)
+        self.check(self.lib.tvc_rerank_candidates(self.handle, gallery.handle, _ptr(q), m, int(q.shape[1]), int(parts),
+                                                  int(kp), C.c_void_p(cand_val), C.c_void_p(cand_idx), int(k),
+                                                  float(threshold), _ptr(sims), _ptr(idx), _stream_of(q)))
+        return sims, idx
 
     # -- kernel (c) ------------------------------------------------------------------------
     def k_occurrence(self, idx, n_bins: int, idx_base: int = 0, counts=None):
@@ -495,6 +561,33 @@ class Gallery:
             sims = sims.reshape(*lead, k)
             idx = idx.reshape(*lead, k)
         return sims, idx
+
+    def search_candidates(self, queries, k: int, scatter: Optional[Scatter] = None, *, normalize_queries: bool = False,
+                          skip_self: bool = False):
+        """Phase 1 of the sharded search on this shard (cuda tensors only).  With `scatter` the candidates
+        go to the slice owners' receive buffers and nothing is returned; otherwise returns the local
+        (cand_val [m, kp] f32, cand_idx [m, kp] i64 global) lists."""
+        import torch
+        flags = (SEARCH_NORMALIZE_Q if normalize_queries else 0) | (SEARCH_SKIP_SELF if skip_self else 0)
+        if isinstance(queries, tuple):
+            # (device pointer of a prepared bf16 operand, rows): see Context.prepare_queries
+            qp, m = int(queries[0]), int(queries[1])
+            flags |= SEARCH_PREPARED_Q
+            code, stream, dev = TVC_BF16, torch.cuda.current_stream().cuda_stream, torch.device("cuda", self.ctx.device)
+        else:
+            q = _rows(queries)
+            if q.ndim > 2:
+                q = q.reshape(-1, q.shape[-1])
+            qp, m, code, stream, dev = _ptr(q), int(q.shape[0]), _dtype_code(q), _stream_of(q), q.device
+        val = idx = None
+        if scatter is None:
+            kp = self.ctx.candidate_width(k)
+            val = torch.empty((m, kp), dtype=torch.float32, device=dev)
+            idx = torch.empty((m, kp), dtype=torch.int64, device=dev)
+        self.ctx.check(self.ctx.lib.tvc_search_candidates(
+            self.ctx.handle, self.handle, C.c_void_p(qp), code, m, self.dim, int(k), flags,
+            C.byref(scatter) if scatter is not None else None, _ptr(val), _ptr(idx), stream))
+        return val, idx
 
     def similarity_matrix(self, queries, *, normalize_queries: bool = False):
         q = _rows(queries)

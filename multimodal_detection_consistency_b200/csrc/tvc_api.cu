@@ -604,9 +604,18 @@ static void fill_row_source(RowSource* rs, const tvc_gallery* g) {
 }
 
 // ------------------------------------------------------------------------------- search
+// candidates-only mode of search_chunk (sharded search, phase 1)
+struct CandOut {
+  const ScatterSpec* sc = nullptr;   // scatter to the slice owners, or
+  float* val = nullptr;              // local [m_total, kp] lists (device)
+  int64_t* idx = nullptr;
+  int64_t m_total = 0;
+};
+
 static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool q_dev, int q_dtype,
                         int64_t m, int64_t row0, int32_t k, float threshold, uint32_t flags,
-                        float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev, cudaStream_t st) {
+                        float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev, cudaStream_t st,
+                        const CandOut* cand = nullptr) {
   const int d = g->d, d_pad = g->d_pad;
   // CTA pairs (cta_group::2) pay off once there are enough 256-row query tiles to feed 74 pairs
   bool pair = m >= ctx->pair_min_rows && (ctx->sm_count % 2) == 0;
@@ -614,32 +623,38 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
   plan.debug = static_cast<int>(ctx->debug_flags);
   plan.skip_self = (flags & TVC_SEARCH_SKIP_SELF) ? 1 : 0;
   plan.self_offset = row0 - g->offset;  // query row i <-> global gallery row i
-  const size_t q_in_b = q_dev ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
-  const size_t q_bf_b = up256(static_cast<size_t>(m) * d_pad * 2);
-  const size_t q_f32_b = g->f32 ? up256(static_cast<size_t>(m) * d * 4) : 0;
+  const bool prepared = (flags & TVC_SEARCH_PREPARED_Q) != 0;   // queries = bf16 [m, d_pad] made by tvc_prepare_queries
+  if (prepared && !cand) return fail(ctx, TVC_ERR_UNSUPPORTED, "prepared queries serve tvc_search_candidates only");
+  const size_t q_in_b = (q_dev || prepared) ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
+  const size_t q_bf_b = prepared ? 0 : up256(static_cast<size_t>(m) * d_pad * 2);
+  const size_t q_f32_b = (g->f32 && !cand) ? up256(static_cast<size_t>(m) * d * 4) : 0;
   const size_t cand_n = static_cast<size_t>(m) * plan.splits * plan.kp;
   const size_t cand_b = up256(cand_n * 4);
-  const size_t os_b = sim_dev ? 0 : up256(static_cast<size_t>(m) * k * 4);
-  const size_t oi_b = idx_dev ? 0 : up256(static_cast<size_t>(m) * k * 8);
+  const size_t os_b = (sim_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 4);
+  const size_t oi_b = (idx_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 8);
   uint8_t* ws;
   int rc = get_ws(ctx, st, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b, &ws);
   if (rc != TVC_OK) return rc;
   uint8_t* p = ws;
   uint8_t* q_in = p; p += q_in_b;
   __nv_bfloat16* q_bf = reinterpret_cast<__nv_bfloat16*>(p); p += q_bf_b;
-  float* q_f32 = g->f32 ? reinterpret_cast<float*>(p) : nullptr; p += q_f32_b;
+  float* q_f32 = q_f32_b ? reinterpret_cast<float*>(p) : nullptr; p += q_f32_b;
   float* cand_val = reinterpret_cast<float*>(p); p += cand_b;
   int32_t* cand_idx = reinterpret_cast<int32_t*>(p); p += cand_b;
   float* d_sim = sim_dev ? out_sim : reinterpret_cast<float*>(p); p += os_b;
   int64_t* d_idx = idx_dev ? out_idx : reinterpret_cast<int64_t*>(p); p += oi_b;
 
-  const void* q_src = queries;
-  if (!q_dev) {
-    rc = to_device(ctx, queries, static_cast<size_t>(m) * d * elem_size(q_dtype), q_in, st, &q_src);
-    if (rc != TVC_OK) return rc;
+  if (prepared) {
+    q_bf = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(queries));
+  } else {
+    const void* q_src = queries;
+    if (!q_dev) {
+      rc = to_device(ctx, queries, static_cast<size_t>(m) * d * elem_size(q_dtype), q_in, st, &q_src);
+      if (rc != TVC_OK) return rc;
+    }
+    TVC_CUDA(ctx, launch_prep_rows(q_src, q_dtype, m, d, d_pad, (flags & TVC_SEARCH_NORMALIZE_Q) != 0, q_bf,
+                                   q_f32, st));
   }
-  TVC_CUDA(ctx, launch_prep_rows(q_src, q_dtype, m, d, d_pad, (flags & TVC_SEARCH_NORMALIZE_Q) != 0, q_bf,
-                                 q_f32, st));
   CUtensorMap tq;
   rc = make_tmap(ctx, &tq, q_bf, m, d_pad, kBM);
   if (rc != TVC_OK) return rc;
@@ -663,6 +678,18 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
   if (ctx->timing) {
     TVC_CUDA(ctx, cudaEventRecord(ev.second, st));
     ctx->timed.push_back(ev);
+  }
+  if (cand) {
+    // sharded search: keep the kp best per row by GEMM score; re-ranking happens on the slice owner
+    ScatterSpec sc{};
+    if (cand->sc) {
+      sc = *cand->sc;
+      if (row0 != 0) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search_candidates: scatter needs m <= 2^20 rows");
+    }
+    TVC_CUDA(ctx, launch_select_candidates(cand_val, cand_idx, m, plan.splits, plan.kp, g->offset, sc,
+                                           cand->val ? cand->val + row0 * plan.kp : nullptr,
+                                           cand->idx ? cand->idx + row0 * plan.kp : nullptr, st));
+    return TVC_OK;
   }
   TVC_CUDA(ctx, launch_rerank(cand_val, cand_idx, m, plan.splits, plan.kp, k, q_f32, g->f32, d, threshold,
                               g->offset, d_sim, d_idx, st));
@@ -711,6 +738,153 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
     if ((!q_dev || !sim_dev || !idx_dev) && r0 + mc < m) TVC_CUDA(ctx, cudaStreamSynchronize(st));
   }
   if (!q_dev || !sim_dev || !idx_dev) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
+int tvc_candidate_width(int32_t k) {
+  if (k < 1 || k > TVC_MAX_K) return 0;
+  return make_search_plan(256, 256, kBK, k, 148, false).kp;
+}
+
+int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
+                          int32_t k, uint32_t flags, const tvc_scatter* scatter, float* cand_val,
+                          int64_t* cand_idx, void* stream) {
+  if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: bad handle");
+  if (m < 0 || (m > 0 && !queries) || q_dtype < 0 || q_dtype > TVC_F16 || g->external || d != g->d)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: bad argument");
+  if (k < 1) return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: k < 1");
+  if (k > TVC_MAX_K) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search_candidates: k > TVC_MAX_K");
+  if (!scatter && (!cand_val || !cand_idx) && m > 0)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: neither scatter nor local lists given");
+  if (scatter && (scatter->n_slices < 1 || scatter->n_slices > kMaxParts || scatter->rows_per_slice < 1 ||
+                  scatter->slot < 0 || scatter->rows_per_slice * scatter->n_slices < m))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: bad scatter description");
+  if (!is_device_ptr(queries) || (!scatter && (!is_device_ptr(cand_val) || !is_device_ptr(cand_idx))))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: device pointers only");
+  if (m == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const int kp = tvc_candidate_width(k);
+  ScatterSpec sc{};
+  CandOut co;
+  co.m_total = m;
+  if (scatter) {
+    sc.n_slices = scatter->n_slices;
+    sc.slot = scatter->slot;
+    sc.rows_per_slice = scatter->rows_per_slice;
+    for (int i = 0; i < scatter->n_slices; ++i) {
+      sc.val[i] = scatter->val[i];
+      sc.idx[i] = reinterpret_cast<long long*>(scatter->idx[i]);
+    }
+    co.sc = &sc;
+  } else {
+    co.val = cand_val;
+    co.idx = cand_idx;
+  }
+  if (g->n == 0) {
+    // empty shard: every slot unused (written by the select kernel from an all-empty candidate list)
+    uint8_t* ws;
+    const size_t cb = up256(static_cast<size_t>(m) * kp * 4);
+    int rc = get_ws(ctx, st, 2 * cb, &ws);
+    if (rc != TVC_OK) return rc;
+    TVC_CUDA(ctx, cudaMemsetAsync(ws, 0xFF, 2 * cb, st));   // idx = -1 everywhere
+    TVC_CUDA(ctx, launch_select_candidates(reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + cb), m, 1,
+                                           kp, g->offset, sc, co.val, co.idx, st));
+    return TVC_OK;
+  }
+  const size_t q_row_b = (flags & TVC_SEARCH_PREPARED_Q) ? static_cast<size_t>(g->d_pad) * 2
+                                                           : static_cast<size_t>(d) * elem_size(q_dtype);
+  for (int64_t r0 = 0; r0 < m; r0 += kMaxRowsPerLaunch) {
+    const int64_t mc = m - r0 < kMaxRowsPerLaunch ? m - r0 : kMaxRowsPerLaunch;
+    const int rc = search_chunk(ctx, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, true, q_dtype, mc, r0,
+                                k, -INFINITY, flags, nullptr, true, nullptr, true, st, &co);
+    if (rc != TVC_OK) return rc;
+  }
+  return TVC_OK;
+}
+
+int tvc_query_row_bytes(int32_t d) { return d > 0 ? (d + kBK - 1) / kBK * kBK * 2 : 0; }
+
+int tvc_prepare_queries(tvc_ctx* ctx, const void* rows, int dtype, int64_t m, int32_t d, uint32_t flags,
+                        int32_t n_dst, void* const* dst, int64_t dst_row0, void* stream) {
+  if (!ctx || m < 0 || d <= 0 || dtype < 0 || dtype > TVC_F16 || n_dst < 1 || n_dst > kMaxParts || !dst ||
+      dst_row0 < 0 || (m > 0 && !rows))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_prepare_queries: bad argument");
+  if (m == 0) return TVC_OK;
+  if (!is_device_ptr(rows)) return fail(ctx, TVC_ERR_INVALID, "tvc_prepare_queries: device pointers only");
+  BcastSpec b{};
+  b.n = n_dst;
+  for (int i = 0; i < n_dst; ++i) {
+    if (!dst[i]) return fail(ctx, TVC_ERR_INVALID, "tvc_prepare_queries: null destination");
+    b.bf16[i] = static_cast<__nv_bfloat16*>(dst[i]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, launch_prep_rows_bcast(rows, dtype, m, d, (d + kBK - 1) / kBK * kBK,
+                                       (flags & TVC_SEARCH_NORMALIZE_Q) != 0, b, dst_row0, nullptr, st));
+  return TVC_OK;
+}
+
+int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, int64_t m, int32_t d,
+                          int32_t parts, int32_t kp, const float* cand_val, const int64_t* cand_idx, int32_t k,
+                          float threshold, float* out_sim, int64_t* out_idx, void* stream) {
+  if (!ctx || !g || g->ctx != ctx) return fail(ctx, TVC_ERR_INVALID, "tvc_rerank_candidates: bad handle");
+  if (m < 0 || d != g->d || parts < 1 || kp < 1 || kp > 64 || k < 1 || k > kp ||
+      (m > 0 && (!queries || !cand_val || !cand_idx || !out_sim || !out_idx)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_rerank_candidates: bad argument");
+  if (m == 0) return TVC_OK;
+  if (!is_device_ptr(queries) || !is_device_ptr(cand_val) || !is_device_ptr(cand_idx) || !is_device_ptr(out_sim) ||
+      !is_device_ptr(out_idx))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_rerank_candidates: device pointers only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  RowSource src;
+  fill_row_source(&src, g);
+  TVC_CUDA(ctx, launch_rerank_merged(cand_val, cand_idx, m, parts, kp, k, queries, src, d, threshold, out_sim,
+                                     out_idx, st));
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------- peer buffers
+int tvc_peer_alloc(tvc_ctx* ctx, int64_t bytes, void** ptr, void* handle) {
+  if (!ctx || bytes <= 0 || !ptr || !handle) return fail(ctx, TVC_ERR_INVALID, "tvc_peer_alloc: bad argument");
+  DeviceGuard guard(ctx->device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, static_cast<size_t>(bytes)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, TVC_ERR_OOM, "tvc_peer_alloc: out of device memory");
+  }
+  TVC_CUDA(ctx, cudaMemset(p, 0, static_cast<size_t>(bytes)));
+  TVC_CUDA(ctx, cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle), p));
+  *ptr = p;
+  return TVC_OK;
+}
+
+int tvc_peer_open(tvc_ctx* ctx, const void* handle, void** ptr) {
+  if (!ctx || !handle || !ptr) return fail(ctx, TVC_ERR_INVALID, "tvc_peer_open: bad argument");
+  DeviceGuard guard(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  TVC_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return TVC_OK;
+}
+
+int tvc_peer_close(tvc_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return TVC_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+  return TVC_OK;
+}
+
+int tvc_peer_free(tvc_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return TVC_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, cudaFree(ptr));
   return TVC_OK;
 }
 

@@ -63,6 +63,46 @@ __global__ void prep_rows_kernel(const T* __restrict__ rows, long long n, int d,
   }
 }
 
+// Vectorised form for fp32 rows that need no normalisation (the query batches of the TVC flow):
+// each lane converts 8 consecutive elements per trip - two 128-bit loads, one 128-bit bf16 store per
+// destination, two 128-bit fp32 stores.  With several destinations the bf16 rows are BROADCAST: every
+// pointer of `dst` is the query buffer of one rank of the box (own HBM or a peer's, mapped through
+// CUDA IPC), so one rank converts its slice of the batch once and the stores over NVLink replace
+// both the replicated conversion and an all-gather of the operand.
+__global__ void __launch_bounds__(256)
+prep_rows_f32v_kernel(const float* __restrict__ rows, long long n, int d, int d_pad, const BcastSpec dst,
+                      long long dst_row0, float* __restrict__ out_f32) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int chunks = d_pad >> 3, live = d >> 3;   // d % 8 == 0 (launcher)
+  for (long long r = warp0; r < n; r += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(rows + r * d);
+    for (int c = lane; c < chunks; c += 32) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (c < live) {
+        a = src[2 * c];
+        b = src[2 * c + 1];
+        if (out_f32) {
+          float4* o = reinterpret_cast<float4*>(out_f32 + r * d);
+          o[2 * c] = a;
+          o[2 * c + 1] = b;
+        }
+      }
+      union {
+        __nv_bfloat162 h[4];
+        uint4 u;
+      } pk;
+      pk.h[0] = __floats2bfloat162_rn(a.x, a.y);
+      pk.h[1] = __floats2bfloat162_rn(a.z, a.w);
+      pk.h[2] = __floats2bfloat162_rn(b.x, b.y);
+      pk.h[3] = __floats2bfloat162_rn(b.z, b.w);
+      for (int t = 0; t < dst.n; ++t)
+        reinterpret_cast<uint4*>(dst.bf16[t] + (dst_row0 + r) * d_pad)[c] = pk.u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- ordering
 // Total order on (value, index): a is better when its value is larger, ties to the lower index.
 __device__ __forceinline__ bool better(float v1, long long i1, float v2, long long i2) {
@@ -204,6 +244,146 @@ rerank_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ ca
       }
     } else {
       bi = LLONG_MIN;  // exhausted (or below threshold: everything after is too)
+      if (lane == 0) {
+        out_sim[row * k + j] = -INFINITY;
+        out_idx[row * k + j] = -1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- sharded search
+// Phase 1 on every shard: best kp GEMM candidates of each query row over the shard's ranges, written
+// with GLOBAL indices either to a local [m, kp] list or straight into the receive buffer of the rank
+// that owns the row's query slice (peer HBM mapped through CUDA IPC: the candidate exchange is this
+// kernel's store stream over NVLink, there is no collective).
+__global__ void __launch_bounds__(kRerankWarps * 32)
+select_candidates_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                         long long m, int splits, int kp, long long row_offset, const ScatterSpec sc,
+                         float* __restrict__ out_val, long long* __restrict__ out_idx) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
+  if (row >= m) return;
+  const int ncand = splits * kp;
+  const float* cv = cand_val + row * ncand;
+  const int32_t* ci = cand_idx + row * ncand;
+  float* dv;
+  long long* di;
+  if (sc.n_slices > 0) {
+    const long long j = row / sc.rows_per_slice, lr = row - j * sc.rows_per_slice;
+    const long long rows_j = min(sc.rows_per_slice, m - j * sc.rows_per_slice);
+    const long long o = (static_cast<long long>(sc.slot) * rows_j + lr) * kp;
+    dv = sc.val[j] + o;
+    di = sc.idx[j] + o;
+  } else {
+    dv = out_val + row * kp;
+    di = out_idx + row * kp;
+  }
+  if (splits == 1) {
+    for (int e = lane; e < kp; e += 32) {
+      const int i = ci[e];
+      dv[e] = i >= 0 ? cv[e] : -INFINITY;
+      di[e] = i >= 0 ? i + row_offset : -1;
+    }
+    return;
+  }
+  float bv = INFINITY;
+  long long bi = -1;
+  int t = 0;
+  for (; t < kp; ++t) {
+    float v;
+    long long i;
+    const bool ok = warp_next_best(
+        ncand, bv, bi, [&](int e, float& vv, long long& ii) { vv = cv[e]; ii = ci[e]; }, v, i);
+    if (!ok) break;
+    if (lane == 0) {
+      dv[t] = v;
+      di[t] = i + row_offset;
+    }
+    bv = v;
+    bi = i;
+  }
+  for (int e = t + lane; e < kp; e += 32) {
+    dv[e] = -INFINITY;
+    di[e] = -1;
+  }
+}
+
+// Phase 2 on the owner of a query slice: the `parts` lists of a row ([parts, m, kp], global indices)
+// are merged to the kp best by GEMM score, re-scored in fp32 from the masters of the owning shards
+// (own HBM or peer HBM over NVLink) and the k best leave ordered (score desc, index asc) - the same
+// selection the single-GPU rerank makes over its gallery ranges.
+__global__ void __launch_bounds__(kRerankWarps * 32)
+rerank_merged_kernel(const float* __restrict__ cand_val, const long long* __restrict__ cand_idx,
+                     long long m, int parts, int kp, int k, const float* __restrict__ q_f32,
+                     const RowSource src, int d, float threshold, float* __restrict__ out_sim,
+                     long long* __restrict__ out_idx) {
+  __shared__ float s_val[kRerankWarps][kMaxKp];
+  __shared__ long long s_idx[kRerankWarps][kMaxKp];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
+  if (row >= m) return;
+  const int ncand = parts * kp;
+  auto fetch = [&](int e, float& vv, long long& ii) {
+    const int pt = e / kp, t = e - pt * kp;
+    const long long o = (static_cast<long long>(pt) * m + row) * kp + t;
+    vv = cand_val[o];
+    ii = cand_idx[o];
+  };
+  {
+    float bv = INFINITY;
+    long long bi = -1;
+    int t = 0;
+    for (; t < kp; ++t) {
+      float v;
+      long long i;
+      if (!warp_next_best(ncand, bv, bi, fetch, v, i)) break;
+      if (lane == 0) {
+        s_val[w][t] = v;
+        s_idx[w][t] = i;
+      }
+      bv = v;
+      bi = i;
+    }
+    for (int e = t + lane; e < kp; e += 32) {
+      s_val[w][e] = -INFINITY;
+      s_idx[w][e] = -1;
+    }
+  }
+  __syncwarp();
+  const float* q = q_f32 + row * d;
+  for (int t = 0; t < kp; ++t) {
+    const long long gi = s_idx[w][t];
+    if (gi < 0) continue;  // warp-uniform
+    int part = -1;
+    for (int pp = 0; pp < src.nparts; ++pp)
+      if (gi >= src.off[pp] && gi < src.off[pp] + src.n[pp]) part = pp;
+    if (part < 0 || src.f32[part] == nullptr) {
+      if (lane == 0) s_idx[w][t] = -1;
+      continue;
+    }
+    const float s = warp_dot_f32(q, src.f32[part] + (gi - src.off[part]) * d, d);
+    if (lane == 0) s_val[w][t] = s;
+  }
+  __syncwarp();
+  float bv = INFINITY;
+  long long bi = -1;
+  for (int j = 0; j < k; ++j) {
+    float v = -INFINITY;
+    long long i = -1;
+    bool ok = false;
+    if (bi != LLONG_MIN)
+      ok = warp_next_best(
+          kp, bv, bi, [&](int e, float& vv, long long& ii) { vv = s_val[w][e]; ii = s_idx[w][e]; }, v, i);
+    if (ok && v >= threshold) {
+      bv = v;
+      bi = i;
+      if (lane == 0) {
+        out_sim[row * k + j] = v;
+        out_idx[row * k + j] = i;
+      }
+    } else {
+      bi = LLONG_MIN;
       if (lane == 0) {
         out_sim[row * k + j] = -INFINITY;
         out_idx[row * k + j] = -1;
@@ -420,31 +600,55 @@ __global__ void gather_rows_kernel(const float* __restrict__ g_f32,
 }  // namespace
 
 // =============================================================================== launchers
-cudaError_t launch_prep_rows(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
-                             __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t stream) {
+cudaError_t launch_prep_rows_bcast(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
+                                   const BcastSpec& dst, int64_t dst_row0, float* out_f32, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const int block = 256;
   long long blocks = (n * 32 + block - 1) / block;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const int grid = static_cast<int>(blocks);
-  switch (dtype) {
-    case TVC_F32:
-      prep_rows_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(rows), n, d, d_pad,
-                                                          normalize, out_bf16, out_f32);
-      break;
-    case TVC_BF16:
-      prep_rows_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
-          static_cast<const __nv_bfloat16*>(rows), n, d, d_pad, normalize, out_bf16, out_f32);
-      break;
-    case TVC_F16:
-      prep_rows_kernel<__half><<<grid, block, 0, stream>>>(static_cast<const __half*>(rows), n, d,
-                                                           d_pad, normalize, out_bf16, out_f32);
-      break;
-    default:
-      return cudaErrorInvalidValue;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  bool vec = dtype == TVC_F32 && !normalize && (d % 8) == 0 && al16(rows) && (!out_f32 || al16(out_f32));
+  for (int t = 0; t < dst.n; ++t) vec = vec && al16(dst.bf16[t]);
+  if (vec) {
+    prep_rows_f32v_kernel<<<grid, block, 0, stream>>>(static_cast<const float*>(rows), n, d, d_pad, dst, dst_row0,
+                                                      out_f32);
+    note_launch();
+    return cudaGetLastError();
   }
-  note_launch();
+  // general path: one launch per destination (rows are re-read; only odd shapes / dtypes get here)
+  for (int t = 0; t < (dst.n > 0 ? dst.n : 1); ++t) {
+    __nv_bfloat16* ob = dst.n > 0 ? dst.bf16[t] + dst_row0 * d_pad : nullptr;
+    float* of = t == 0 ? out_f32 : nullptr;
+    switch (dtype) {
+      case TVC_F32:
+        prep_rows_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(rows), n, d, d_pad, normalize,
+                                                            ob, of);
+        break;
+      case TVC_BF16:
+        prep_rows_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(rows), n, d,
+                                                                    d_pad, normalize, ob, of);
+        break;
+      case TVC_F16:
+        prep_rows_kernel<__half><<<grid, block, 0, stream>>>(static_cast<const __half*>(rows), n, d, d_pad,
+                                                             normalize, ob, of);
+        break;
+      default:
+        return cudaErrorInvalidValue;
+    }
+    note_launch();
+  }
   return cudaGetLastError();
+}
+
+cudaError_t launch_prep_rows(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
+                             __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t stream) {
+  BcastSpec dst{};
+  if (out_bf16) {
+    dst.n = 1;
+    dst.bf16[0] = out_bf16;
+  }
+  return launch_prep_rows_bcast(rows, dtype, n, d, d_pad, normalize, dst, 0, out_f32, stream);
 }
 
 cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
@@ -456,6 +660,31 @@ cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_
   const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
   rerank_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(
       cand_val, cand_idx, m, splits, kp, k, q_f32, g_f32, d, threshold, global_row_offset, out_sim,
+      reinterpret_cast<long long*>(out_idx));
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
+                                     int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
+                                     int64_t* out_idx, cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
+  select_candidates_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(cand_val, cand_idx, m, splits, kp,
+                                                                   global_row_offset, sc, out_val,
+                                                                   reinterpret_cast<long long*>(out_idx));
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rerank_merged(const float* cand_val, const int64_t* cand_idx, int64_t m, int parts, int kp,
+                                 int k, const float* q_f32, const RowSource& src, int d, float threshold,
+                                 float* out_sim, int64_t* out_idx, cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  if (kp > kMaxKp) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
+  rerank_merged_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(
+      cand_val, reinterpret_cast<const long long*>(cand_idx), m, parts, kp, k, q_f32, src, d, threshold, out_sim,
       reinterpret_cast<long long*>(out_idx));
   note_launch();
   return cudaGetLastError();

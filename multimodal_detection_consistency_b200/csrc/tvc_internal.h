@@ -55,6 +55,15 @@ cudaError_t launch_gemm_store(const CUtensorMap& tmap_q, const CUtensorMap& tmap
 cudaError_t launch_prep_rows(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
                              __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t stream);
 
+// same, with the bf16 rows written at row `dst_row0` of up to kMaxParts destinations (own / peer query buffers)
+constexpr int kMaxParts = 16;
+struct BcastSpec {
+  int n;
+  __nv_bfloat16* bf16[kMaxParts];
+};
+cudaError_t launch_prep_rows_bcast(const void* rows, int dtype, int64_t n, int d, int d_pad, bool normalize,
+                                   const BcastSpec& dst, int64_t dst_row0, float* out_f32, cudaStream_t stream);
+
 // select top-kp by GEMM score over splits, re-score in fp32 from the masters, emit ordered top-k.
 cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
                           int kp, int k, const float* q_f32, const float* g_f32, int d,
@@ -74,7 +83,6 @@ cudaError_t launch_gather_rows(const float* g_f32, const __nv_bfloat16* g_bf16, 
 
 // Where the rows behind global indices live: up to kMaxParts row shards, each resident in this GPU's
 // HBM or in a PEER GPU's HBM mapped through CUDA IPC (read over NVLink by the kernel itself).
-constexpr int kMaxParts = 16;
 struct RowSource {
   int nparts;
   int d_pad;
@@ -83,6 +91,24 @@ struct RowSource {
   long long off[kMaxParts];               // global index of the shard's first row
   long long n[kMaxParts];                 // rows in the shard
 };
+
+// Destination of the candidates of a sharded search: row r belongs to query slice r / rows_per_slice,
+// whose owner's receive buffers [n_slices, rows_in_slice, kp] (local or peer-mapped) are val/idx[j].
+struct ScatterSpec {
+  int n_slices;            // 0: no scatter, write the local [m, kp] lists
+  int slot;                // this shard's position in every receive buffer
+  long long rows_per_slice;
+  float* val[kMaxParts];
+  long long* idx[kMaxParts];
+};
+
+cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
+                                     int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
+                                     int64_t* out_idx, cudaStream_t stream);
+
+cudaError_t launch_rerank_merged(const float* cand_val, const int64_t* cand_idx, int64_t m, int parts, int kp,
+                                 int k, const float* q_f32, const RowSource& src, int d, float threshold,
+                                 float* out_sim, int64_t* out_idx, cudaStream_t stream);
 
 struct ConsistencyEmbArgs {
   const float* img;

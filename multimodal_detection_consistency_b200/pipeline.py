@@ -57,6 +57,9 @@ class CudaEngine:
     def k_occurrence(self, idx, n_bins, counts):
         return self.ctx.k_occurrence(idx, n_bins, 0, counts)
 
+    def make_exchange(self, dist, group, world, rank):
+        return PeerExchange(self.ctx, dist, group, world, rank)
+
     def peer_group(self, gallery, total_rows, dist, group, world, rank):
         """[own shard + CUDA-IPC views of every peer's fp32 master]: kernel (b) then reads rows of other
         shards straight from peer HBM over NVLink instead of staging them with collectives."""
@@ -66,6 +69,97 @@ class CudaEngine:
         for r, (handle, n, off) in enumerate(info):
             parts.append(gallery if r == rank else N.Gallery.import_ipc(handle, n, gallery.dim, off, self.ctx))
         return N.Gallery.group(parts)
+
+
+class PeerExchange:
+    """Candidate exchange of the sharded search without a data-path collective: every rank owns a
+    double-buffered receive area [2][P, rows_in_slice, KP] (values + indices) allocated through
+    libtvc and mapped by all peers with CUDA IPC; phase 1 of the search stores each row's candidates
+    straight into the owner's area over NVLink, one stream-ordered barrier (a 4-byte all-reduce)
+    separates it from phase 2, which re-ranks on the owner from local + peer fp32 masters."""
+
+    def __init__(self, ctx, dist, group, world, rank):
+        self.ctx, self.dist, self.group, self.world, self.rank = ctx, dist, group, world, rank
+        self.areas = {}           # (tag, rows_per_slice, kp) -> dict(own=[(val, idx)] * 2, peers=[[(val, idx)] * 2] * P)
+        self.parity = {}
+        self._token = None
+
+    def _area(self, tag, rows_per_slice: int, kp: int):
+        key = (tag, rows_per_slice, kp)
+        area = self.areas.get(key)
+        if area is not None:
+            return area
+        n = self.world * rows_per_slice * kp
+        vb, ib = n * 4, n * 8
+        own = [self.ctx.peer_alloc(2 * (vb + ib))]
+        ptr, handle = own[0]
+        info = [None] * self.world
+        self.dist.all_gather_object(info, handle, group=self.group)
+        bases = [ptr if r == self.rank else self.ctx.peer_open(h) for r, h in enumerate(info)]
+        # layout of one rank's area: [val buf0 | val buf1 | idx buf0 | idx buf1]
+        area = dict(bases=bases, vb=vb, ib=ib, own=ptr)
+        self.areas[key] = area
+        self.parity[key] = 0
+        return area
+
+    def begin_batch(self, rows_slice, q_total: int, v: int, lo: int):
+        """Convert this rank's slice of the query rows to the bf16 GEMM operand once and store it into
+        every rank's query buffer (own HBM + peers over NVLink): after the barrier each rank holds the
+        operand of the WHOLE batch although it only ever saw (or uploaded) its own slice."""
+        d = int(rows_slice.shape[1])
+        per = -(-q_total // self.world)
+        rows_cap = per * self.world * v
+        row_bytes = self.ctx.query_row_bytes(d)
+        key = ("q", rows_cap, d)
+        area = self.areas.get(key)
+        if area is None:
+            nbytes = rows_cap * row_bytes
+            ptr, handle = self.ctx.peer_alloc(2 * nbytes)
+            info = [None] * self.world
+            self.dist.all_gather_object(info, handle, group=self.group)
+            area = dict(bases=[ptr if r == self.rank else self.ctx.peer_open(h) for r, h in enumerate(info)],
+                        nbytes=nbytes, own=ptr)
+            self.areas[key] = area
+            self.parity[key] = 0
+        b = self.parity[key]
+        self.parity[key] = b ^ 1
+        if rows_slice.shape[0] > 0:
+            self.ctx.prepare_queries(rows_slice, [base + b * area["nbytes"] for base in area["bases"]], lo * v)
+        self.barrier(rows_slice.device)
+        self._operand = (area["own"] + b * area["nbytes"], q_total * v)
+
+    def barrier(self, device):
+        import torch
+        if self._token is None:
+            self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.dist.all_reduce(self._token, group=self.group)
+
+    def search(self, tag, gallery, group_gallery, rows_slice, q_total: int, v: int, lo: int, hi: int, k: int,
+               threshold: float):
+        """Global top-k of this rank's query slice [lo, hi): (sims [(hi-lo)*v, k], idx).  rows_slice are
+        the slice's fp32 rows (re-ranking); the GEMM operand is the one begin_batch spread."""
+        per = -(-q_total // self.world)
+        rows_per_slice = per * v
+        kp = self.ctx.candidate_width(k)
+        area = self._area(tag, rows_per_slice, kp)
+        key = (tag, rows_per_slice, kp)
+        b = self.parity[key]
+        self.parity[key] = b ^ 1
+        sc = N.Scatter()
+        sc.n_slices, sc.slot, sc.rows_per_slice = self.world, self.rank, rows_per_slice
+        for r, base in enumerate(area["bases"]):
+            sc.val[r] = base + b * area["vb"]
+            sc.idx[r] = base + 2 * area["vb"] + b * area["ib"]
+        gallery.search_candidates(self._operand, k, sc)
+        self.barrier(rows_slice.device)
+        mine = (hi - lo) * v
+        if mine == 0:
+            import torch
+            return (torch.empty((0, k), dtype=torch.float32, device=rows_slice.device),
+                    torch.empty((0, k), dtype=torch.int64, device=rows_slice.device))
+        own = area["own"]
+        return self.ctx.rerank_candidates(group_gallery, rows_slice, own + b * area["vb"],
+                                          own + 2 * area["vb"] + b * area["ib"], self.world, kp, k, threshold)
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -126,9 +220,16 @@ class TVCScorer:
             if self.bank is not None:
                 self._bank_group = engine.peer_group(self.bank, self.b_total, self.dist, self.group, self.world,
                                                      self.rank)
+        self._exchange = None
+        if self.world > 1 and self._gallery_group is not None and hasattr(engine, "make_exchange"):
+            self._exchange = engine.make_exchange(self.dist, self.group, self.world, self.rank)
         self.track_hubness = track_hubness
         self.k_occurrence = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
         self._host: Dict[str, torch.Tensor] = {}
+        self._dev_stage: Dict[str, torch.Tensor] = {}
+        self._copy_stream = None
+        self.host_chunks = 4                # pieces a host batch is pipelined in (1 = off)
+        self.min_chunk_queries = 2048       # ... when every piece keeps at least this many queries
         self.profile = False            # True: CUDA-event time per phase, read with phase_times()
         self._marks = []
 
@@ -219,7 +320,72 @@ class TVCScorer:
     def score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False):
         """img, txt: [Q, d]; var: [Q, V, d] (host or device, fp32).  In multi-rank mode every rank passes
         the SAME full batch and receives the results of its own contiguous slice of the queries.
-        Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim."""
+        Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim.
+
+        Host batches on one GPU are pipelined: the batch is cut into `host_chunks` pieces, piece c+1 is
+        uploaded on a copy stream while piece c is searched and scored, and piece c's results go back
+        to pinned host memory behind it - only the first upload and the last download are exposed."""
+        host_in = not (isinstance(var, torch.Tensor) and var.device.type == "cuda")
+        if (host_in and self.world == 1 and self.device.type == "cuda" and self.host_chunks > 1
+                and int(var.shape[0]) >= self.host_chunks * self.min_chunk_queries):
+            return self._score_batch_pipelined(img, txt, var, gen, g_cnt, to_host)
+        return self._score_batch(img, txt, var, gen, g_cnt, to_host=to_host)
+
+    def _staging(self, name: str, shape, dtype) -> torch.Tensor:
+        buf = self._dev_stage.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._dev_stage[name] = buf
+        return buf
+
+    def _score_batch_pipelined(self, img, txt, var, gen, g_cnt, to_host: bool):
+        q_total = int(var.shape[0])
+        c_n = self.host_chunks
+        bounds = [(q_total * c // c_n, q_total * (c + 1) // c_n) for c in range(c_n)]
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(main)                     # the staging buffers may still be read by the previous call
+        srcs = dict(img=(img, torch.float32), txt=(txt, torch.float32), var=(var, torch.float32))
+        if gen is not None:
+            srcs["gen"] = (gen, torch.float32)
+        if g_cnt is not None:
+            srcs["g_cnt"] = (g_cnt, torch.int32)
+        host = {n: (t if isinstance(t, torch.Tensor) else torch.as_tensor(t)) for n, (t, _) in srcs.items()}
+        dev = {n: self._staging(n, host[n].shape, dt) for n, (_, dt) in srcs.items()}
+        events = []
+        with torch.cuda.stream(cs):
+            for a, b in bounds:
+                for n in ("var", "img", "txt", "gen", "g_cnt"):     # var first: the search waits on it
+                    if n in dev:
+                        dev[n][a:b].copy_(host[n][a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        pieces = []
+        for (a, b), ev in zip(bounds, events):
+            main.wait_event(ev)
+            o = self._score_batch(dev["img"][a:b], dev["txt"][a:b], dev["var"][a:b],
+                                  dev["gen"][a:b] if "gen" in dev else None,
+                                  dev["g_cnt"][a:b] if "g_cnt" in dev else None, to_host=False)
+            o.pop("slice")
+            if to_host:
+                for name, t in o.items():
+                    buf = self._pinned(name, torch.empty((q_total,) + tuple(t.shape[1:]), dtype=t.dtype, device="meta"))
+                    buf[a:b].copy_(t, non_blocking=True)
+            else:
+                pieces.append(o)
+        if to_host:
+            main.synchronize()
+            out = {name: self._host[name] for name in o}
+            self._mark("to_host")
+        else:
+            out = {name: torch.cat([pc[name] for pc in pieces], 0) for name in pieces[0]}
+        out["slice"] = (0, q_total)
+        return out
+
+    def _score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False):
         self._mark("begin")
         q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
         if v != self.params.n_variants:
@@ -228,26 +394,43 @@ class TVCScorer:
         qs = hi - lo
         k = self.k
         host_var = not (isinstance(var, torch.Tensor) and var.device.type == self.device.type == "cuda")
-        if self.world > 1 and host_var and self.device.type == "cuda":
-            # every rank holds the same host batch: upload only this rank's slice over PCIe and
-            # all-gather the rest over NVLink (1/world of the host->device traffic per GPU)
-            per = -(-q_total // self.world)
-            piece = torch.zeros((per, v, d), dtype=torch.float32, device=self.device)
-            if qs > 0:
-                piece[:qs].copy_(torch.as_tensor(var[lo:hi]), non_blocking=True)
-            full = torch.empty((self.world * per, v, d), dtype=torch.float32, device=self.device)
-            self.dist.all_gather_into_tensor(full, piece, group=self.group)
-            var = full[:q_total]
-        else:
-            var = self._dev(var)
-        rows_all = var.view(q_total * v, d)
-        g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
-        self._mark("search_gallery")
         b_sim = b_idx = None
-        if self.bank is not None:
-            b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
-            self._mark("search_bank")
-        img_s, txt_s, var_s = self._dev(img[lo:hi]), self._dev(txt[lo:hi]), var[lo:hi]
+        if self.world > 1 and self._exchange is not None:
+            # peer-memory path: this rank only touches (uploads) ITS slice of the batch.  The bf16 operand
+            # of the whole batch is assembled in every rank's HBM by the prepare kernel's peer stores, the
+            # candidates are stored into the slice owners' HBM, and the owners re-rank.
+            var_s = self._dev(var[lo:hi])
+            rows_s = var_s.view(qs * v, d)
+            ex = self._exchange
+            ex.begin_batch(rows_s, q_total, v, lo)
+            g_sim, g_idx = ex.search("gallery", self.gallery, self._gallery_group, rows_s, q_total, v, lo, hi, k,
+                                     -math.inf)
+            self._mark("search_gallery")
+            if self.bank is not None:
+                b_sim, b_idx = ex.search("bank", self.bank, self._bank_group, rows_s, q_total, v, lo, hi, k,
+                                         self.bank_threshold)
+                self._mark("search_bank")
+        else:
+            if self.world > 1 and host_var and self.device.type == "cuda":
+                # every rank holds the same host batch: upload only this rank's slice over PCIe and
+                # all-gather the rest over NVLink (1/world of the host->device traffic per GPU)
+                per = -(-q_total // self.world)
+                piece = torch.zeros((per, v, d), dtype=torch.float32, device=self.device)
+                if qs > 0:
+                    piece[:qs].copy_(torch.as_tensor(var[lo:hi]), non_blocking=True)
+                full = torch.empty((self.world * per, v, d), dtype=torch.float32, device=self.device)
+                self.dist.all_gather_into_tensor(full, piece, group=self.group)
+                var = full[:q_total]
+            else:
+                var = self._dev(var)
+            rows_all = var.view(q_total * v, d)
+            g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
+            self._mark("search_gallery")
+            if self.bank is not None:
+                b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
+                self._mark("search_bank")
+            var_s = var[lo:hi]
+        img_s, txt_s = self._dev(img[lo:hi]), self._dev(txt[lo:hi])
         gen_s = self._dev(gen[lo:hi]) if gen is not None else None
         gcnt_s = self._dev(g_cnt[lo:hi], torch.int32) if g_cnt is not None else None
         ret_idx = g_idx.view(qs, v * k)

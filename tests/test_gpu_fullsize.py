@@ -129,3 +129,27 @@ def test_1m_gallery_properties(tvc_ctx):
     assert float((ref.values - sims[sel]).abs().max()) <= 1e-3
     diff = (ref.values - sims[sel]).abs()
     assert (not bool((~same).any())) or float(diff[~same].max()) <= 1e-3
+
+
+def test_pipelined_host_batches_equal_one_shot(tvc_ctx):
+    """TVCScorer's chunked upload/compute/download pipeline returns exactly the one-shot result."""
+    import torch
+    from multimodal_detection_consistency_b200.pipeline import TVCScorer
+    d = 256
+    g = O.synth_gallery(20000, d, seed=4)
+    bank = O.synth_gallery(3000, d, seed=5)
+    img, txt, var = (torch.from_numpy(x).pin_memory() for x in O.synth_queries(g, 1000, 5, seed=6))
+    outs = []
+    for chunks in (1, 4):
+        sc = TVCScorer(g, bank, k=10, device="cuda:0")
+        sc.host_chunks, sc.min_chunk_queries = chunks, 100
+        o = sc.score_batch(img, txt, var, to_host=True)
+        outs.append(({k: v.clone() for k, v in o.items() if k != "slice"}, sc.k_occurrence.cpu().clone()))
+        assert o["slice"] == (0, 1000)
+        o2 = sc.score_batch(img, txt, var)            # device-resident results, same pipeline
+        torch.cuda.synchronize()
+        for name, t in outs[-1][0].items():
+            assert torch.equal(o2[name].cpu(), t), name
+    for name, t in outs[0][0].items():
+        assert torch.equal(t, outs[1][0][name]), name
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -1,5 +1,6 @@
-"""Two-GPU run of the sharded TVCScorer (NCCL candidate all-to-all, merge kernel, kernel (b) reading
-peer shards over CUDA IPC / NVLink, histogram all-reduce) against the single-GPU result.
+"""Two-GPU run of the sharded TVCScorer (candidates stored into the owner's HBM over NVLink and
+re-ranked there from local + peer fp32 masters, kernel (b) reading peer shards over CUDA IPC,
+histogram all-reduce; a second pass forces the NCCL all-to-all + merge path) against the single-GPU result.
 Skipped on boxes with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
 import os
 import socket
@@ -44,12 +45,17 @@ def _worker(rank, world, port, out_dir):
     sc = TVCScorer(g[glo:ghi], bank[blo:bhi], k=10, total_gallery_rows=len(g), total_bank_rows=len(bank),
                    device=f"cuda:{rank}")
     assert sc._gallery_group is not None          # the peer-memory path, not the staged fetch
-    out = sc.score_batch(img, txt, var, to_host=True)
-    lo, hi = out["slice"]
-    torch.cuda.synchronize()
-    np.savez(Path(out_dir) / f"r{rank}.npz", lo=lo, hi=hi, scores=out["scores"].numpy(), flags=out["flags"].numpy(),
-             topk_idx=out["topk_idx"].numpy(), topk_sim=out["topk_sim"].numpy(), bank_idx=out["bank_idx"].numpy(),
-             hub=sc.k_occurrence.cpu().numpy())
+    assert sc._exchange is not None
+    for tag in ("peer", "peer2", "nccl"):
+        if tag == "nccl":
+            sc._exchange = None                   # candidate all-to-all + merge kernel instead
+        sc.reset_hubness()
+        out = sc.score_batch(img, txt, var, to_host=True)   # (peer2: the second receive buffer)
+        lo, hi = out["slice"]
+        torch.cuda.synchronize()
+        np.savez(Path(out_dir) / f"{tag}_r{rank}.npz", lo=lo, hi=hi, scores=out["scores"].numpy(),
+                 flags=out["flags"].numpy(), topk_idx=out["topk_idx"].numpy(), topk_sim=out["topk_sim"].numpy(),
+                 bank_idx=out["bank_idx"].numpy(), hub=sc.k_occurrence.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,15 +70,16 @@ def test_two_gpu_sharded_equals_single_gpu(tmp_path):
     want = {k: (v.numpy().copy() if hasattr(v, "numpy") else v) for k, v in want.items()}
     hub = ref.k_occurrence.cpu().numpy()
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    covered = 0
-    for r in range(2):
-        z = np.load(tmp_path / f"r{r}.npz")
-        lo, hi = int(z["lo"]), int(z["hi"])
-        covered += hi - lo
-        assert np.array_equal(z["topk_idx"], want["topk_idx"][lo:hi])
-        assert np.array_equal(z["bank_idx"], want["bank_idx"][lo:hi])
-        assert np.abs(z["topk_sim"] - want["topk_sim"][lo:hi]).max() <= 1e-6
-        assert np.abs(z["scores"] - want["scores"][lo:hi]).max() <= 1e-5
-        assert np.array_equal(z["flags"], want["flags"][lo:hi])
-        assert np.array_equal(z["hub"], hub)
-    assert covered == len(img)
+    for tag in ("peer", "peer2", "nccl"):
+        covered = 0
+        for r in range(2):
+            z = np.load(tmp_path / f"{tag}_r{r}.npz")
+            lo, hi = int(z["lo"]), int(z["hi"])
+            covered += hi - lo
+            assert np.array_equal(z["topk_idx"], want["topk_idx"][lo:hi]), tag
+            assert np.array_equal(z["bank_idx"], want["bank_idx"][lo:hi]), tag
+            assert np.abs(z["topk_sim"] - want["topk_sim"][lo:hi]).max() <= 1e-6
+            assert np.abs(z["scores"] - want["scores"][lo:hi]).max() <= 1e-5
+            assert np.array_equal(z["flags"], want["flags"][lo:hi])
+            assert np.array_equal(z["hub"], hub)
+        assert covered == len(img)

@@ -177,3 +177,59 @@ def test_pair_kernel_matches_oracle(tvc_ctx, m, n, d, k):
     if idx_self is not None:
         rs, ri = O.search(g[:m], g, k, skip_self=True)
         _check_topk(sims_self, idx_self, rs, ri, g[:m] @ g.T)
+
+
+@pytest.mark.parametrize("n,d,m,k,shards", [(5000, 256, 700, 10, 3), (40000, 128, 5000, 10, 4), (900, 64, 33, 5, 2)])
+def test_sharded_two_phase_search_equals_unsharded(tvc_ctx, n, d, m, k, shards):
+    """tvc_search_candidates (scatter into per-owner receive buffers) + tvc_rerank_candidates over a
+    gallery group returns exactly what tvc_search returns on the unsharded gallery."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    from multimodal_detection_consistency_b200._native import Scatter
+    g = O.synth_gallery(n, d, seed=7, clusters=32, dup_rate=0.01)
+    q = torch.from_numpy(O.synth_queries(g, m, 1, seed=8)[2].reshape(m, d)).cuda()
+    full = tvc.Gallery(g, ctx=tvc_ctx)
+    want_s, want_i = full.search(q, k)
+    per = -(-n // shards)
+    parts = [tvc.Gallery(g[r * per:(r + 1) * per], global_row_offset=r * per, ctx=tvc_ctx) for r in range(shards)]
+    group = tvc.Gallery.group(parts)
+    kp = tvc_ctx.candidate_width(k)
+    owners = 3                                             # query slices (the "ranks" that re-rank)
+    rps = -(-m // owners)
+    val = [torch.full((shards, min(rps, max(0, m - j * rps)), kp), float("nan"), device="cuda") for j in range(owners)]
+    idx = [torch.full((shards, min(rps, max(0, m - j * rps)), kp), -7, dtype=torch.int64, device="cuda")
+           for j in range(owners)]
+    # the bf16 operand is prepared once, slice by slice, into two "rank" buffers (broadcast form)
+    d_pad = tvc_ctx.query_row_bytes(d) // 2
+    op = [torch.zeros((m, d_pad), dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    for j in range(owners):
+        rows = q[j * rps:(j + 1) * rps]
+        if rows.shape[0]:
+            tvc_ctx.prepare_queries(rows, [o.data_ptr() for o in op], j * rps)
+    torch.cuda.synchronize()
+    assert torch.equal(op[0], op[1])
+    assert torch.equal(op[0][:, :d], q.to(torch.bfloat16)) and not op[0][:, d:].any()
+    for r, part in enumerate(parts):
+        sc = Scatter()
+        sc.n_slices, sc.slot, sc.rows_per_slice = owners, r, rps
+        for j in range(owners):
+            sc.val[j], sc.idx[j] = val[j].data_ptr(), idx[j].data_ptr()
+        # odd shards search the prepared operand, even shards the raw fp32 rows: same candidates
+        part.search_candidates((op[r % 2].data_ptr(), m) if r % 2 else q, k, sc)
+    got_s, got_i = [], []
+    for j in range(owners):
+        rows = q[j * rps:(j + 1) * rps]
+        if rows.shape[0] == 0:
+            continue
+        s, i = tvc_ctx.rerank_candidates(group, rows, val[j].data_ptr(), idx[j].data_ptr(), shards, kp, k)
+        got_s.append(s)
+        got_i.append(i)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(got_i), want_i)
+    assert torch.equal(torch.cat(got_s), want_s)
+    # local (non-scattered) candidate lists: global indices, sorted by GEMM score
+    cv, ci = parts[1].search_candidates(q, k)
+    torch.cuda.synchronize()
+    ok = ci >= 0
+    assert ((ci[ok] >= per) & (ci[ok] < 2 * per)).all()
+    assert (cv[:, :-1] >= cv[:, 1:]).all()

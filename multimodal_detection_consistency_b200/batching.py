@@ -1,0 +1,113 @@
+"""Micro-batching of single-sample calls.
+
+The reference's production entry feeds the hot path ONE sample per Python call from a pool of worker
+threads (`ThreadPoolExecutor(max_workers=4)`, src/pipeline.py:42,288,555-560 -> process_single ->
+`retrieve_images_by_text(text, top_k=5)` :450-476 and `detect_adversarial(image, text)` :519-526);
+its own `batch_*` methods are loops over the single call (src/retrieval.py:724-762,
+src/detector.py:711-734).  On a GPU every such call is one encoder launch plus one search launch
+that streams the whole gallery for a single row, so `pipeline.py` - which must stay unchanged - is
+launch-latency bound at one sample per launch.
+
+`MicroBatcher` coalesces the calls that are in flight at the same time into one batched call
+without a background thread: the first caller of a round becomes the leader, waits a bounded
+moment for followers (only when concurrency has actually been observed, so a lone sequential
+caller pays nothing), runs the batched function once and hands every caller its own result.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from typing import Any, Callable, Hashable, List, Optional, Sequence
+
+
+class _Round:
+    __slots__ = ("items", "results", "error", "done", "closed")
+
+    def __init__(self):
+        self.items: List[Any] = []
+        self.results: Optional[Sequence[Any]] = None
+        self.error: Optional[BaseException] = None
+        self.done = threading.Event()
+        self.closed = False
+
+
+class MicroBatcher:
+    """submit(item) -> batch_fn([items...])[position of item]; thread-safe, leader/follower.
+
+    batch_fn(key, items) must return one result per item, in order.  Calls with different `key`s
+    (e.g. different top_k) are never mixed.  max_batch bounds a round; max_delay_s bounds how long a
+    leader waits for followers; idle_s is how recently a second thread must have been seen for the
+    leader to wait at all."""
+
+    def __init__(self, batch_fn: Callable[[Hashable, List[Any]], Sequence[Any]], max_batch: int = 256,
+                 max_delay_s: float = 0.002, idle_s: float = 0.050):
+        self.batch_fn = batch_fn
+        self.max_batch = int(max_batch)
+        self.max_delay_s = float(max_delay_s)
+        self.idle_s = float(idle_s)
+        self._lock = threading.Lock()
+        self._cv = threading.Condition(self._lock)
+        self._open = {}                 # key -> _Round collecting items
+        self._last_thread = None
+        self._last_other = -1e30        # last time a call came from a thread other than the previous one
+        self._inside = 0                # callers currently inside submit()
+        self.rounds = 0                 # statistics: batched calls made / items served
+        self.items = 0
+
+    def submit(self, item: Any, key: Hashable = None) -> Any:
+        now = time.monotonic()
+        me = threading.get_ident()
+        with self._cv:
+            if self._last_thread is not None and self._last_thread != me:
+                self._last_other = now
+            self._last_thread = me
+            self._inside += 1
+            rnd = self._open.get(key)
+            leader = rnd is None
+            if leader:
+                rnd = self._open[key] = _Round()
+            pos = len(rnd.items)
+            rnd.items.append(item)
+            if len(rnd.items) >= self.max_batch:
+                rnd.closed = True
+                self._open.pop(key, None)
+                self._cv.notify_all()
+            if leader:
+                # wait for followers only when other threads are around
+                concurrent = (self._inside > 1) or (now - self._last_other) < self.idle_s
+                deadline = now + (self.max_delay_s if concurrent else 0.0)
+                while not rnd.closed:
+                    left = deadline - time.monotonic()
+                    if left <= 0:
+                        break
+                    self._cv.wait(left)
+                if not rnd.closed:
+                    rnd.closed = True
+                    self._open.pop(key, None)
+        try:
+            if leader:
+                try:
+                    out = self.batch_fn(key, rnd.items)
+                    if len(out) != len(rnd.items):
+                        raise RuntimeError(f"batch function returned {len(out)} results for {len(rnd.items)} items")
+                    rnd.results = out
+                except BaseException as e:  # noqa: BLE001 - handed to every caller of the round
+                    rnd.error = e
+                finally:
+                    with self._lock:
+                        self.rounds += 1
+                        self.items += len(rnd.items)
+                    rnd.done.set()
+            else:
+                rnd.done.wait()
+            if rnd.error is not None:
+                raise rnd.error
+            return rnd.results[pos]
+        finally:
+            with self._lock:
+                self._inside -= 1
+
+    def stats(self):
+        with self._lock:
+            return dict(rounds=self.rounds, items=self.items,
+                        mean_batch=(self.items / self.rounds) if self.rounds else 0.0)

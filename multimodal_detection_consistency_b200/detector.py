@@ -21,6 +21,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native as N
+from .batching import MicroBatcher
 
 logger = logging.getLogger(__name__)
 
@@ -73,6 +74,9 @@ class AdversarialDetector:
         self.detection_stats = {"total_detections": 0, "cache_hits": 0, "detection_time": 0.0,
                                 "method_usage": {m: 0 for m in self.config.detection_methods}}
         self._ctx = None
+        # single-sample calls made concurrently are coalesced (batching.MicroBatcher)
+        self.micro_batch = True
+        self._batcher = MicroBatcher(lambda key, items: self._detect_group(items, list(key)), max_batch=256)
 
     # component accessors keep the reference's names (src/detector.py:257-343)
     def _get_clip_model(self):
@@ -117,20 +121,29 @@ class AdversarialDetector:
                 "scores": scores, "variant_similarities": sv, "reference_similarities": sg, "methods_used": active}
 
     # ------------------------------------------------------------------ reference-shaped entry
-    def _encode_sample(self, image, text, methods):
+    def _encode_samples(self, samples: Sequence[Tuple[Any, str]], methods):
+        """Variants / references per sample (upstream generators), then ONE text-encoder call and ONE
+        image-encoder call for the whole group (the reference encodes every string and image in its own
+        call, src/detector.py:461-470,531)."""
         clip = self._get_clip_model()
         if clip is None:
             raise ValueError("no clip_model: pass one to AdversarialDetector or use detect_embeddings")
-        variants: List[str] = []
-        if "text_variants" in methods and self._get_text_augmenter() is not None:
-            variants = list(self._get_text_augmenter().generate_variants(text) or [])
-        refs, gen_time = [], 0.0
-        if "sd_reference" in methods and self._get_sd_generator() is not None:
-            r = self._get_sd_generator().generate_reference_images(text, num_images=self.config.num_reference_images)
-            refs, gen_time = list(r.get("images", [])), r.get("generation_time", 0.0)
-        temb = _np(clip.encode_text([text] + variants))
-        iemb = _np(clip.encode_image([image] + refs))
-        return temb, iemb, variants, refs, gen_time
+        aug = self._get_text_augmenter() if "text_variants" in methods else None
+        sd = self._get_sd_generator() if "sd_reference" in methods else None
+        texts, images, meta = [], [], []
+        for image, text in samples:
+            variants = list(aug.generate_variants(text) or []) if aug is not None else []
+            refs, gen_time = [], 0.0
+            if sd is not None:
+                r = sd.generate_reference_images(text, num_images=self.config.num_reference_images)
+                refs, gen_time = list(r.get("images", [])), r.get("generation_time", 0.0)
+            meta.append((len(texts), 1 + len(variants), len(images), 1 + len(refs), variants, refs, gen_time))
+            texts += [text] + variants
+            images += [image] + refs
+        temb_all = _np(clip.encode_text(texts))
+        iemb_all = _np(clip.encode_image(images))
+        return [(temb_all[t0:t0 + tn], iemb_all[i0:i0 + inn], variants, refs, gen_time)
+                for t0, tn, i0, inn, variants, refs, gen_time in meta]
 
     def detect_adversarial(self, image, text: str, methods: Optional[List[str]] = None) -> Dict[str, Any]:
         """src/detector.py:345-439."""
@@ -141,7 +154,12 @@ class AdversarialDetector:
                 self.detection_stats["cache_hits"] += 1
                 return self.detection_cache[key]
             t0 = time.time()
-            result = self._detect_group([(image, text)], methods)[0]
+            if self.micro_batch:
+                # concurrent callers (the pipeline's worker threads, src/pipeline.py:555-560) share one
+                # encoder call and one kernel launch
+                result = dict(self._batcher.submit((image, text), key=tuple(methods)))
+            else:
+                result = self._detect_group([(image, text)], methods)[0]
             result["detection_time"] = time.time() - t0
             if self.config.enable_cache:
                 if len(self.detection_cache) >= self.config.cache_size:
@@ -160,7 +178,7 @@ class AdversarialDetector:
 
     def _detect_group(self, samples: Sequence[Tuple[Any, str]], methods: Sequence[str]) -> List[Dict[str, Any]]:
         """Encode every sample, bucket by (V, G), one kernel launch per bucket."""
-        enc = [self._encode_sample(im, tx, methods) for im, tx in samples]
+        enc = self._encode_samples(samples, methods)
         buckets: Dict[Tuple[int, int], List[int]] = {}
         for i, (temb, iemb, variants, refs, _) in enumerate(enc):
             buckets.setdefault((len(variants), len(refs)), []).append(i)

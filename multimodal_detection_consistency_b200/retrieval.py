@@ -25,6 +25,7 @@ import numpy as np
 
 from . import faiss_compat
 from ._native import Gallery
+from .batching import MicroBatcher
 
 logger = logging.getLogger(__name__)
 
@@ -201,6 +202,11 @@ class MultiModalRetriever:
         self.text_index: Optional[Gallery] = None
         self.feature_cache: Dict[str, Any] = {}
         self.retrieval_cache: Dict[str, Any] = {}
+        # single-query calls made concurrently (the pipeline's worker threads, src/pipeline.py:555-560)
+        # are coalesced into one encoder call + one search launch (batching.MicroBatcher)
+        self.micro_batch = True
+        self._t2i_batcher = MicroBatcher(lambda k, texts: self.batch_retrieve_images_by_texts(texts, k))
+        self._i2t_batcher = MicroBatcher(lambda k, images: self.batch_retrieve_texts_by_images(images, k))
 
     def _initialize_clip_model(self):
         """The reference builds `src.models.CLIPModel` here (src/retrieval.py:347-369); that package is
@@ -304,6 +310,8 @@ class MultiModalRetriever:
                 return self.retrieval_cache[key]
             if self.image_features is None or self.image_index is None:
                 raise ValueError("image index not built")
+            if self.micro_batch:
+                return self._t2i_batcher.submit(query_text, key=top_k)
             q = _to_numpy(self.clip_model.encode_text([query_text], normalize=self.config.normalize_features))
             idx, scores = self._search_index(self.image_index, q, top_k)
             paths = [self.image_paths[i] for i in idx if i >= 0]
@@ -329,6 +337,11 @@ class MultiModalRetriever:
                 image, key = query_image, f"img2text_pil_{id(query_image)}_{top_k}"
             if self.config.enable_cache and key in self.retrieval_cache:
                 return self.retrieval_cache[key]
+            if self.micro_batch:
+                result = self._i2t_batcher.submit(image, key=top_k)
+                if self.config.enable_cache and result[0]:
+                    self.retrieval_cache[key] = result
+                return result
             q = _to_numpy(self.clip_model.encode_image([image], normalize=self.config.normalize_features))
             idx, scores = self._search_index(self.text_index, q, top_k)
             result = ([self.texts[i] for i in idx if i >= 0], [float(s) for s, i in zip(scores, idx) if i >= 0])

@@ -269,3 +269,56 @@ def test_hubness_api_matches_reference_outputs():
     counts, hub = hubness_scores(f, 10)
     assert counts.sum() == f.shape[0] * 10
     assert np.abs(hub - z["spec_hubness"]).sum() <= 0.01 * z["spec_hubness"].sum() + 1e-12
+
+
+def test_pipeline_worker_threads_are_micro_batched(tvc_ctx):
+    """The reference's pipeline calls retrieve_images_by_text / detect_adversarial one sample at a
+    time from 4 worker threads (src/pipeline.py:288,450-476,519-526,555-560); concurrent calls must
+    return exactly the sequential results while sharing encoder calls and kernel launches."""
+    from concurrent.futures import ThreadPoolExecutor
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(0)
+    d, n = 64, 500
+    gallery = O.l2_normalize(rng.standard_normal((n, d)).astype(np.float32))
+
+    class Clip:                                  # table look-up encoder, counts its calls
+        def __init__(self):
+            self.calls = 0
+
+        def _emb(self, keys):
+            self.calls += 1
+            out = np.stack([np.random.default_rng(abs(hash(str(k))) % (2 ** 31)).standard_normal(d) for k in keys])
+            return O.l2_normalize(out.astype(np.float32))
+
+        def encode_text(self, texts, normalize=True):
+            return self._emb(texts)
+
+        def encode_image(self, images, normalize=True):
+            return self._emb(images)
+
+    class Aug:
+        def generate_variants(self, text):
+            return [f"{text} v{i}" for i in range(5)]
+
+    texts = [f"a photo of thing {i}" for i in range(48)]
+    images = [f"img{i}" for i in range(48)]
+    seq_clip, par_clip = Clip(), Clip()
+    results = {}
+    for tag, clip, workers in (("seq", seq_clip, 1), ("par", par_clip, 8)):
+        r = tvc.MultiModalRetriever(tvc.RetrievalConfig(enable_cache=False), clip_model=clip)
+        r.build_image_index_from_features(gallery, [f"p{i}.jpg" for i in range(n)])
+        det = tvc.AdversarialDetector(tvc.DetectorConfig(detection_methods=["text_variants", "consistency"],
+                                                         enable_cache=False), clip_model=clip, text_augmenter=Aug())
+        r._t2i_batcher.max_delay_s = det._batcher.max_delay_s = 0.02
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            ret = list(ex.map(lambda t: r.retrieve_images_by_text(t, top_k=5), texts))
+            dets = list(ex.map(lambda it: det.detect_adversarial(it[0], it[1]), zip(images, texts)))
+        results[tag] = (ret, dets, r._t2i_batcher.stats(), det._batcher.stats())
+    (ret_s, det_s, _, _), (ret_p, det_p, st_r, st_d) = results["seq"], results["par"]
+    assert ret_p == ret_s and all(len(p) == 5 for p, _ in ret_p)
+    for a, b in zip(det_p, det_s):
+        assert a["is_adversarial"] == b["is_adversarial"]
+        assert abs(a["aggregated_score"] - b["aggregated_score"]) < 1e-6
+        assert a["detection_details"]["text_variants"]["num_variants"] == 5
+    assert st_r["rounds"] < len(texts) and st_d["rounds"] < len(texts)      # calls were coalesced
+    assert par_clip.calls < seq_clip.calls

@@ -20,6 +20,7 @@
  *                                                                                experiments/defenses/text_variants.py:412-451
  *   tvc_k_occurrence               hubness_counts[j] += 1 double loop            references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:43-57
  *                                  (top1 == 0).sum()                             src/attacks/hubness_attack.py:492-496
+ *   tvc_retrieval_metrics          argsort + per-query Python loops (Recall/Precision/NDCG@K, RR, AP)  src/utils/metrics.py:386-574
  *   tvc_merge_topk                 (new) merge of per-shard top-k candidates after the NCCL all-gather
  *   tvc_search_candidates /        (new) sharded search: candidates written into the owner's HBM over NVLink,
  *   tvc_rerank_candidates                re-ranked there from local + peer fp32 masters
@@ -258,6 +259,16 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
                         const float* gen, const int32_t* g_cnt, tvc_gallery* gen_gallery,
                         const int64_t* gen_idx, int32_t n_gen_cand, float* scores, uint8_t* flags,
                         float* out_sv, float* out_sr, float* out_sg, void* stream);
+
+/* Retrieval quality of ranked lists (src/utils/metrics.py:386-574, binary relevance).  topk_idx [q, k]
+ * is the search output (rank order, -1 = unused); the relevant items of query i are
+ * rel_idx[rel_ptr[i] .. rel_ptr[i+1]).  out [q, 2 + 3*n_k] per query: reciprocal rank, average
+ * precision, then recall@K, precision@K, NDCG@K for each of the n_k <= 8 values K <= k.  RR and AP
+ * are those of the full ranking whenever every relevant item lies inside the top-k list (AP is
+ * normalised by the number of relevant items; a first hit beyond k gives RR = 0). */
+int tvc_retrieval_metrics(tvc_ctx* ctx, const int64_t* topk_idx, int64_t q, int32_t k, const int64_t* rel_ptr,
+                          const int64_t* rel_idx, int64_t n_rel, const int32_t* k_values, int32_t n_k, float* out,
+                          void* stream);
 
 /* k-occurrence histogram N_k(j) = #{rows i : j in idx[i, :k]}; idx < 0 or >= n_bins ignored.
  * counts [n_bins] int32; zero_first != 0 clears it before accumulating. `idx_base` is subtracted

@@ -113,6 +113,8 @@ _EXPORTS = {
     "tvc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tvc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tvc_retrieval_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "tvc_k_occurrence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_int, C.c_void_p]),
 }
@@ -318,6 +320,27 @@ class Context:
                                                   int(kp), C.c_void_p(cand_val), C.c_void_p(cand_idx), int(k),
                                                   float(threshold), _ptr(sims), _ptr(idx), _stream_of(q)))
         return sims, idx
+
+    # -- retrieval metrics ---------------------------------------------------------------------
+    def retrieval_metrics(self, topk_idx, rel_ptr, rel_idx, k_values):
+        """Per-query [rr, ap, recall@K.., precision@K.., ndcg@K..] from ranked lists topk_idx [q, k] and a
+        CSR relevance set (rel_ptr [q+1], rel_idx).  numpy in -> numpy out, torch cuda in -> torch cuda out."""
+        q, k = int(topk_idx.shape[0]), int(topk_idx.shape[1])
+        ks = (C.c_int32 * len(k_values))(*[int(x) for x in k_values])
+        cols = 2 + 3 * len(k_values)
+        if _is_torch(topk_idx):
+            import torch
+            topk_idx, rel_ptr, rel_idx = (t.contiguous().to(torch.int64) for t in (topk_idx, rel_ptr, rel_idx))
+            out = torch.empty((q, cols), dtype=torch.float32, device=topk_idx.device)
+            n_rel = int(rel_idx.numel())
+        else:
+            topk_idx, rel_ptr, rel_idx = (np.ascontiguousarray(t, dtype=np.int64) for t in (topk_idx, rel_ptr, rel_idx))
+            out = np.empty((q, cols), np.float32)
+            n_rel = int(rel_idx.size)
+        self.check(self.lib.tvc_retrieval_metrics(self.handle, _ptr(topk_idx), q, k, _ptr(rel_ptr),
+                                                  _ptr(rel_idx) if n_rel else None, n_rel, ks, len(k_values),
+                                                  _ptr(out), _stream_of(topk_idx)))
+        return out
 
     # -- kernel (c) ------------------------------------------------------------------------
     def k_occurrence(self, idx, n_bins: int, idx_base: int = 0, counts=None):

@@ -848,6 +848,42 @@ int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, in
   return TVC_OK;
 }
 
+// ------------------------------------------------------------------------------- retrieval metrics
+int tvc_retrieval_metrics(tvc_ctx* ctx, const int64_t* topk_idx, int64_t q, int32_t k, const int64_t* rel_ptr,
+                          const int64_t* rel_idx, int64_t n_rel, const int32_t* k_values, int32_t n_k, float* out,
+                          void* stream) {
+  if (!ctx || q < 0 || k < 1 || k > 64 || n_k < 0 || n_k > 8 || n_rel < 0 || (n_k > 0 && !k_values) ||
+      (q > 0 && (!topk_idx || !rel_ptr || !out)) || (n_rel > 0 && !rel_idx))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_retrieval_metrics: bad argument");
+  MetricKs ks{};
+  ks.n = n_k;
+  for (int i = 0; i < n_k; ++i) {
+    if (k_values[i] < 1 || k_values[i] > k)
+      return fail(ctx, TVC_ERR_INVALID, "tvc_retrieval_metrics: every K must lie in [1, k]");
+    ks.k[i] = k_values[i];
+  }
+  if (q == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const size_t Q = static_cast<size_t>(q), cols = 2 + 3 * static_cast<size_t>(n_k);
+  uint8_t* ws;
+  int rc = get_ws(ctx, st, up256(Q * k * 8) + up256((Q + 1) * 8) + up256(static_cast<size_t>(n_rel) * 8 + 8) +
+                               up256(Q * cols * 4), &ws);
+  if (rc != TVC_OK) return rc;
+  Stager sg{ctx, st, ws};
+  const int64_t *d_topk, *d_ptr, *d_rel;
+  if ((rc = sg.in(topk_idx, Q * k, &d_topk)) || (rc = sg.in(rel_ptr, Q + 1, &d_ptr)) ||
+      (rc = sg.in(rel_idx, static_cast<size_t>(n_rel), &d_rel)))
+    return rc;
+  bool staged;
+  float* d_out = sg.out_buf(out, Q * cols, &staged);
+  TVC_CUDA(ctx, launch_retrieval_metrics(d_topk, q, k, d_ptr, d_rel, ks, d_out, st));
+  if (staged) TVC_CUDA(ctx, cudaMemcpyAsync(out, d_out, Q * cols * 4, cudaMemcpyDeviceToHost, st));
+  if (sg.any_host) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
 // ------------------------------------------------------------------------------- peer buffers
 int tvc_peer_alloc(tvc_ctx* ctx, int64_t bytes, void** ptr, void* handle) {
   if (!ctx || bytes <= 0 || !ptr || !handle) return fail(ctx, TVC_ERR_INVALID, "tvc_peer_alloc: bad argument");

@@ -580,6 +580,71 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
   }
 }
 
+// ------------------------------------------------------------------------------- retrieval metrics
+// Recall@K / Precision@K / NDCG@K, reciprocal rank and average precision of every query from its
+// ranked top-k list and its set of relevant items (src/utils/metrics.py:386-574: binary relevance,
+// DCG = sum rel_i / log2(i + 2), IDCG with all relevant items first).  One warp per query: lane j
+// tests ranks j and j + 32 against the relevant set, the hit mask is shared with two ballots.
+constexpr int kMaxMetricK = 8;
+__global__ void __launch_bounds__(128)
+retrieval_metrics_kernel(const long long* __restrict__ topk, long long nq, int k,
+                         const long long* __restrict__ rel_ptr, const long long* __restrict__ rel_idx,
+                         const MetricKs ks, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const long long r0 = rel_ptr[q], r1 = rel_ptr[q + 1];
+  const int n_rel = static_cast<int>(r1 - r0);
+  unsigned hit[2] = {0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    bool is_hit = false;
+    if (j < k) {
+      const long long id = topk[q * k + j];
+      if (id >= 0)
+        for (long long r = r0; r < r1 && !is_hit; ++r) is_hit = rel_idx[r] == id;
+    }
+    hit[h] = __ballot_sync(kFull, is_hit);
+  }
+  const unsigned long long mask = static_cast<unsigned long long>(hit[0]) | (static_cast<unsigned long long>(hit[1]) << 32);
+  if (lane != 0) return;
+  const int cols = 2 + 3 * ks.n;
+  float* o = out + q * cols;
+  double rr = 0.0, ap = 0.0;
+  if (mask) rr = 1.0 / static_cast<double>(__ffsll(static_cast<long long>(mask)));
+  {
+    int seen = 0;
+    unsigned long long m = mask;
+    while (m) {
+      const int p = __ffsll(static_cast<long long>(m)) - 1;
+      m &= m - 1;
+      ++seen;
+      ap += static_cast<double>(seen) / static_cast<double>(p + 1);
+    }
+    ap = n_rel > 0 ? ap / n_rel : 0.0;
+  }
+  o[0] = static_cast<float>(rr);
+  o[1] = static_cast<float>(ap);
+  for (int t = 0; t < ks.n; ++t) {
+    const int kv = ks.k[t];
+    const unsigned long long lim = kv >= 64 ? ~0ull : ((1ull << kv) - 1ull);
+    unsigned long long m = mask & lim;
+    const int hits = __popcll(m);
+    double dcg = 0.0, idcg = 0.0;
+    while (m) {
+      const int p = __ffsll(static_cast<long long>(m)) - 1;
+      m &= m - 1;
+      dcg += 1.0 / log2(static_cast<double>(p + 2));
+    }
+    const int ideal = n_rel < kv ? n_rel : kv;
+    for (int i = 0; i < ideal; ++i) idcg += 1.0 / log2(static_cast<double>(i + 2));
+    o[2 + t] = n_rel > 0 ? static_cast<float>(static_cast<double>(hits) / n_rel) : 0.f;
+    o[2 + ks.n + t] = kv > 0 ? static_cast<float>(static_cast<double>(hits) / kv) : 0.f;
+    o[2 + 2 * ks.n + t] = idcg > 0.0 ? static_cast<float>(dcg / idcg) : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------- gather rows
 __global__ void gather_rows_kernel(const float* __restrict__ g_f32,
                                    const __nv_bfloat16* __restrict__ g_bf16, int d, int d_pad,
@@ -739,6 +804,17 @@ cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t id
     k_occurrence_kernel<true><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot);
   else
     k_occurrence_kernel<false><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_retrieval_metrics(const int64_t* topk, int64_t nq, int k, const int64_t* rel_ptr,
+                                     const int64_t* rel_idx, const MetricKs& ks, float* out, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int grid = static_cast<int>((nq + 3) / 4);
+  retrieval_metrics_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const long long*>(topk), nq, k,
+                                                     reinterpret_cast<const long long*>(rel_ptr),
+                                                     reinterpret_cast<const long long*>(rel_idx), ks, out);
   note_launch();
   return cudaGetLastError();
 }

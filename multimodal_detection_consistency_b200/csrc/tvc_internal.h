@@ -77,6 +77,13 @@ cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t id
                                 int64_t n_bins, int32_t* counts, int sm_count, int* flag_scratch,
                                 cudaStream_t stream);
 
+struct MetricKs {
+  int n;
+  int k[8];
+};
+cudaError_t launch_retrieval_metrics(const int64_t* topk, int64_t nq, int k, const int64_t* rel_ptr,
+                                     const int64_t* rel_idx, const MetricKs& ks, float* out, cudaStream_t stream);
+
 cudaError_t launch_gather_rows(const float* g_f32, const __nv_bfloat16* g_bf16, int d, int d_pad,
                                const int64_t* idx, int64_t n, int64_t n_rows, float* out,
                                cudaStream_t stream);

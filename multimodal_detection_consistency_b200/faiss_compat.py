@@ -95,18 +95,66 @@ def index_gpu_to_cpu(index):
     return index
 
 
+# ---- on-disk format ---------------------------------------------------------------------------
+# FAISS's native flat-index layout (faiss/impl/index_write.cpp, write_index / write_index_header,
+# v1.7.x - the version the reference pins, README.md:546), little endian:
+#   fourcc "IxFI" (inner product) | "IxF2" (L2)          uint32
+#   d                                                     int32
+#   ntotal                                                int64
+#   two reserved idx_t (1 << 20)                          2 x int64
+#   is_trained                                            uint8
+#   metric_type (0 = inner product, 1 = L2)               int32
+#   [metric_arg float32 when metric_type > 1]
+#   number of float32 values (ntotal * d)                 uint64
+#   the rows                                              float32 [ntotal, d]
+# Files written here are meant to be readable by a real faiss.read_index and vice versa; faiss is not
+# installable in the build container, so the layout is restated from the published source and covered
+# only by our own round trip (tests/test_formats.py).
+_FOURCC_IP, _FOURCC_L2 = b"IxFI", b"IxF2"
+
+
+def _pack_flat(rows: np.ndarray, d: int, metric: int = METRIC_INNER_PRODUCT) -> bytes:
+    import struct
+    rows = np.ascontiguousarray(rows, dtype="<f4").reshape(-1, d) if rows.size else np.zeros((0, d), "<f4")
+    head = (_FOURCC_IP if metric == METRIC_INNER_PRODUCT else _FOURCC_L2)
+    head += struct.pack("<iqqqBi", d, rows.shape[0], 1 << 20, 1 << 20, 1, metric)
+    return head + struct.pack("<Q", rows.size) + rows.tobytes()
+
+
+def _unpack_flat(blob: bytes):
+    import struct
+    if blob[:4] not in (_FOURCC_IP, _FOURCC_L2):
+        raise ValueError("not a FAISS flat index (fourcc %r): only IndexFlatIP / IndexFlatL2 files are exact" % blob[:4])
+    d, ntotal, _, _, _, metric = struct.unpack_from("<iqqqBi", blob, 4)
+    off = 4 + struct.calcsize("<iqqqBi")
+    if metric > 1:
+        off += 4
+    (count,) = struct.unpack_from("<Q", blob, off)
+    off += 8
+    if count != ntotal * d:
+        raise ValueError(f"corrupt flat index: {count} values for {ntotal} x {d}")
+    rows = np.frombuffer(blob, dtype="<f4", count=count, offset=off).reshape(ntotal, d)
+    return d, metric, rows
+
+
 def write_index(index: IndexFlatIP, path: str) -> None:
-    """Sidecar written next to the retriever pickle (src/retrieval.py:781-783): the fp32 rows."""
+    """Sidecar written next to the retriever pickle (src/retrieval.py:781-783) in FAISS's own layout."""
     with open(path, "wb") as f:
-        pickle.dump({"format": "tvc-flat-ip", "d": index.d, "rows": index.reconstruct_n()}, f)
+        f.write(_pack_flat(index.reconstruct_n(), index.d))
 
 
 def read_index(path: str) -> IndexFlatIP:
+    """FAISS flat-index files (see above); also the pickle sidecar earlier versions of this module wrote."""
     with open(path, "rb") as f:
-        blob = pickle.load(f)
-    if not isinstance(blob, dict) or blob.get("format") != "tvc-flat-ip":
-        raise ValueError(f"{path} is not a tvc flat-IP sidecar")
-    idx = IndexFlatIP(int(blob["d"]))
-    if len(blob["rows"]):
-        idx.add(blob["rows"])
+        blob = f.read()
+    if blob[:4] in (_FOURCC_IP, _FOURCC_L2):
+        d, _, rows = _unpack_flat(blob)
+    else:
+        old = pickle.loads(blob)
+        if not isinstance(old, dict) or old.get("format") != "tvc-flat-ip":
+            raise ValueError(f"{path} is neither a FAISS flat index nor a tvc sidecar")
+        d, rows = int(old["d"]), old["rows"] if old.get("rows") is not None else np.zeros((0, int(old["d"])), np.float32)
+    idx = IndexFlatIP(int(d))
+    if len(rows):
+        idx.add(np.ascontiguousarray(rows, dtype=np.float32))
     return idx

@@ -1,0 +1,94 @@
+"""Retrieval evaluation on the device: mirrors `RetrievalMetrics` /
+`RetrievalEvaluator` of src/utils/metrics.py:69-86,379-574.  The reference argsorts the full
+[N_queries, N_candidates] similarity matrix and walks every query in Python; here the ranked lists
+come from the exact top-k search (kernel a) and one kernel reduces them (tvc_retrieval_metrics).
+Recall@K, Precision@K and NDCG@K are exact for every K up to the list length; MRR and mAP are those of
+the full ranking whenever every relevant item lies inside the list (always true for matrices with at
+most 64 candidates), otherwise they are the list-truncated values."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+MAX_LIST = 56          # TVC_MAX_K: longest ranked list the search kernel returns
+
+
+@dataclass
+class RetrievalMetrics:
+    """src/utils/metrics.py:69-86."""
+    recall_at_k: Dict[int, float]
+    precision_at_k: Dict[int, float]
+    map_score: float
+    ndcg_at_k: Dict[int, float]
+    mrr: float
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"recall_at_k": self.recall_at_k, "precision_at_k": self.precision_at_k, "map_score": self.map_score,
+                "ndcg_at_k": self.ndcg_at_k, "mrr": self.mrr}
+
+
+def _csr(relevant) -> (np.ndarray, np.ndarray):
+    """list of per-query index lists, or a dense 0/1 matrix -> (rel_ptr [q+1], rel_idx)."""
+    if isinstance(relevant, np.ndarray) and relevant.ndim == 2:
+        rows, cols = np.nonzero(relevant)
+        ptr = np.zeros(relevant.shape[0] + 1, np.int64)
+        np.add.at(ptr, rows + 1, 1)
+        return np.cumsum(ptr), cols.astype(np.int64)
+    ptr = np.zeros(len(relevant) + 1, np.int64)
+    ptr[1:] = np.cumsum([len(r) for r in relevant])
+    idx = np.concatenate([np.asarray(r, np.int64).ravel() for r in relevant]) if len(relevant) else np.zeros(0, np.int64)
+    return ptr, idx
+
+
+class RetrievalEvaluator:
+    """src/utils/metrics.py:379-574."""
+
+    @staticmethod
+    def from_topk(topk_idx, relevant, k_values: Sequence[int] = (1, 5, 10, 20, 50),
+                  ctx: Optional[N.Context] = None) -> RetrievalMetrics:
+        """Ranked lists [q, k] (numpy or torch cuda, the search output) + relevance (dense 0/1 matrix or one
+        index list per query) -> RetrievalMetrics.  K values beyond the list length are clipped to it."""
+        ctx = ctx or N.Context.get()
+        k = int(topk_idx.shape[1])
+        ks = [min(int(x), k) for x in k_values]
+        ptr, idx = _csr(relevant)
+        if N._is_torch(topk_idx):
+            import torch
+            ptr_t, idx_t = torch.from_numpy(ptr).to(topk_idx.device), torch.from_numpy(idx).to(topk_idx.device)
+            per_q = ctx.retrieval_metrics(topk_idx, ptr_t, idx_t, ks).double().mean(0).cpu().numpy()
+        else:
+            per_q = ctx.retrieval_metrics(np.asarray(topk_idx), ptr, idx, ks).astype(np.float64).mean(0)
+        nk = len(ks)
+        return RetrievalMetrics(
+            recall_at_k={int(kv): float(per_q[2 + t]) for t, kv in enumerate(k_values)},
+            precision_at_k={int(kv): float(per_q[2 + nk + t]) for t, kv in enumerate(k_values)},
+            map_score=float(per_q[1]),
+            ndcg_at_k={int(kv): float(per_q[2 + 2 * nk + t]) for t, kv in enumerate(k_values)},
+            mrr=float(per_q[0]))
+
+    @staticmethod
+    def compute_retrieval_metrics(similarities: np.ndarray, relevance: np.ndarray,
+                                  k_values: List[int] = [1, 5, 10, 20, 50]) -> RetrievalMetrics:  # noqa: B006
+        """The reference's signature (src/utils/metrics.py:386-459): a precomputed similarity matrix.  The
+        ranked lists are a stable descending sort on the device (ties to the lower index; plumbing, not
+        a kernel of ours - at gallery scale use evaluate(), which never builds the matrix); the reduction
+        is tvc_retrieval_metrics."""
+        import torch
+        ctx = N.Context.get()
+        sims = torch.as_tensor(np.ascontiguousarray(similarities, dtype=np.float32)).to(f"cuda:{ctx.device}")
+        k = min(int(sims.shape[1]), 64)
+        order = torch.sort(-sims, dim=1, stable=True).indices[:, :k].contiguous()
+        return RetrievalEvaluator.from_topk(order, np.asarray(relevance), k_values, ctx=ctx)
+
+    @staticmethod
+    def evaluate(gallery: N.Gallery, query_features, relevant, k_values: Sequence[int] = (1, 5, 10, 20, 50),
+                 normalize_queries: bool = False) -> RetrievalMetrics:
+        """Search + metrics without the similarity matrix ever existing (what the evaluation loops of
+        experiments/run_experiments.py need at gallery scale)."""
+        k = min(max(int(x) for x in k_values), MAX_LIST, len(gallery))
+        _, idx = gallery.search(query_features, k, normalize_queries=normalize_queries)
+        return RetrievalEvaluator.from_topk(idx, relevant, k_values, ctx=gallery.ctx)

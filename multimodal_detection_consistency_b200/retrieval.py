@@ -422,33 +422,58 @@ class MultiModalRetriever:
         i2 = (imf.astype(np.float64) ** 2).sum(1)[None, :]
         return (1.0 / (1.0 + np.sqrt(np.maximum(t2 + i2 - 2.0 * dots, 0.0)))).astype(np.float32)
 
-    # -- persistence (src/retrieval.py:764-882): pickle {features, paths|texts, config} + sidecar --
-    def _save(self, save_path, payload, index):
+    # -- persistence (src/retrieval.py:764-882): pickle {features, paths|texts, config} + .faiss sidecar --
+    def _save(self, save_path, payload, features):
         save_path = Path(save_path)
         save_path.parent.mkdir(parents=True, exist_ok=True)
         with open(save_path, "wb") as f:
             pickle.dump(payload, f)
-        if index is not None:
+        if features is not None:
+            # the sidecar the reference writes with faiss.write_index (:781-783), in FAISS's flat layout
             with open(save_path.with_suffix(".faiss"), "wb") as f:
-                pickle.dump({"format": "tvc-flat-ip", "d": int(index.dim), "rows": None}, f)  # rows live in the pickle
+                f.write(faiss_compat._pack_flat(np.asarray(features, np.float32), int(np.asarray(features).shape[1])))
 
     def save_image_index(self, save_path: str):
         self._save(save_path, {"image_features": self.image_features, "image_paths": self.image_paths,
-                               "config": self.config}, self.image_index)
+                               "config": self.config}, self.image_features if self.image_index is not None else None)
 
     def save_text_index(self, save_path: str):
         self._save(save_path, {"text_features": self.text_features, "texts": self.texts, "config": self.config},
-                   self.text_index)
+                   self.text_features if self.text_index is not None else None)
+
+    @staticmethod
+    def _load_payload(load_path) -> Dict[str, Any]:
+        """Files written by the reference pickle its own `src.retrieval.RetrievalConfig`; when that module
+        is not importable the class is mapped onto ours instead of failing the load."""
+        class _Unpickler(pickle.Unpickler):
+            def find_class(self, module, name):
+                try:
+                    return super().find_class(module, name)
+                except (ImportError, AttributeError):
+                    if name == "RetrievalConfig":
+                        return RetrievalConfig
+                    if name == "IndexConfig":
+                        return IndexConfig
+                    raise
+        with open(Path(load_path), "rb") as f:
+            return _Unpickler(f).load()
+
+    def _load(self, load_path, feat_key):
+        data = self._load_payload(load_path)
+        feats = data.get(feat_key)
+        side = Path(load_path).with_suffix(".faiss")
+        if feats is None and side.exists():          # features only in the sidecar
+            with open(side, "rb") as f:
+                _, _, feats = faiss_compat._unpack_flat(f.read())
+        return data, feats
 
     def load_image_index(self, load_path: str):
-        with open(Path(load_path), "rb") as f:
-            data = pickle.load(f)
-        self.build_image_index_from_features(data["image_features"], data["image_paths"])
+        data, feats = self._load(load_path, "image_features")
+        self.build_image_index_from_features(feats, data["image_paths"])
 
     def load_text_index(self, load_path: str):
-        with open(Path(load_path), "rb") as f:
-            data = pickle.load(f)
-        self.build_text_index_from_features(data["text_features"], data["texts"])
+        data, feats = self._load(load_path, "text_features")
+        self.build_text_index_from_features(feats, data["texts"])
 
     def clear_cache(self):
         self.feature_cache.clear()

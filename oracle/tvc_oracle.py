@@ -494,3 +494,32 @@ def synth_queries(gallery: np.ndarray, q: int, v: int, seed: int = 123, q_noise:
     var = txt[:, None, :] + v_noise * sd * rng.standard_normal((q, v, d), dtype=np.float32)
     var = l2_normalize(var.reshape(q * v, d)).reshape(q, v, d)
     return img, txt, var
+
+
+# --------------------------------------------------------------------------------------------
+# Retrieval metrics from ranked lists (src/utils/metrics.py:386-574: binary relevance,
+# DCG = sum rel_i / log2(i + 2), IDCG with all relevant items first, AP = mean precision at the
+# ranks of the relevant items, RR = 1 / rank of the first relevant item).
+def retrieval_metrics_from_topk(topk_idx: np.ndarray, relevant: Sequence[Sequence[int]],
+                                k_values: Sequence[int]) -> np.ndarray:
+    """Per query [rr, ap, recall@K.., precision@K.., ndcg@K..] with RR/AP restricted to the list
+    (AP normalised by the number of relevant items)."""
+    q, k = topk_idx.shape
+    nk = len(k_values)
+    out = np.zeros((q, 2 + 3 * nk), dtype=np.float64)
+    for i in range(q):
+        rel = set(int(x) for x in relevant[i])
+        hits = np.array([int(j) >= 0 and int(j) in rel for j in topk_idx[i]], dtype=bool)
+        pos = np.flatnonzero(hits)
+        if len(pos):
+            out[i, 0] = 1.0 / (pos[0] + 1)
+            out[i, 1] = sum((n + 1) / (p + 1) for n, p in enumerate(pos)) / len(rel)
+        for t, kv in enumerate(k_values):
+            h = hits[:kv]
+            nh = int(h.sum())
+            out[i, 2 + t] = nh / len(rel) if rel else 0.0
+            out[i, 2 + nk + t] = nh / kv
+            dcg = sum(1.0 / math.log2(p + 2) for p in np.flatnonzero(h))
+            idcg = sum(1.0 / math.log2(j + 2) for j in range(min(kv, len(rel))))
+            out[i, 2 + 2 * nk + t] = dcg / idcg if idcg > 0 else 0.0
+    return out

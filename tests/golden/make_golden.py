@@ -8,7 +8,7 @@ What runs is the reference's code, unmodified: ReferenceBank.query_similar, Cons
 make_decision, SimilarityCalculator, MultiModalRetriever._search_index (sklearn fallback branch),
 ConsistencyCalculator, AdversarialDetector.detect_adversarial,
 MultiModalDefenseDetector._compute_consistency_scores / _deduplicate_references,
-HubnessAttack.compute_hubness, and the `compute_hubness` pseudo-code block of
+HubnessAttack.compute_hubness, RetrievalEvaluator.compute_retrieval_metrics, and the `compute_hubness` pseudo-code block of
 references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md (exec'd from the markdown).
 Modules the reference imports but does not ship or that are not installed here (src.models, faiss,
 matplotlib, seaborn, plotly, nltk, and the syntactically broken experiments/defenses/
@@ -363,13 +363,43 @@ def gold_hubness(mods, out):
     np.savez_compressed(out / "hubness.npz", **res)
 
 
+def gold_retrieval_metrics(mods, out):
+    """RetrievalEvaluator.compute_retrieval_metrics (src/utils/metrics.py:386-574) on similarity
+    matrices whose values are distinct (the reference's argsort has no defined tie order)."""
+    M = mods["src.utils.metrics"]
+    rng = np.random.default_rng(11)
+    res = {}
+    for tag, nq, nc, p_rel in [("small", 40, 50, 0.08), ("wide", 60, 400, 0.01)]:
+        sims = rng.permutation(nq * nc).reshape(nq, nc).astype(np.float64) / (nq * nc)
+        rel = (rng.uniform(size=(nq, nc)) < p_rel).astype(np.int64)
+        rel[0] = 0                                        # a query without relevant items
+        ks = [1, 5, 10, 20, 50]
+        m = M.RetrievalEvaluator.compute_retrieval_metrics(sims, rel, ks)
+        per_q = np.zeros((nq, 2), np.float64)
+        order = np.argsort(-sims, axis=1)
+        for i in range(nq):
+            sr = rel[i][order[i]]
+            per_q[i, 0] = M.RetrievalEvaluator._compute_reciprocal_rank(sr)
+            per_q[i, 1] = M.RetrievalEvaluator._compute_average_precision(sr)
+        res.update({f"{tag}_sims": sims.astype(np.float32), f"{tag}_rel": rel, f"{tag}_ks": np.array(ks),
+                    f"{tag}_recall": np.array([m.recall_at_k[k] for k in ks]),
+                    f"{tag}_precision": np.array([m.precision_at_k[k] for k in ks]),
+                    f"{tag}_ndcg": np.array([m.ndcg_at_k[k] for k in ks]),
+                    f"{tag}_map": np.float64(m.map_score), f"{tag}_mrr": np.float64(m.mrr), f"{tag}_per_query": per_q})
+    np.savez_compressed(out / "retrieval_metrics.npz", **res)
+
+
 def main():
     mods = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "retrieval_metrics":
+        gold_retrieval_metrics(mods, OUT)
+        return
     gold_ref_bank(mods, OUT)
     gold_consistency_checker(mods, OUT)
     gold_similarity(mods, OUT)
     gold_detectors(mods, OUT)
     gold_hubness(mods, OUT)
+    gold_retrieval_metrics(mods, OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
 

@@ -212,3 +212,20 @@ def test_bf16_round():
     import torch
     want = torch.from_numpy(x).bfloat16().float().numpy()
     assert np.array_equal(O.bf16_round(x), want)
+
+
+def test_retrieval_metrics_oracle_matches_reference_evaluator():
+    """oracle.retrieval_metrics_from_topk on the full ranking == RetrievalEvaluator.compute_retrieval_metrics
+    (src/utils/metrics.py:386-574) run by tests/golden/make_golden.py."""
+    z = np.load(GOLD / "retrieval_metrics.npz")
+    for tag in ("small", "wide"):
+        sims, rel = z[f"{tag}_sims"], z[f"{tag}_rel"]
+        ks = [int(k) for k in z[f"{tag}_ks"]]
+        order = np.argsort(-sims, axis=1, kind="stable")
+        per_q = O.retrieval_metrics_from_topk(order, [list(np.flatnonzero(r)) for r in rel], ks)
+        out, nk = per_q.mean(0), len(ks)
+        assert np.abs(out[2:2 + nk] - z[f"{tag}_recall"]).max() < 1e-12
+        assert np.abs(out[2 + nk:2 + 2 * nk] - z[f"{tag}_precision"]).max() < 1e-12
+        assert np.abs(out[2 + 2 * nk:] - z[f"{tag}_ndcg"]).max() < 1e-12
+        assert abs(out[0] - float(z[f"{tag}_mrr"])) < 1e-12 and abs(out[1] - float(z[f"{tag}_map"])) < 1e-12
+        assert np.abs(per_q[:, :2] - z[f"{tag}_per_query"]).max() < 1e-12

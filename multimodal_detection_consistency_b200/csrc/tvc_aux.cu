@@ -585,7 +585,6 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
 // ranked top-k list and its set of relevant items (src/utils/metrics.py:386-574: binary relevance,
 // DCG = sum rel_i / log2(i + 2), IDCG with all relevant items first).  One warp per query: lane j
 // tests ranks j and j + 32 against the relevant set, the hit mask is shared with two ballots.
-constexpr int kMaxMetricK = 8;
 __global__ void __launch_bounds__(128)
 retrieval_metrics_kernel(const long long* __restrict__ topk, long long nq, int k,
                          const long long* __restrict__ rel_ptr, const long long* __restrict__ rel_idx,

@@ -313,7 +313,7 @@ __device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(kSimsBlock)
+__global__ void __launch_bounds__(kSimsBlock, 8)
 consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const float* __restrict__ s0,
                         const float* __restrict__ sv, const float* __restrict__ sr,
                         const int32_t* __restrict__ r_cnt, const float* __restrict__ sg,

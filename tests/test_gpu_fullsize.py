@@ -153,3 +153,63 @@ def test_pipelined_host_batches_equal_one_shot(tvc_ctx):
     for name, t in outs[0][0].items():
         assert torch.equal(t, outs[1][0][name]), name
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_c4_cc3m_scale_properties(tvc_ctx):
+    """configs[3]: 100k queries x 5 variants vs a 3M-image 768-d gallery (one GPU holds it: 4.6 GB bf16 +
+    9.2 GB fp32).  Size-independent properties on all 500k rows, the two-phase sharded search on a
+    sample, a torch fp32 reference on a sample, and the hubness histogram identities."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    n, d, k, nq, v = 3_000_000, 768, 10, 100_000, 5
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    g = torch.empty((n, d), device="cuda")
+    for a in range(0, n, 500_000):
+        g[a:a + 500_000] = torch.nn.functional.normalize(torch.randn(500_000, d, device="cuda", generator=gen), dim=1)
+    base = g[torch.randint(0, n, (nq,), device="cuda", generator=gen)]
+    var = torch.nn.functional.normalize(
+        base[:, None, :] + (0.6 / d ** 0.5) * torch.randn(nq, v, d, device="cuda", generator=gen), dim=2)
+    rows = var.view(nq * v, d)
+    full = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = full.search(rows, k)
+    torch.cuda.synchronize()
+    assert bool((idx >= 0).all()) and bool((idx < n).all())
+    assert bool((sims[:, :-1] >= sims[:, 1:]).all())
+    tie = sims[:, :-1] == sims[:, 1:]
+    assert bool((idx[:, :-1][tie] < idx[:, 1:][tie]).all())           # ties to the lower index
+    assert bool((idx.sort(dim=1).values[:, 1:] != idx.sort(dim=1).values[:, :-1]).all())   # no row twice
+    for a in range(0, nq * v, 50_000):                                  # every similarity is its index's fp32 dot
+        dots = (rows[a:a + 50_000, None, :] * g[idx[a:a + 50_000]]).sum(-1)
+        assert float((dots - sims[a:a + 50_000]).abs().max()) <= 1e-5
+    # hubness histogram: integer identities + the oracle on the same indices
+    counts = tvc_ctx.k_occurrence(idx, n)
+    torch.cuda.synchronize()
+    assert int(counts.sum()) == nq * v * k
+    assert torch.equal(counts, torch.bincount(idx.reshape(-1), minlength=n).to(torch.int32))
+    # two-phase sharded search (3 shards, 2 slice owners) on a 20k-row sample == the unsharded result
+    from multimodal_detection_consistency_b200._native import Scatter
+    sub = rows[:20_000]
+    per, kp, rps = 1_000_000, tvc_ctx.candidate_width(k), 10_000
+    parts = [tvc.Gallery.wrap_rows(g[r * per:(r + 1) * per], r * per, ctx=tvc_ctx) for r in range(3)]
+    group = tvc.Gallery.group(parts)
+    val = [torch.empty((3, rps, kp), device="cuda") for _ in range(2)]
+    ix = [torch.empty((3, rps, kp), dtype=torch.int64, device="cuda") for _ in range(2)]
+    for r in range(3):
+        shard = tvc.Gallery(g[r * per:(r + 1) * per], global_row_offset=r * per, keep_master=False, ctx=tvc_ctx)
+        sc = Scatter()
+        sc.n_slices, sc.slot, sc.rows_per_slice = 2, r, rps
+        for j in range(2):
+            sc.val[j], sc.idx[j] = val[j].data_ptr(), ix[j].data_ptr()
+        shard.search_candidates(sub, k, sc)
+        torch.cuda.synchronize()
+        shard.close()
+    for j in range(2):
+        s2, i2 = tvc_ctx.rerank_candidates(group, sub[j * rps:(j + 1) * rps], val[j].data_ptr(), ix[j].data_ptr(), 3, kp, k)
+        torch.cuda.synchronize()
+        assert torch.equal(i2, idx[j * rps:(j + 1) * rps]) and torch.equal(s2, sims[j * rps:(j + 1) * rps])
+    # torch fp32 reference on sampled rows
+    sel = torch.randperm(nq * v, device="cuda", generator=gen)[:128]
+    ref = torch.topk(rows[sel] @ g.T, k, dim=1)
+    same = ref.indices == idx[sel]
+    assert float(same.float().mean()) > 0.99
+    assert float((ref.values - sims[sel]).abs().max()) <= 1e-3

@@ -233,3 +233,22 @@ def test_sharded_two_phase_search_equals_unsharded(tvc_ctx, n, d, m, k, shards):
     ok = ci >= 0
     assert ((ci[ok] >= per) & (ci[ok] < 2 * per)).all()
     assert (cv[:, :-1] >= cv[:, 1:]).all()
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_half_precision_rows_and_queries(tvc_ctx, dtype):
+    """tvc_dtype BF16 / F16 inputs (gallery rows and queries): the search runs on exactly the values
+    given, so the result equals the fp32 search of the up-converted rows."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(5)
+    dt = getattr(torch, dtype)
+    g = torch.from_numpy(_unit(rng, 3000, 192)).cuda().to(dt)
+    q = torch.from_numpy(_unit(rng, 257, 192)).cuda().to(dt)
+    s_half, i_half = tvc.Gallery(g, ctx=tvc_ctx).search(q, 10)
+    s_f32, i_f32 = tvc.Gallery(g.float(), ctx=tvc_ctx).search(q.float(), 10)
+    torch.cuda.synchronize()
+    assert torch.equal(i_half, i_f32) and torch.equal(s_half, s_f32)
+    ref_s, ref_i = O.search(q.float().cpu().numpy(), g.float().cpu().numpy(), 10)
+    assert (i_half.cpu().numpy() != ref_i).mean() < 0.01
+    assert np.abs(s_half.cpu().numpy() - ref_s).max() <= (2e-3 if dtype == "float16" else 2e-3)

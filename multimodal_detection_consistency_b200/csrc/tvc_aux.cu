@@ -287,25 +287,32 @@ select_candidates_kernel(const float* __restrict__ cand_val, const int32_t* __re
     }
     return;
   }
+  // lane t keeps the t-th best (and t + 32 for kp = 64) and the row leaves as two coalesced stores:
+  // single-lane stores would cross NVLink as 2 * kp tiny writes per row
   float bv = INFINITY;
   long long bi = -1;
-  int t = 0;
-  for (; t < kp; ++t) {
+  float keep_v[2] = {-INFINITY, -INFINITY};
+  long long keep_i[2] = {-1, -1};
+  for (int t = 0; t < kp; ++t) {
     float v;
     long long i;
     const bool ok = warp_next_best(
         ncand, bv, bi, [&](int e, float& vv, long long& ii) { vv = cv[e]; ii = ci[e]; }, v, i);
     if (!ok) break;
-    if (lane == 0) {
-      dv[t] = v;
-      di[t] = i + row_offset;
+    if (lane == (t & 31)) {
+      keep_v[t >> 5] = v;
+      keep_i[t >> 5] = i + row_offset;
     }
     bv = v;
     bi = i;
   }
-  for (int e = t + lane; e < kp; e += 32) {
-    dv[e] = -INFINITY;
-    di[e] = -1;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int e = lane + 32 * h;
+    if (e < kp) {
+      dv[e] = keep_v[h];
+      di[e] = keep_i[h];
+    }
   }
 }
 

@@ -320,6 +320,7 @@ def main():
                    d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
                    api="TVCScorer.score_batch(pinned host tensors, to_host=True)")
 
+    scorer.close()
     if rank != 0:
         if world > 1:
             dist.barrier()

@@ -18,6 +18,7 @@
  *                                                                                experiments/defenses/detector.py:228-300
  *                                                                                experiments/defenses/consistency_checker.py:74-272
  *                                                                                experiments/defenses/text_variants.py:412-451
+ *   tvc_reference_vector_rule      the documented rule: mean reference vectors, S = cos, sigma = std(S)  README.md:474-482,846
  *   tvc_k_occurrence               hubness_counts[j] += 1 double loop            references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:43-57
  *                                  (top1 == 0).sum()                             src/attacks/hubness_attack.py:492-496
  *   tvc_retrieval_metrics          argsort + per-query Python loops (Recall/Precision/NDCG@K, RR, AP)  src/utils/metrics.py:386-574
@@ -259,6 +260,17 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
                         const float* gen, const int32_t* g_cnt, tvc_gallery* gen_gallery,
                         const int64_t* gen_idx, int32_t n_gen_cand, float* scores, uint8_t* flags,
                         float* out_sv, float* out_sr, float* out_sg, void* stream);
+
+/* The documented TVC reference-vector rule (README.md:474-482, 846; prose only in the reference): for
+ * every text variant v the rows ret_idx [Q, V, k] of `ret_gallery` (-1 = unused) and the generated rows
+ * gen [Q, V, m, d] are averaged into a per-variant reference vector r_v, the r_v into the Reference
+ * Vector r;  out_s [Q, V] = cos(image, r_v) (0 for a variant without rows), out_ref [Q] = cos(image, r)
+ * (may be NULL), out_sigma [Q] = std_v(out_s) (population, fp64), flags [Q] = TVC_FLAG_SIGMA_ADV iff
+ * sigma > sigma_threshold.  k + m <= 32, V <= TVC_MAX_VARIANTS; fp32 masters required. */
+int tvc_reference_vector_rule(tvc_ctx* ctx, int64_t q, int32_t d, int32_t v, const float* img,
+                              tvc_gallery* ret_gallery, const int64_t* ret_idx, int32_t k, const float* gen,
+                              int32_t m, float sigma_threshold, float* out_s, float* out_ref, float* out_sigma,
+                              uint8_t* flags, void* stream);
 
 /* Retrieval quality of ranked lists (src/utils/metrics.py:386-574, binary relevance).  topk_idx [q, k]
  * is the search output (rank order, -1 = unused); the relevant items of query i are

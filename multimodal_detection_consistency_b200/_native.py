@@ -113,6 +113,9 @@ _EXPORTS = {
     "tvc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tvc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tvc_reference_vector_rule": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tvc_retrieval_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "tvc_k_occurrence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
@@ -320,6 +323,35 @@ class Context:
                                                   int(kp), C.c_void_p(cand_val), C.c_void_p(cand_idx), int(k),
                                                   float(threshold), _ptr(sims), _ptr(idx), _stream_of(q)))
         return sims, idx
+
+    def reference_vector_rule(self, img, ret_gallery=None, ret_idx=None, gen=None, sigma_threshold: float = 0.30,
+                              want_ref: bool = True):
+        """README.md:474-482: img [Q,d]; ret_idx [Q,V,k] into ret_gallery and/or gen [Q,V,m,d].
+        Returns (s [Q,V], ref_sim [Q], sigma [Q], flags [Q]); numpy in/out or torch cuda in/out."""
+        q, d = int(img.shape[0]), int(img.shape[1])
+        torch_mode = _is_torch(img)
+        if ret_idx is not None:
+            v, k = int(ret_idx.shape[1]), int(ret_idx.shape[2])
+        else:
+            v, k = int(gen.shape[1]), 0
+        m = int(gen.shape[2]) if gen is not None else 0
+        if torch_mode:
+            import torch
+            img = img.contiguous().float()
+            ret_idx = ret_idx.contiguous().to(torch.int64) if ret_idx is not None else None
+            gen = gen.contiguous().float() if gen is not None else None
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=img.device)  # noqa: E731
+            s, ref, sig, fl = mk((q, v), torch.float32), mk((q,), torch.float32), mk((q,), torch.float32), mk((q,), torch.uint8)
+        else:
+            img = np.ascontiguousarray(img, np.float32)
+            ret_idx = np.ascontiguousarray(ret_idx, np.int64) if ret_idx is not None else None
+            gen = np.ascontiguousarray(gen, np.float32) if gen is not None else None
+            s, ref, sig, fl = np.empty((q, v), np.float32), np.empty(q, np.float32), np.empty(q, np.float32), np.empty(q, np.uint8)
+        self.check(self.lib.tvc_reference_vector_rule(
+            self.handle, q, d, v, _ptr(img), ret_gallery.handle if ret_gallery is not None else None, _ptr(ret_idx), k,
+            _ptr(gen), m, float(sigma_threshold), _ptr(s), _ptr(ref) if want_ref else None, _ptr(sig), _ptr(fl),
+            _stream_of(img)))
+        return s, (ref if want_ref else None), sig, fl
 
     # -- retrieval metrics ---------------------------------------------------------------------
     def retrieval_metrics(self, topk_idx, rel_ptr, rel_idx, k_values):

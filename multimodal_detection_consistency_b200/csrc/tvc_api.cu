@@ -1138,6 +1138,57 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
   return TVC_OK;
 }
 
+int tvc_reference_vector_rule(tvc_ctx* ctx, int64_t q, int32_t d, int32_t v, const float* img,
+                              tvc_gallery* ret_gallery, const int64_t* ret_idx, int32_t k, const float* gen,
+                              int32_t m, float sigma_threshold, float* out_s, float* out_ref, float* out_sigma,
+                              uint8_t* flags, void* stream) {
+  if (!ctx || q < 0 || d <= 0 || v < 1 || v > TVC_MAX_VARIANTS || k < 0 || m < 0 || k + m < 1 || k + m > 32 ||
+      (q > 0 && (!img || !out_s || !out_sigma || !flags)) || (k > 0 && (!ret_gallery || !ret_idx)) || (m > 0 && !gen))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_reference_vector_rule: bad argument");
+  if (ret_gallery && ret_gallery->d != d)
+    return fail(ctx, TVC_ERR_INVALID, "tvc_reference_vector_rule: gallery dimension mismatch");
+  if (q == 0) return TVC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const size_t Q = static_cast<size_t>(q), D = static_cast<size_t>(d), V = static_cast<size_t>(v);
+  const size_t need = up256(Q * D * 4) + up256(Q * V * k * 8) + up256(Q * V * m * D * 4) + up256(Q * V * 4) +
+                      2 * up256(Q * 4) + up256(Q) + 4096;
+  const bool all_dev = is_device_ptr(img) && (!ret_idx || is_device_ptr(ret_idx)) && (!gen || is_device_ptr(gen)) &&
+                       is_device_ptr(out_s) && is_device_ptr(out_sigma) && is_device_ptr(flags) &&
+                       (!out_ref || is_device_ptr(out_ref));
+  uint8_t* ws;
+  const size_t valid_b = up256(Q * V);
+  int rc = get_ws(ctx, st, valid_b + (all_dev ? 4096 : need), &ws);
+  if (rc != TVC_OK) return rc;
+  uint8_t* valid_ws = ws;
+  Stager sg{ctx, st, ws + valid_b};
+  const float *d_img, *d_gen;
+  const int64_t* d_idx;
+  if ((rc = sg.in(img, Q * D, &d_img)) || (rc = sg.in(ret_idx, Q * V * k, &d_idx)) ||
+      (rc = sg.in(gen, Q * V * m * D, &d_gen)))
+    return rc;
+  RowSource src{};
+  if (k > 0) {
+    fill_row_source(&src, ret_gallery);
+    for (int i = 0; i < src.nparts; ++i)
+      if (!src.f32[i]) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_reference_vector_rule: gallery without fp32 master");
+  }
+  bool s0, s1, s2, s3;
+  float* o_s = sg.out_buf(out_s, Q * V, &s0);
+  float* o_ref = sg.out_buf(out_ref, Q, &s1);
+  float* o_sig = sg.out_buf(out_sigma, Q, &s2);
+  uint8_t* o_fl = sg.out_buf(flags, Q, &s3);
+  TVC_CUDA(ctx, launch_reference_vector(q, d, v, d_img, src, d_idx, k, d_gen, m, sigma_threshold, o_s, o_ref, o_sig,
+                                        o_fl, valid_ws, ctx->sm_count, st));
+  if (s0) TVC_CUDA(ctx, cudaMemcpyAsync(out_s, o_s, Q * V * 4, cudaMemcpyDeviceToHost, st));
+  if (s1) TVC_CUDA(ctx, cudaMemcpyAsync(out_ref, o_ref, Q * 4, cudaMemcpyDeviceToHost, st));
+  if (s2) TVC_CUDA(ctx, cudaMemcpyAsync(out_sigma, o_sig, Q * 4, cudaMemcpyDeviceToHost, st));
+  if (s3) TVC_CUDA(ctx, cudaMemcpyAsync(flags, o_fl, Q, cudaMemcpyDeviceToHost, st));
+  if (sg.any_host) TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return TVC_OK;
+}
+
 // ------------------------------------------------------------------------------- kernel (c)
 int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int64_t idx_base,
                      int64_t n_bins, int32_t* counts, int zero_first, void* stream) {

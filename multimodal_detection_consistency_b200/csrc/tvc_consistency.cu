@@ -1032,6 +1032,288 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
   }
 }
 
+// ------------------------------------------------------------------------------- README reference-vector rule
+// README.md:474-482, 846: per text variant v the top-k retrieved gallery rows and the m generated rows
+// are averaged into a per-variant reference vector r_v, the variants' vectors are averaged into the
+// Reference Vector r, S_v = cos(image, r_v), sigma = std_v(S_v) and the sample is adversarial iff
+// sigma > threshold (confidence = sigma).  Every gathered row is used exactly once, so nothing is
+// staged: one block per query, one warp per variant streams its k + m rows with 128-bit loads into a
+// register accumulator (two rows in flight), dots it with the image row and leaves r_v in shared
+// memory for the cross-variant mean.  Bytes per query: 4 d (1 + V (k + m)).
+constexpr int kRvSeg = 1024;            // floats of a row handled per pass (8 float4 per lane)
+__global__ void __launch_bounds__(TVC_MAX_VARIANTS * 32)
+reference_vector_kernel(long long nq, int d, int V, const float* __restrict__ img, const RowSource src,
+                        const long long* __restrict__ ret_idx, int k, const float* __restrict__ gen, int m,
+                        float sigma_threshold, float* __restrict__ out_s, float* __restrict__ out_ref,
+                        float* __restrict__ out_sigma, uint8_t* __restrict__ flags) {
+  extern __shared__ __align__(16) float s_rv[];        // [V][seg] per-variant mean segment
+  __shared__ float s_part[TVC_MAX_VARIANTS][3];         // img.sum, |sum|^2, (unused)
+  __shared__ float s_ref[3];                            // img.r, |r|^2, |img|^2
+  __shared__ int s_cnt[TVC_MAX_VARIANTS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (d & 3) == 0;
+  for (long long q = blockIdx.x; q < nq; q += gridDim.x) {
+    float dot_v = 0.f, nrm_v = 0.f;       // this warp's variant: img . sum_v and |sum_v|^2
+    float dot_r = 0.f, nrm_r = 0.f, nrm_i = 0.f;   // warp 0: img . r, |r|^2, |img|^2
+    // resolve this variant's rows once (lane j holds row j's pointer; k + m <= 32 is enforced by the host)
+    const float* my_row = nullptr;
+    if (lane < k) {
+      const long long gi = ret_idx[(q * V + w) * k + lane];
+      const int part = find_part(src, gi);
+      if (part >= 0 && src.f32[part] != nullptr) my_row = src.f32[part] + (gi - src.off[part]) * d;
+    } else if (lane < k + m) {
+      my_row = gen + ((q * V + w) * m + (lane - k)) * d;
+    }
+    const unsigned have = __ballot_sync(kFull, my_row != nullptr);
+    const int cnt = __popc(have);
+    if (lane == 0) s_cnt[w] = cnt;
+    const float inv_cnt = cnt > 0 ? 1.0f / static_cast<float>(cnt) : 0.f;
+    const float* irow = img + q * d;
+    for (int seg0 = 0; seg0 < d; seg0 += kRvSeg) {
+      const int seg = min(kRvSeg, d - seg0);
+      float4 acc[kRvSeg / 128];
+#pragma unroll
+      for (int c = 0; c < kRvSeg / 128; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned todo = have;
+      while (todo) {
+        const int j0 = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int j1 = todo ? __ffs(todo) - 1 : -1;
+        if (j1 >= 0) todo &= todo - 1;
+        const float* r0 = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), j0)) + seg0;
+        const float* r1 = j1 >= 0 ? reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), j1)) + seg0 : nullptr;
+        if (vec) {
+          float4 x[kRvSeg / 128], y[kRvSeg / 128];
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            const int e = (c * 32 + lane) * 4;
+            x[c] = e < seg ? __ldg(reinterpret_cast<const float4*>(r0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y[c] = (r1 && e < seg) ? __ldg(reinterpret_cast<const float4*>(r1 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            acc[c].x += x[c].x; acc[c].y += x[c].y; acc[c].z += x[c].z; acc[c].w += x[c].w;
+            acc[c].x += y[c].x; acc[c].y += y[c].y; acc[c].z += y[c].z; acc[c].w += y[c].w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            float* ac = reinterpret_cast<float*>(&acc[c]);
+            for (int t = 0; t < 4; ++t) {
+              const int e = (c * 32 + lane) * 4 + t;
+              if (e < seg) ac[t] += r0[e] + (r1 ? r1[e] : 0.f);
+            }
+          }
+        }
+      }
+      // dot with the image segment, norm of the sum, and (when the Reference Vector is wanted) the
+      // per-variant MEAN segment to shared memory
+      const bool want_ref = out_ref != nullptr;
+#pragma unroll
+      for (int c = 0; c < kRvSeg / 128; ++c) {
+        const int e0 = (c * 32 + lane) * 4;
+        if (e0 >= seg) continue;
+        float xi[4];
+        if (vec) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(irow + seg0 + e0));
+          xi[0] = t4.x; xi[1] = t4.y; xi[2] = t4.z; xi[3] = t4.w;
+        } else {
+          for (int t = 0; t < 4; ++t) xi[t] = e0 + t < seg ? irow[seg0 + e0 + t] : 0.f;
+        }
+        const float* ac = reinterpret_cast<const float*>(&acc[c]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (e0 + t < seg) {
+            dot_v = fmaf(xi[t], ac[t], dot_v);
+            nrm_v = fmaf(ac[t], ac[t], nrm_v);
+            if (!want_ref) nrm_i = fmaf(xi[t], xi[t], nrm_i);
+            if (want_ref) s_rv[w * kRvSeg + e0 + t] = ac[t] * inv_cnt;
+          }
+        }
+      }
+      if (!want_ref) continue;
+      __syncthreads();
+      if (w == 0) {
+        for (int e = lane; e < seg; e += 32) {
+          float r = 0.f;
+          int nv = 0;
+          for (int v = 0; v < V; ++v)
+            if (s_cnt[v] > 0) {
+              r += s_rv[v * kRvSeg + e];
+              ++nv;
+            }
+          r = nv > 0 ? r / static_cast<float>(nv) : 0.f;
+          const float xi = irow[seg0 + e];
+          dot_r = fmaf(xi, r, dot_r);
+          nrm_r = fmaf(r, r, nrm_r);
+          nrm_i = fmaf(xi, xi, nrm_i);
+        }
+      }
+      __syncthreads();
+    }
+    dot_v = warp_sum(dot_v);
+    nrm_v = warp_sum(nrm_v);
+    if (w == 0) {
+      dot_r = warp_sum(dot_r);
+      nrm_r = warp_sum(nrm_r);
+      nrm_i = warp_sum(nrm_i);     // (without the Reference Vector every warp accumulated |img|^2 itself)
+      if (lane == 0) {
+        s_ref[0] = dot_r;
+        s_ref[1] = nrm_r;
+        s_ref[2] = nrm_i;
+      }
+    }
+    if (lane == 0) {
+      s_part[w][0] = dot_v;
+      s_part[w][1] = nrm_v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float ni = s_ref[2];
+      double sum = 0.0;
+      int n = 0;
+      float sv[TVC_MAX_VARIANTS];
+      for (int v = 0; v < V; ++v) {
+        sv[v] = 0.f;
+        if (s_cnt[v] > 0) {
+          sv[v] = cos_of(s_part[v][0], ni, s_part[v][1]);
+          sum += sv[v];
+          ++n;
+        }
+        out_s[q * V + v] = sv[v];
+      }
+      double sigma = 0.0;
+      if (n > 0) {
+        const double mu = sum / n;
+        double acc2 = 0.0;
+        for (int v = 0; v < V; ++v)
+          if (s_cnt[v] > 0) acc2 = fma(sv[v] - mu, sv[v] - mu, acc2);
+        sigma = sqrt(acc2 / n);
+      }
+      out_sigma[q] = static_cast<float>(sigma);
+      if (out_ref) out_ref[q] = n > 0 ? cos_of(s_ref[0], ni, s_ref[1]) : 0.f;
+      flags[q] = sigma > static_cast<double>(sigma_threshold) ? TVC_FLAG_SIGMA_ADV : 0;
+    }
+    __syncthreads();
+  }
+}
+
+// Same rule when the Reference Vector itself is not asked for: the (query, variant) pairs are independent,
+// so every warp takes pairs from a flat index space (no block-level synchronisation at all) and a
+// second, tiny kernel turns S [Q, V] into sigma and the decision.
+__global__ void __launch_bounds__(256, 4)
+reference_vector_flat_kernel(long long nq, int d, int V, const float* __restrict__ img, const RowSource src,
+                             const long long* __restrict__ ret_idx, int k, const float* __restrict__ gen, int m,
+                             float* __restrict__ out_s, uint8_t* __restrict__ valid) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (d & 3) == 0;
+  for (long long item = warp0; item < nq * V; item += nwarps) {
+    const long long q = item / V;
+    const float* my_row = nullptr;
+    if (lane < k) {
+      const long long gi = ret_idx[item * k + lane];
+      const int part = find_part(src, gi);
+      if (part >= 0 && src.f32[part] != nullptr) my_row = src.f32[part] + (gi - src.off[part]) * d;
+    } else if (lane < k + m) {
+      my_row = gen + (item * m + (lane - k)) * d;
+    }
+    const unsigned have = __ballot_sync(kFull, my_row != nullptr);
+    const float* irow = img + q * d;
+    float dot_v = 0.f, nrm_v = 0.f, nrm_i = 0.f;
+    for (int seg0 = 0; seg0 < d; seg0 += kRvSeg) {
+      const int seg = min(kRvSeg, d - seg0);
+      float4 acc[kRvSeg / 128];
+#pragma unroll
+      for (int c = 0; c < kRvSeg / 128; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned todo = have;
+      while (todo) {
+        const int j0 = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int j1 = todo ? __ffs(todo) - 1 : -1;
+        if (j1 >= 0) todo &= todo - 1;
+        const float* r0 = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), j0)) + seg0;
+        const float* r1 = j1 >= 0 ? reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), j1)) + seg0 : nullptr;
+        if (vec) {
+          float4 x[kRvSeg / 128], y[kRvSeg / 128];
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            const int e = (c * 32 + lane) * 4;
+            x[c] = e < seg ? __ldcs(reinterpret_cast<const float4*>(r0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y[c] = (r1 && e < seg) ? __ldcs(reinterpret_cast<const float4*>(r1 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            acc[c].x += x[c].x; acc[c].y += x[c].y; acc[c].z += x[c].z; acc[c].w += x[c].w;
+            acc[c].x += y[c].x; acc[c].y += y[c].y; acc[c].z += y[c].z; acc[c].w += y[c].w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kRvSeg / 128; ++c) {
+            float* ac = reinterpret_cast<float*>(&acc[c]);
+            for (int t = 0; t < 4; ++t) {
+              const int e = (c * 32 + lane) * 4 + t;
+              if (e < seg) ac[t] += r0[e] + (r1 ? r1[e] : 0.f);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kRvSeg / 128; ++c) {
+        const int e0 = (c * 32 + lane) * 4;
+        if (e0 >= seg) continue;
+        float xi[4];
+        if (vec) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(irow + seg0 + e0));
+          xi[0] = t4.x; xi[1] = t4.y; xi[2] = t4.z; xi[3] = t4.w;
+        } else {
+          for (int t = 0; t < 4; ++t) xi[t] = e0 + t < seg ? irow[seg0 + e0 + t] : 0.f;
+        }
+        const float* ac = reinterpret_cast<const float*>(&acc[c]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (e0 + t < seg) {
+            dot_v = fmaf(xi[t], ac[t], dot_v);
+            nrm_v = fmaf(ac[t], ac[t], nrm_v);
+            nrm_i = fmaf(xi[t], xi[t], nrm_i);
+          }
+      }
+    }
+    dot_v = warp_sum(dot_v);
+    nrm_v = warp_sum(nrm_v);
+    nrm_i = warp_sum(nrm_i);
+    if (lane == 0) {
+      out_s[item] = have ? cos_of(dot_v, nrm_i, nrm_v) : 0.f;
+      valid[item] = have ? 1 : 0;
+    }
+  }
+}
+
+__global__ void reference_sigma_kernel(long long nq, int V, const float* __restrict__ s,
+                                       const uint8_t* __restrict__ valid, float sigma_threshold,
+                                       float* __restrict__ out_sigma, uint8_t* __restrict__ flags) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  double sum = 0.0;
+  int n = 0;
+  for (int v = 0; v < V; ++v)
+    if (valid[q * V + v]) {
+      sum += s[q * V + v];
+      ++n;
+    }
+  double sigma = 0.0;
+  if (n > 0) {
+    const double mu = sum / n;
+    double acc2 = 0.0;
+    for (int v = 0; v < V; ++v)
+      if (valid[q * V + v]) acc2 = fma(s[q * V + v] - mu, s[q * V + v] - mu, acc2);
+    sigma = sqrt(acc2 / n);
+  }
+  out_sigma[q] = static_cast<float>(sigma);
+  flags[q] = sigma > static_cast<double>(sigma_threshold) ? TVC_FLAG_SIGMA_ADV : 0;
+}
+
 }  // namespace
 
 // =============================================================================== launchers
@@ -1130,6 +1412,42 @@ cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int 
   if (blocks > 148 * 8) blocks = 148 * 8;
   consistency_emb_generic_kernel<<<static_cast<int>(blocks), warps * 32, per_warp * warps, stream>>>(
       p, q, d, a, scores, flags, rows_cap);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reference_vector(int64_t q, int d, int v, const float* img, const RowSource& src,
+                                    const int64_t* ret_idx, int k, const float* gen, int m, float sigma_threshold,
+                                    float* out_s, float* out_ref, float* out_sigma, uint8_t* flags,
+                                    uint8_t* valid_ws, int sm_count, cudaStream_t stream) {
+  if (q <= 0) return cudaSuccess;
+  if (v < 1 || v > TVC_MAX_VARIANTS || k + m > 32 || k < 0 || m < 0) return cudaErrorInvalidValue;
+  if (out_ref == nullptr && valid_ws != nullptr) {
+    // independent (query, variant) pairs + a tiny sigma pass
+    long long blocks = (q * v + 7) / 8;
+    const long long cap = static_cast<long long>(sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    reference_vector_flat_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+        q, d, v, img, src, reinterpret_cast<const long long*>(ret_idx), k, gen, m, out_s, valid_ws);
+    note_launch();
+    reference_sigma_kernel<<<static_cast<int>((q + 255) / 256), 256, 0, stream>>>(q, v, out_s, valid_ws,
+                                                                                  sigma_threshold, out_sigma, flags);
+    note_launch();
+    return cudaGetLastError();
+  }
+  const size_t smem = static_cast<size_t>(v) * kRvSeg * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(reference_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TVC_MAX_VARIANTS * kRvSeg * 4);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long blocks = static_cast<long long>(sm_count) * 8;
+  if (blocks > q) blocks = q;
+  reference_vector_kernel<<<static_cast<int>(blocks), v * 32, smem, stream>>>(
+      q, d, v, img, src, reinterpret_cast<const long long*>(ret_idx), k, gen, m, sigma_threshold, out_s, out_ref,
+      out_sigma, flags);
   note_launch();
   return cudaGetLastError();
 }

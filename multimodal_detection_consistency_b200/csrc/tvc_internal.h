@@ -152,6 +152,11 @@ cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int 
                                    const ConsistencyEmbArgs& a, float* scores, uint8_t* flags,
                                    int sm_count, int force_generic, cudaStream_t stream);
 
+cudaError_t launch_reference_vector(int64_t q, int d, int v, const float* img, const RowSource& src,
+                                    const int64_t* ret_idx, int k, const float* gen, int m, float sigma_threshold,
+                                    float* out_s, float* out_ref, float* out_sigma, uint8_t* flags,
+                                    uint8_t* valid_ws, int sm_count, cudaStream_t stream);
+
 // counts every kernel launch made by the library (reported through tvc_ctx_launch_count)
 void note_launch(int n = 1);
 int64_t launches_so_far();

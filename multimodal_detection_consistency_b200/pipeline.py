@@ -130,6 +130,19 @@ class PeerExchange:
         self.barrier(rows_slice.device)
         self._operand = (area["own"] + b * area["nbytes"], q_total * v)
 
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier)."""
+        for area in self.areas.values():
+            for r, base in enumerate(area["bases"]):
+                try:
+                    if r == self.rank:
+                        self.ctx.peer_free(base)
+                    else:
+                        self.ctx.peer_close(base)
+                except Exception:  # noqa: BLE001 - teardown order at interpreter exit
+                    pass
+        self.areas.clear()
+
     def barrier(self, device):
         import torch
         if self._token is None:
@@ -507,6 +520,16 @@ class TVCScorer:
             self._mark("to_host")
         out["slice"] = (lo, hi)
         return out
+
+    def close(self):
+        """Release the peer-memory buffers of the multi-GPU path (collective: every rank calls it)."""
+        if self._exchange is not None:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            if self.dist is not None:
+                self.dist.barrier(group=self.group)
+            self._exchange.close()
+            self._exchange = None
 
     def reset_hubness(self):
         if self.k_occurrence is not None:

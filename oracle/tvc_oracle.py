@@ -523,3 +523,41 @@ def retrieval_metrics_from_topk(topk_idx: np.ndarray, relevant: Sequence[Sequenc
             idcg = sum(1.0 / math.log2(j + 2) for j in range(min(kv, len(rel))))
             out[i, 2 + 2 * nk + t] = dcg / idcg if idcg > 0 else 0.0
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# The documented reference-vector rule (README.md:474-482, 846; the reference has prose and pseudo-code
+# only, no executable form - parity for this mode is against this restatement, unpinned):
+#   per variant: mean of its top-k retrieved rows and its m generated rows -> r_v; mean_v r_v -> r;
+#   S_v = cos(image, r_v); sigma = std(S) (population); adversarial iff sigma > threshold.
+def reference_vector_rule(img: np.ndarray, ret_rows: Optional[np.ndarray], ret_idx: Optional[np.ndarray],
+                          gen: Optional[np.ndarray], sigma_threshold: float = 0.30, ret_offset: int = 0):
+    q = img.shape[0]
+    v = ret_idx.shape[1] if ret_idx is not None else gen.shape[1]
+    s = np.zeros((q, v), dtype=np.float64)
+    ref = np.zeros(q, dtype=np.float64)
+    sigma = np.zeros(q, dtype=np.float64)
+    for i in range(q):
+        means, valid = [], []
+        for j in range(v):
+            rows = []
+            if ret_idx is not None:
+                for gi in ret_idx[i, j]:
+                    gi = int(gi) - ret_offset
+                    if 0 <= gi < ret_rows.shape[0]:
+                        rows.append(ret_rows[gi].astype(np.float32))
+            if gen is not None:
+                rows.extend(gen[i, j].astype(np.float32))
+            if rows:
+                r = np.mean(np.stack(rows).astype(np.float64), axis=0)
+                means.append(r)
+                valid.append(j)
+                s[i, j] = float(np.dot(img[i].astype(np.float64), r) /
+                                max(np.linalg.norm(img[i].astype(np.float64)) * np.linalg.norm(r), 1e-8))
+        if valid:
+            sigma[i] = float(np.std(s[i, valid]))
+            rr = np.mean(np.stack(means), axis=0)
+            ref[i] = float(np.dot(img[i].astype(np.float64), rr) /
+                           max(np.linalg.norm(img[i].astype(np.float64)) * np.linalg.norm(rr), 1e-8))
+    flags = (sigma > np.float32(sigma_threshold)).astype(np.uint8) * FLAG_SIGMA_ADV
+    return s, ref, sigma, flags

@@ -68,6 +68,18 @@ for q in ([16384] if quick else [2048, 16384, 65536]):
     print(f"(b) emb   Q={q:8d}: {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s = {byt/ms/1e6/peak*100:5.1f}% of measured HBM peak  "
           f"({q/ms/1e3:.2f} M queries/s, {nret:.1f} refs/query)", flush=True)
 
+# ---- (b) README reference-vector rule: 4*d*(1 + V*(k+m)) read per query, every row used once
+kk, mm = 5, 3
+for q in ([16384] if quick else [2048, 16384]):
+    img = torch.nn.functional.normalize(torch.randn(q, d, device=dev), dim=1)
+    ridx = torch.randint(0, n, (q, V, kk), device=dev)
+    gen4 = torch.nn.functional.normalize(torch.randn(q, V, mm, d, device=dev), dim=3)
+    ms = timeit(lambda: ctx.reference_vector_rule(img, gal, ridx, gen4, want_ref=False), 5)
+    ms_ref = timeit(lambda: ctx.reference_vector_rule(img, gal, ridx, gen4), 5)
+    byt = q * (4 * d * (1 + V * (kk + mm)) + V * kk * 8 + V * 4 + 9)
+    print(f"(b) refvec Q={q:7d}: {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s = {byt/ms/1e6/peak*100:5.1f}% of measured HBM peak  "
+          f"({q/ms/1e3:.2f} M queries/s; with the cross-variant Reference Vector {ms_ref*1e3:.1f} us)", flush=True)
+
 # ---- (c) k-occurrence: 8*M*k read + 4*N written (+ 4*N zero fill)
 for (m, k, nb) in ([(5_000_000, 10, 1_000_000)] if quick else [(50_000, 10, 118_287), (500_000, 10, 1_000_000), (5_000_000, 10, 1_000_000), (5_000_000, 10, 10_000)]):
     idx = (nb * torch.rand(m, k, device=dev) ** 3).long().clamp_(0, nb - 1)      # skewed: hubs

@@ -206,3 +206,44 @@ def test_emb_mode_pipelined_equals_generic(tvc_ctx):
         assert np.array_equal(a[1], b[1])
         for x, y in zip(a[2], b[2]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("q,d,V,k,m,with_ret,with_gen", [
+    (300, 768, 5, 5, 3, True, True),       # README: top_k = 5, m = 3 (README.md:240,252)
+    (257, 768, 8, 10, 0, True, False),
+    (64, 100, 3, 0, 4, False, True),       # generated rows only, d not a multiple of 4 * 32
+    (33, 2048, 16, 20, 12, True, True),    # widest: k + m = 32, two row segments
+    (1, 64, 1, 1, 0, True, False),
+])
+def test_reference_vector_rule(tvc_ctx, q, d, V, k, m, with_ret, with_gen):
+    """tvc_reference_vector_rule against the oracle restatement of README.md:474-482 (the reference has no
+    executable form of this rule): S within 2e-3 (observed ~1e-6), sigma likewise, flags identical
+    outside a 1e-5 band around the threshold."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(q + d)
+    g = O.synth_gallery(2000, d, seed=3, clusters=16)
+    img = O.l2_normalize(rng.standard_normal((q, d)).astype(np.float32))
+    ret_idx = gen = gal = None
+    if with_ret:
+        gal = tvc.Gallery(g, global_row_offset=500, ctx=tvc_ctx)
+        ret_idx = rng.integers(500, 2500, (q, V, k)).astype(np.int64)
+        ret_idx[rng.uniform(size=ret_idx.shape) < 0.1] = -1
+        ret_idx[0, 0, :] = -1                                  # a variant without retrieved rows
+    if with_gen:
+        gen = O.l2_normalize(rng.standard_normal((q * V * m, d)).astype(np.float32)).reshape(q, V, m, d)
+    thr = 0.02
+    s, ref, sig, fl = tvc_ctx.reference_vector_rule(img, gal, ret_idx, gen, sigma_threshold=thr)
+    ws, wref, wsig, wfl = O.reference_vector_rule(img, g, ret_idx, gen, thr, ret_offset=500)
+    assert np.abs(s - ws).max() <= 5e-6 and np.abs(ref - wref).max() <= 5e-6 and np.abs(sig - wsig).max() <= 5e-6
+    ok = np.abs(wsig - thr) > 1e-5
+    assert np.array_equal(fl[ok], wfl[ok])
+    # without the Reference Vector the (query, variant) pairs run as independent warps: same S, sigma, flags
+    s2, none, sig2, fl2 = tvc_ctx.reference_vector_rule(img, gal, ret_idx, gen, sigma_threshold=thr, want_ref=False)
+    assert none is None and np.abs(s2 - ws).max() <= 5e-6 and np.abs(sig2 - wsig).max() <= 5e-6
+    assert np.array_equal(fl2[ok], wfl[ok])
+    import torch
+    ts = tvc_ctx.reference_vector_rule(torch.from_numpy(img).cuda(), gal,
+                                       torch.from_numpy(ret_idx).cuda() if with_ret else None,
+                                       torch.from_numpy(gen).cuda() if with_gen else None, sigma_threshold=thr)
+    torch.cuda.synchronize()
+    assert np.array_equal(ts[0].cpu().numpy(), s) and np.array_equal(ts[3].cpu().numpy(), fl)

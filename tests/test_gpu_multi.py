@@ -46,6 +46,7 @@ def _worker(rank, world, port, out_dir):
                    device=f"cuda:{rank}")
     assert sc._gallery_group is not None          # the peer-memory path, not the staged fetch
     assert sc._exchange is not None
+    ex = sc._exchange
     for tag in ("peer", "peer2", "nccl"):
         if tag == "nccl":
             sc._exchange = None                   # candidate all-to-all + merge kernel instead
@@ -56,6 +57,8 @@ def _worker(rank, world, port, out_dir):
         np.savez(Path(out_dir) / f"{tag}_r{rank}.npz", lo=lo, hi=hi, scores=out["scores"].numpy(),
                  flags=out["flags"].numpy(), topk_idx=out["topk_idx"].numpy(), topk_sim=out["topk_sim"].numpy(),
                  bank_idx=out["bank_idx"].numpy(), hub=sc.k_occurrence.cpu().numpy())
+    sc._exchange = ex
+    sc.close()
     dist.barrier()
     dist.destroy_process_group()
 

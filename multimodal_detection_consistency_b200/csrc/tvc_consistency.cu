@@ -569,11 +569,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // group).  Groups: 0 = image/text/variants (always resident), 1 = retrieval rows, 2 = generative rows.
 struct EmbTask {
   short a_row, b_row0;      // stage row numbers
-  unsigned char nb, norms;  // B rows, 1 = also write |A|^2 and |B|^2
+  unsigned char nb, norms;  // B rows; 1 = image task (also writes |A|^2, |B|^2), 0 / 2 = off-diagonal /
+                            // diagonal block of a group's pair table (`pad` A rows x nb B rows)
   unsigned char ga, gb;     // validity groups of A and of the B rows
   short ia, ib0;            // index of A / first B inside its group
   short out;                // result offset of (A, B0); consecutive B -> consecutive floats
-  short pad;
+  short pad;                // A rows of a block task
 };
 
 // per-stage control block and results (shared memory)
@@ -597,6 +598,7 @@ struct EmbLists {
   float sg[TVC_MAX_REFS];
   float sx[kXMax];
   float sq[kMaxStageRows];   // |row| of every stage row
+  float dimg[kMaxStageRows]; // image . row (copied out so that the stage can be released early)
   long long kept_idx[TVC_MAX_REFS];
   int kept_slot[TVC_MAX_REFS];
   int info[4];   // kept, need_slow
@@ -607,7 +609,7 @@ struct EmbLists {
 // (bit-identical results).  Returns the total of value number bitrev-ish index `multi_index<N>(lane)`.
 template <int N>
 __device__ __forceinline__ float warp_sum_multi(float (&v)[N], int lane) {
-  static_assert(N == 8 || N == 16, "N");
+  static_assert(N == 8 || N == 16 || N == 32, "N");
   int off = 16;
 #pragma unroll
   for (int n = N; n > 1; n >>= 1, off >>= 1) {
@@ -625,6 +627,9 @@ __device__ __forceinline__ float warp_sum_multi(float (&v)[N], int lane) {
 }
 template <int N>
 __device__ __forceinline__ int multi_index(int lane) {
+  if (N == 32)
+    return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2) | (((lane >> 1) & 1) << 3) |
+           ((lane & 1) << 4);
   if (N == 16) return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2) | (((lane >> 1) & 1) << 3);
   return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2);
 }
@@ -682,6 +687,52 @@ __device__ __forceinline__ void run_task_nb(const EmbTask& t, const float* rows,
       }
     }
   }
+}
+
+// Block task: the pair dots of up to 5 rows A against up to 5 rows B of one group (DIAG: A == B, pairs
+// i < j only).  25 accumulators per lane against 10 row reads - the tasks are bound by shared-memory
+// bandwidth (128 B/clk/SM), and one-row-against-five tasks read 55 rows for the 45 pairs of 10
+// references where three block tasks read 20.  Per pair the additions happen in the same order as
+// everywhere else (lane-strided float4s, then the butterfly tree), so results stay bit-identical.
+template <bool DIAG>
+__device__ __forceinline__ void run_block_task(const EmbTask& t, int na, int nb, const float* rows, int d,
+                                               float* out) {
+  const int lane = threadIdx.x & 31;
+  const float4* A = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.a_row) * d);
+  const float4* B = reinterpret_cast<const float4*>(rows + static_cast<size_t>(t.b_row0) * d);
+  const int d4 = d >> 2;
+  float v[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = 0.f;
+  for (int c = lane; c < d4; c += 32) {
+    float4 x[kJB];
+#pragma unroll
+    for (int i = 0; i < kJB; ++i) x[i] = i < na ? A[static_cast<size_t>(i) * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kJB; ++j) {
+      if (j >= nb) continue;
+      const float4 y = DIAG ? x[j] : B[static_cast<size_t>(j) * d4 + c];
+      // component-major: the (up to) five chains of column j advance together, so no FMA waits on
+      // the one issued just before it
+#pragma unroll
+      for (int i = 0; i < kJB; ++i)
+        if (!DIAG || i < j) v[i * kJB + j] = fmaf(x[i].x, y.x, v[i * kJB + j]);
+#pragma unroll
+      for (int i = 0; i < kJB; ++i)
+        if (!DIAG || i < j) v[i * kJB + j] = fmaf(x[i].y, y.y, v[i * kJB + j]);
+#pragma unroll
+      for (int i = 0; i < kJB; ++i)
+        if (!DIAG || i < j) v[i * kJB + j] = fmaf(x[i].z, y.z, v[i * kJB + j]);
+#pragma unroll
+      for (int i = 0; i < kJB; ++i)
+        if (!DIAG || i < j) v[i * kJB + j] = fmaf(x[i].w, y.w, v[i * kJB + j]);
+    }
+  }
+  const float r = warp_sum_multi<32>(v, lane);
+  const int idx = multi_index<32>(lane);
+  const int i = idx / kJB, j = idx - i * kJB;
+  if (idx < kJB * kJB && i < na && j < nb && (!DIAG || i < j))
+    out[(t.ia + i) * TVC_MAX_REFS + t.ib0 + j] = r;
 }
 
 template <bool NORMS>
@@ -776,7 +827,7 @@ __device__ int select_from_stage(const tvc_detector_params& p, EmbStage* st, int
 // producer side: take the first `cap` distinct valid indices of a candidate list, start their copies
 __device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const RowSource& src,
                                                    const long long* cand, int ncand, int cap, float* rows_grp,
-                                                   int d, uint64_t* bar) {
+                                                   int d, uint64_t* bar, long long first_chunk) {
   const int lane = threadIdx.x & 31;
   const uint32_t row_bytes = static_cast<uint32_t>(d) * 4u;
   int n = 0, end = 0;
@@ -785,7 +836,7 @@ __device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const 
     long long gi = -1;
     int part = -1;
     if (c < ncand) {
-      gi = cand[c];
+      gi = c0 == 0 ? first_chunk : cand[c];   // the first 32 candidates were loaded a query ahead
       part = find_part(src, gi);
     }
     bool take = part >= 0;
@@ -861,17 +912,21 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     for (int b = 0; b < R; b += kJB) add(0, row_ret + b, min(kJB, R - b), 1, 0, 1, 0, b, row_ret + b);
     for (int b = 0; b < G; b += kJB)
       add(0, row_gen + b, min(kJB, G - b), 1, 0, gen_direct ? 3 : 2, 0, b, row_gen + b);
-    for (int i = 0; i < V; ++i)
-      for (int b = i + 1; b < V; b += kJB)
-        add(row_var + i, row_var + b, min(kJB, V - b), 0, 0, 0, i, b, i * TVC_MAX_VARIANTS + b);
+    // pair tables of a group in 5 x 5 blocks (diagonal blocks: pairs i < j only)
+    static_assert(TVC_MAX_REFS == TVC_MAX_VARIANTS, "one pair-table stride");
+    auto add_pairs = [&](int row0, int n, int grp) {
+      for (int bi = 0; bi < n; bi += kJB)
+        for (int bj = bi; bj < n; bj += kJB) {
+          const int na = min(kJB, n - bi), nb = min(kJB, n - bj);
+          if (bi == bj && na < 2) continue;
+          add(row0 + bi, row0 + bj, nb, bi == bj ? 2 : 0, grp, grp, bi, bj, 0);
+          s_tasks[nt - 1].pad = static_cast<short>(na);
+        }
+    };
+    add_pairs(row_var, V, 0);
     if (p.dedup_threshold > -1.0f) {
-      for (int i = 0; i < R; ++i)
-        for (int b = i + 1; b < R; b += kJB)
-          add(row_ret + i, row_ret + b, min(kJB, R - b), 0, 1, 1, i, b, i * TVC_MAX_REFS + b);
-      if (gen_idx)
-        for (int i = 0; i < G; ++i)
-          for (int b = i + 1; b < G; b += kJB)
-            add(row_gen + i, row_gen + b, min(kJB, G - b), 0, 2, 2, i, b, i * TVC_MAX_REFS + b);
+      add_pairs(row_ret, R, 1);
+      if (gen_idx) add_pairs(row_gen, G, 2);
     }
     s_ntasks = nt;
     s_next = 0u;
@@ -893,7 +948,19 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     if (w - kEmbConsumers >= n_stages) return;
     const int s = w - kEmbConsumers;     // this producer's stage
     uint32_t round = 0;
+    // the first 32 candidates of each list are read one query ahead, so the dependent global load is
+    // not on the stage's critical path (it completes while the producer is parked on `empty`)
+    long long pre_ret = -1, pre_gen = -1;
+    auto preload = [&](long long qn) {
+      if (has_ret && lane < a.n_ret_cand)
+        pre_ret = (reinterpret_cast<const long long*>(a.ret_idx) + qn * a.n_ret_cand)[lane];
+      if (gen_idx && lane < a.n_gen_cand)
+        pre_gen = (reinterpret_cast<const long long*>(a.gen_idx) + qn * a.n_gen_cand)[lane];
+    };
+    if (s < my_n) preload(blockIdx.x + s * static_cast<long long>(gridDim.x));
     for (long long i = s; i < my_n; i += n_stages, ++round) {
+      const long long cur_ret = pre_ret, cur_gen = pre_gen;
+      if (i + n_stages < my_n) preload(blockIdx.x + (i + n_stages) * static_cast<long long>(gridDim.x));
       if (round > 0) mbar_wait_parked(&s_empty[s], (round - 1) & 1u);
       const long long q = blockIdx.x + i * static_cast<long long>(gridDim.x);
       EmbStage* st = &s_stage[s];
@@ -912,10 +979,10 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
       uint32_t bytes = static_cast<uint32_t>(ndirect) * row_bytes;
       if (has_ret)
         bytes += prefetch_group(st, 0, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
-                                a.n_ret_cand, R, rows + static_cast<size_t>(row_ret) * d, d, bar);
+                                a.n_ret_cand, R, rows + static_cast<size_t>(row_ret) * d, d, bar, cur_ret);
       if (gen_idx)
         bytes += prefetch_group(st, 1, a.genr, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand,
-                                a.n_gen_cand, G, rows + static_cast<size_t>(row_gen) * d, d, bar);
+                                a.n_gen_cand, G, rows + static_cast<size_t>(row_gen) * d, d, bar, cur_gen);
       if (lane == 0) {
         st->q = q;
         if (!has_ret) { st->pf_n[0] = 0; st->pf_end[0] = 0; }
@@ -947,6 +1014,7 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
     mbar_wait_parked(&s_full[s], par);
     if (lane == 0) TVC_TRACE(i, 2);
+    const unsigned long long t_task0 = a.trace != nullptr ? gtime_ns() : 0ull;
     {
       const EmbTask tk = s_tasks[t];
       const int valid1 = st->pf_n[0], valid2 = st->pf_n[1], valid3 = st->n_gen_direct;
@@ -954,13 +1022,21 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
       const int vb = tk.gb == 0 ? 1 << 20 : (tk.gb == 1 ? valid1 : (tk.gb == 2 ? valid2 : valid3));
       const int nb = min(static_cast<int>(tk.nb), vb - tk.ib0);
       if (tk.ia < va && nb > 0) {
-        if (tk.norms)
+        if (tk.norms == 1) {
           run_task<true>(tk, nb, rows, d, st, st->d_img);
-        else
-          run_task<false>(tk, nb, rows, d, st, tk.ga == 0 ? st->d_var : st->d_ref[tk.ga - 1]);
+        } else {
+          const int na = min(static_cast<int>(tk.pad), va - tk.ia);
+          float* tab = tk.ga == 0 ? st->d_var : st->d_ref[tk.ga - 1];
+          if (tk.norms == 2)
+            run_block_task<true>(tk, na, nb, rows, d, tab);
+          else
+            run_block_task<false>(tk, na, nb, rows, d, tab);
+        }
       }
     }
     __syncwarp();
+    if (a.trace != nullptr && blockIdx.x == 0 && i < 512 && lane == 0)   // slot 6: longest task (ns << 8 | task)
+      atomicMax(a.trace + i * 8 + 6, ((gtime_ns() - t_task0) << 8) | static_cast<unsigned long long>(t));
     if (lane == 0) mbar_arrive(&s_done[s]);     // one arrival per unit, executed or skipped
     if (t != ntasks - 1) continue;
 
@@ -968,42 +1044,100 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     mbar_wait_parked(&s_done[s], par);
     if (lane == 0) TVC_TRACE(i, 3);
     const long long q = st->q;
-    for (int r = lane; r < stage_rows; r += 32) L->sq[r] = sqrtf(st->nrm2[r]);
-    __syncwarp();
-    const float sq_img = L->sq[0];
-    const float s0 = st->d_img[1] / fmaxf(sq_img * L->sq[1], 1e-8f);
-    if (lane < V) L->sv[lane] = st->d_img[row_var + lane] / fmaxf(sq_img * L->sq[row_var + lane], 1e-8f);
     const int nx = V * (V - 1) / 2;
-    for (int e = lane; e < nx; e += 32) {
-      // e-th pair (ii < jj) in row-major order of the upper triangle
-      int ii = 0, rem = e;
-      while (rem >= V - 1 - ii) {
-        rem -= V - 1 - ii;
-        ++ii;
+    const float thr = p.dedup_threshold;
+    // Can the greedy de-duplication drop anything?  cos(i, j) > thr needs dot > 0 and
+    // dot^2 > thr^2 |i|^2 |j|^2, which costs no division or square root; the test below is that
+    // inequality loosened by 1e-4 (and always true for thr <= 0 or degenerate rows), one lane per row.
+    bool maybe_dup = false;
+    if (thr > -1.0f) {
+      const float t2 = thr > 0.f ? thr * thr * (1.0f - 1e-4f) : -1.f;
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+        if (grp == 0 ? !has_ret : !gen_idx) continue;
+        const int n = st->pf_n[grp], base = grp == 0 ? row_ret : row_gen;
+        if (lane < n) {
+          const float ns = st->nrm2[base + lane];
+          for (int j = 0; j < lane; ++j) {
+            const float dot = st->d_ref[grp][j * TVC_MAX_REFS + lane], nn = st->nrm2[base + j] * ns;
+            maybe_dup |= t2 < 0.f || nn < 1e-12f || (dot > 0.f && dot * dot > t2 * nn);
+          }
+        }
       }
-      const int jj = ii + 1 + rem;
-      L->sx[e] = st->d_var[ii * TVC_MAX_VARIANTS + jj] / fmaxf(L->sq[row_var + ii] * L->sq[row_var + jj], 1e-8f);
     }
-    int nr = 0;
-    if (has_ret)
-      nr = select_from_stage(p, st, 0, rows, d, row_ret, a.ret,
-                             reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand, a.n_ret_cand, R,
-                             L->sr, L);
-    int ng = 0;
-    if (gen_direct) {
-      ng = st->n_gen_direct;
-      if (lane < ng) L->sg[lane] = st->d_img[row_gen + lane] / fmaxf(sq_img * L->sq[row_gen + lane], 1e-8f);
-    } else if (gen_idx) {
-      ng = select_from_stage(p, st, 1, rows, d, row_gen, a.genr,
-                             reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand, a.n_gen_cand, G,
-                             L->sg, L);
+    maybe_dup = __any_sync(kFull, maybe_dup);
+    float s0;
+    int nr = 0, ng = 0;
+    if (!maybe_dup) {
+      // fast path (the common case): nothing can be dropped, so the first min(cap, prefetched) rows are
+      // the references.  Copy the ~50 scalars still needed, hand the stage back, then do the divisions.
+      nr = has_ret ? min(R, st->pf_n[0]) : 0;
+      ng = gen_direct ? st->n_gen_direct : (gen_idx ? min(G, st->pf_n[1]) : 0);
+      for (int r = lane; r < stage_rows; r += 32) {
+        L->sq[r] = st->nrm2[r];
+        L->dimg[r] = st->d_img[r];
+      }
+      for (int e = lane; e < nx; e += 32) {
+        int ii = 0, rem = e;     // e-th pair (ii < jj) in row-major order of the upper triangle
+        while (rem >= V - 1 - ii) {
+          rem -= V - 1 - ii;
+          ++ii;
+        }
+        L->sx[e] = st->d_var[ii * TVC_MAX_VARIANTS + ii + 1 + rem];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      if (lane == 0) TVC_TRACE(i, 4);
+      for (int r = lane; r < stage_rows; r += 32) L->sq[r] = sqrtf(L->sq[r]);
+      __syncwarp();
+      const float sq_img = L->sq[0];
+      s0 = L->dimg[1] / fmaxf(sq_img * L->sq[1], 1e-8f);
+      if (lane < V) L->sv[lane] = L->dimg[row_var + lane] / fmaxf(sq_img * L->sq[row_var + lane], 1e-8f);
+      for (int e = lane; e < nx; e += 32) {
+        int ii = 0, rem = e;
+        while (rem >= V - 1 - ii) {
+          rem -= V - 1 - ii;
+          ++ii;
+        }
+        L->sx[e] = L->sx[e] / fmaxf(L->sq[row_var + ii] * L->sq[row_var + ii + 1 + rem], 1e-8f);
+      }
+      if (lane < nr) L->sr[lane] = L->dimg[row_ret + lane] / fmaxf(sq_img * L->sq[row_ret + lane], 1e-8f);
+      if (lane < ng) L->sg[lane] = L->dimg[row_gen + lane] / fmaxf(sq_img * L->sq[row_gen + lane], 1e-8f);
+      __syncwarp();
+    } else {
+      for (int r = lane; r < stage_rows; r += 32) L->sq[r] = sqrtf(st->nrm2[r]);
+      __syncwarp();
+      const float sq_img = L->sq[0];
+      s0 = st->d_img[1] / fmaxf(sq_img * L->sq[1], 1e-8f);
+      if (lane < V) L->sv[lane] = st->d_img[row_var + lane] / fmaxf(sq_img * L->sq[row_var + lane], 1e-8f);
+      for (int e = lane; e < nx; e += 32) {
+        int ii = 0, rem = e;
+        while (rem >= V - 1 - ii) {
+          rem -= V - 1 - ii;
+          ++ii;
+        }
+        const int jj = ii + 1 + rem;
+        L->sx[e] = st->d_var[ii * TVC_MAX_VARIANTS + jj] / fmaxf(L->sq[row_var + ii] * L->sq[row_var + jj], 1e-8f);
+      }
+      if (has_ret)
+        nr = select_from_stage(p, st, 0, rows, d, row_ret, a.ret,
+                               reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand, a.n_ret_cand, R,
+                               L->sr, L);
+      if (gen_direct) {
+        ng = st->n_gen_direct;
+        if (lane < ng) L->sg[lane] = st->d_img[row_gen + lane] / fmaxf(sq_img * L->sq[row_gen + lane], 1e-8f);
+      } else if (gen_idx) {
+        ng = select_from_stage(p, st, 1, rows, d, row_gen, a.genr,
+                               reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand, a.n_gen_cand, G,
+                               L->sg, L);
+      }
+      // everything still needed lives in this warp's lists: hand the stage back
+      // (the slow path may have written rows with ordinary stores; the next writer is a bulk copy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      if (lane == 0) TVC_TRACE(i, 4);
     }
-    // everything still needed lives in this warp's lists: hand the stage back
-    // (the slow path may have written rows with ordinary stores; the next writer is a bulk copy)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);
-    if (lane == 0) TVC_TRACE(i, 4);
     // similarity lists -> global; the statistics kernel (consistency_sims_kernel) takes it from there
     const int Vp = p.n_variants, Rp = p.n_retrieval, Gp = p.n_generative;
     if (lane == 0) {

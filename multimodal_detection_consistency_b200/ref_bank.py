@@ -87,6 +87,11 @@ class ReferenceBank:
         self._gallery: Optional[Gallery] = None
         self._row_items: List[ReferenceItem] = []
         self._row_of: Dict[int, int] = {}
+        # write-through persistence: an append-only journal next to the reference's four JSON files, folded
+        # into them every `journal_compact_every` operations (the reference rewrites all of references.json
+        # on every insert, src/ref_bank.py:163,505-516 - O(B) per insert)
+        self.journal_compact_every = 256
+        self._journal_ops = 0
         if self.config.persistence_enabled:
             Path(self.config.save_path).mkdir(parents=True, exist_ok=True)
         self._load_from_disk()
@@ -143,10 +148,14 @@ class ReferenceBank:
                 self.references.append(item)
                 self._dev_append([item])
                 self.stats["total_added"] += 1
+                clustered = False
                 if self.config.auto_clustering and len(self.references) % self.config.clustering_interval == 0:
-                    self._perform_clustering()
+                    clustered = self._perform_clustering()
                 if self.config.persistence_enabled:
-                    self._save_to_disk()
+                    if clustered:
+                        self._save_to_disk()              # cluster ids changed on many items: fold everything
+                    else:
+                        self._journal({"op": "add", "item": item.to_dict()})
                 return True
         except Exception as e:  # noqa: BLE001
             logger.error("add_reference failed: %s", e)
@@ -272,6 +281,8 @@ class ReferenceBank:
         item = self.references.pop(idx)
         self._dev_remove(item)
         self._update_clusters_after_removal(idx)
+        if self.config.persistence_enabled:
+            self._journal({"op": "remove", "index": int(idx)})
 
     def _remove_reference(self):
         """src/ref_bank.py:365-399."""
@@ -335,6 +346,26 @@ class ReferenceBank:
         return float(np.dot(vec1, vec2) / (n1 * n2))
 
     # ------------------------------------------------------------------ persistence (:505-576)
+    _JOURNAL = "references.journal.jsonl"
+
+    def _journal(self, op: Dict[str, Any]):
+        """Append one operation; fold the journal into the JSON files every journal_compact_every ops."""
+        try:
+            with open(Path(self.config.save_path) / self._JOURNAL, "a") as f:
+                f.write(json.dumps(op) + "\n")
+            self._journal_ops += 1
+            if self._journal_ops >= self.journal_compact_every:
+                self._save_to_disk()
+        except Exception as e:  # noqa: BLE001
+            logger.error("journal write failed: %s", e)
+
+    def flush(self):
+        """Fold the journal into references.json / clusters.json / stats.json / config.json (the layout the
+        reference reads back, src/ref_bank.py:537-576)."""
+        with self._lock:
+            if self.config.persistence_enabled:
+                self._save_to_disk()
+
     def _save_to_disk(self):
         try:
             root = Path(self.config.save_path)
@@ -346,6 +377,10 @@ class ReferenceBank:
                 indent=2))
             (root / "stats.json").write_text(json.dumps(self.stats, indent=2))
             (root / "config.json").write_text(json.dumps(asdict(self.config), indent=2))
+            j = root / self._JOURNAL
+            if j.exists():
+                j.unlink()
+            self._journal_ops = 0
         except Exception as e:  # noqa: BLE001
             logger.error("save to disk failed: %s", e)
 
@@ -353,9 +388,9 @@ class ReferenceBank:
         try:
             root = Path(self.config.save_path)
             refs_file = root / "references.json"
-            if not self.config.persistence_enabled or not refs_file.exists():
+            if not self.config.persistence_enabled or not (refs_file.exists() or (root / self._JOURNAL).exists()):
                 return
-            data = json.loads(refs_file.read_text())
+            data = json.loads(refs_file.read_text()) if refs_file.exists() else []
             if isinstance(data, dict):  # the snapshot shipped in cache/ref_bank wraps the list
                 data = data.get("references", [])
             self.references = [ReferenceItem.from_dict(d) for d in data]
@@ -368,6 +403,20 @@ class ReferenceBank:
             sf = root / "stats.json"
             if sf.exists():
                 self.stats.update(json.loads(sf.read_text()))
+            jf = root / self._JOURNAL
+            if jf.exists():                                 # operations made after the last fold
+                for line in jf.read_text().splitlines():
+                    if not line.strip():
+                        continue
+                    op = json.loads(line)
+                    if op.get("op") == "add":
+                        self.references.append(ReferenceItem.from_dict(op["item"]))
+                        self.stats["total_added"] += 1
+                    elif op.get("op") == "remove" and 0 <= op["index"] < len(self.references):
+                        self.references.pop(op["index"])
+                        self._update_clusters_after_removal(op["index"])
+                        self.stats["total_removed"] += 1
+                    self._journal_ops += 1
             self._dev_rebuild()
         except Exception as e:  # noqa: BLE001
             logger.error("load from disk failed: %s", e)

@@ -135,7 +135,18 @@ def test_reference_bank_insert_dedup_eviction_persistence(tmp_path):
         assert len(got) >= 1 and got[0][0].metadata["i"] == 30 + int(idx[0])
     sims = bank._compute_similarities(vecs[33])
     assert np.abs(sims - O.ref_bank_similarities(live, vecs[33])).max() <= 2e-3
-    # reload from the 4-file JSON layout (src/ref_bank.py:505-576)
+    # write-through journal: 110 operations so far, nothing folded yet; a reload replays it
+    root = tmp_path / "bank"
+    assert (root / "references.journal.jsonl").exists() and not (root / "references.json").exists()
+    bank2 = ReferenceBank(cfg)
+    assert len(bank2.references) == 50 and bank2.stats["total_added"] == 80 and bank2.stats["total_removed"] == 30
+    assert [r.metadata["i"] for r in bank2.references] == list(range(30, 80))
+    # fold into the reference's 4-file JSON layout (src/ref_bank.py:505-576) and reload from that
+    bank.flush()
+    import json
+    assert not (root / "references.journal.jsonl").exists()
+    assert len(json.loads((root / "references.json").read_text())) == 50
+    assert sorted(p.name for p in root.iterdir()) == ["clusters.json", "config.json", "references.json", "stats.json"]
     bank2 = ReferenceBank(cfg)
     assert len(bank2.references) == 50
     a, b = bank.query_similar(vecs[60], 3, 0.5), bank2.query_similar(vecs[60], 3, 0.5)

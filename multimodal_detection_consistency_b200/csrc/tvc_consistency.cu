@@ -880,6 +880,7 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
   __shared__ EmbTask s_tasks[kMaxTasks];
   __shared__ int s_ntasks;
   __shared__ unsigned s_next;
+  __shared__ unsigned s_released[kEmbMaxStages];   // queries finished per stage (see the consumer loop)
   __shared__ EmbStage s_stage[kEmbMaxStages];
   __shared__ EmbLists s_lists[kEmbConsumers];
   float* s_rows = reinterpret_cast<float*>(s_raw);
@@ -930,6 +931,7 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     }
     s_ntasks = nt;
     s_next = 0u;
+    for (int s = 0; s < kEmbMaxStages; ++s) s_released[s] = 0u;
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_done[s], static_cast<uint32_t>(nt));   // one arrival per task
@@ -1012,6 +1014,19 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     const long long i = iu;
     EmbStage* st = &s_stage[s];
     float* rows = s_rows + static_cast<size_t>(s) * stage_floats;
+    // An mbarrier wait names its phase by one parity bit, so a waiter may be at most one phase ahead.
+    // With fewer tasks per query than consumer warps the unit queue can run two rounds ahead of a stage
+    // that a slow finisher (the de-duplication slow path) still holds: a unit of round r would then see
+    // the completed phase r - 2 and start on the previous query's rows.  Wait until every earlier round
+    // of the stage has been released before naming the phase.
+    if (round > 0) {
+      unsigned rel = 0;
+      do {
+        if (lane == 0) rel = *reinterpret_cast<volatile unsigned*>(&s_released[s]);
+        rel = __shfl_sync(kFull, rel, 0);
+        if (rel < round) __nanosleep(200);
+      } while (rel < round);
+    }
     mbar_wait_parked(&s_full[s], par);
     if (lane == 0) TVC_TRACE(i, 2);
     const unsigned long long t_task0 = a.trace != nullptr ? gtime_ns() : 0ull;
@@ -1086,7 +1101,10 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
         L->sx[e] = st->d_var[ii * TVC_MAX_VARIANTS + ii + 1 + rem];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
+      if (lane == 0) {
+        atomicAdd(&s_released[s], 1u);
+        mbar_arrive(&s_empty[s]);
+      }
       if (lane == 0) TVC_TRACE(i, 4);
       for (int r = lane; r < stage_rows; r += 32) L->sq[r] = sqrtf(L->sq[r]);
       __syncwarp();
@@ -1135,7 +1153,10 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
       // (the slow path may have written rows with ordinary stores; the next writer is a bulk copy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
+      if (lane == 0) {
+        atomicAdd(&s_released[s], 1u);
+        mbar_arrive(&s_empty[s]);
+      }
       if (lane == 0) TVC_TRACE(i, 4);
     }
     // similarity lists -> global; the statistics kernel (consistency_sims_kernel) takes it from there

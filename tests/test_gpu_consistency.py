@@ -247,3 +247,35 @@ def test_reference_vector_rule(tvc_ctx, q, d, V, k, m, with_ret, with_gen):
                                        torch.from_numpy(gen).cuda() if with_gen else None, sigma_threshold=thr)
     torch.cuda.synchronize()
     assert np.array_equal(ts[0].cpu().numpy(), s) and np.array_equal(ts[3].cpu().numpy(), fl)
+
+
+def test_emb_mode_repeatable_when_slow_finishers_hold_stages(tvc_ctx):
+    """Regression: with fewer tasks per query than consumer warps the unit queue could run two rounds ahead
+    of a stage held by a slow finisher (de-duplication slow path) and alias the mbarrier phase parity.
+    d = 256 gives four 20 KB stages and ten tasks per query; 2 % duplicate gallery rows make slow paths
+    frequent.  Every run must equal the one-warp-per-query kernel bit for bit."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    d, nq, V, k = 256, 3000, 5, 10
+    g = O.synth_gallery(20000, d, seed=3, clusters=128, dup_rate=0.02)
+    bank = O.synth_gallery(3000, d, seed=4, clusters=128, dup_rate=0.02)
+    img, txt, var = (torch.from_numpy(x).cuda() for x in O.synth_queries(g, nq, V, seed=5))
+    gal, bnk = tvc.Gallery(g, ctx=tvc_ctx), tvc.Gallery(bank, ctx=tvc_ctx)
+    _, ridx = gal.search(var, k)
+    _, gidx = bnk.search(var, k)
+    ridx, gidx = ridx.reshape(nq, V * k), gidx.reshape(nq, V * k)
+    params = tvc.default_params()
+
+    def run():
+        s, f = tvc_ctx.consistency_emb(params, img, txt, var, ret_gallery=gal, ret_idx=ridx, gen_gallery=bnk,
+                                       gen_idx=gidx)
+        torch.cuda.synchronize()
+        return s.clone(), f.clone()
+    tvc_ctx.set_option("emb_generic", 1)
+    try:
+        want_s, want_f = run()
+    finally:
+        tvc_ctx.set_option("emb_generic", 0)
+    for _ in range(6):
+        s, f = run()
+        assert torch.equal(s, want_s) and torch.equal(f, want_f)

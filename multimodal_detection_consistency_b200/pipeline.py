@@ -76,14 +76,13 @@ class PeerExchange:
     double-buffered receive area [2][P, rows_in_slice, KP] (values + indices) allocated through
     libtvc and mapped by all peers with CUDA IPC; phase 1 of the search stores each row's candidates
     straight into the owner's area over NVLink, one stream-ordered barrier (a 4-byte all-reduce)
-    separates it from phase 2, which re-ranks on the owner from local + peer fp32 masters."""
+    separates the phase 1 of all searches of a batch from their phase 2, which re-ranks on the owner from local + peer fp32 masters."""
 
     def __init__(self, ctx, dist, group, world, rank):
         self.ctx, self.dist, self.group, self.world, self.rank = ctx, dist, group, world, rank
         self.areas = {}           # (tag, rows_per_slice, kp) -> dict(own=[(val, idx)] * 2, peers=[[(val, idx)] * 2] * P)
         self.parity = {}
         self._token = None
-        self._side = None
         self._operand = None
 
     def _area(self, tag, rows_per_slice: int, kp: int):
@@ -149,10 +148,9 @@ class PeerExchange:
             self._token = torch.zeros(1, dtype=torch.int32, device=device)
         self.dist.all_reduce(self._token, group=self.group)
 
-    def search(self, tag, gallery, group_gallery, rows_slice, q_total: int, v: int, lo: int, hi: int, k: int,
-               threshold: float, defer: bool = False):
-        """Global top-k of this rank's query slice [lo, hi): (sims [(hi-lo)*v, k], idx).  rows_slice are
-        the slice's fp32 rows (re-ranking); the GEMM operand is the one begin_batch spread."""
+    def scatter(self, tag, gallery, q_total: int, v: int, k: int):
+        """Phase 1 on this rank's shard: GEMM + top-KP of ALL rows (the operand begin_batch spread), the
+        candidates stored into the slice owners' receive buffers.  Returns the token collect() needs."""
         per = -(-q_total // self.world)
         rows_per_slice = per * v
         kp = self.ctx.candidate_width(k)
@@ -166,38 +164,19 @@ class PeerExchange:
             sc.val[r] = base + b * area["vb"]
             sc.idx[r] = base + 2 * area["vb"] + b * area["ib"]
         gallery.search_candidates(self._operand, k, sc)
-        self.barrier(rows_slice.device)
-        mine = (hi - lo) * v
-        if mine == 0:
-            import torch
-            empty = (torch.empty((0, k), dtype=torch.float32, device=rows_slice.device),
-                     torch.empty((0, k), dtype=torch.int64, device=rows_slice.device))
-            return (lambda: empty) if defer else empty
-        own = area["own"]
-        args = (group_gallery, rows_slice, own + b * area["vb"], own + 2 * area["vb"] + b * area["ib"], self.world, kp,
-                k, threshold)
-        if not defer:
-            return self.ctx.rerank_candidates(*args)
-        # re-rank on a side stream: it is bound by NVLink reads of peer rows and leaves the SMs mostly
-        # idle, so it runs under the next search's GEMM; the caller joins with wait()
-        import torch
-        main = torch.cuda.current_stream(rows_slice.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(rows_slice.device)
-        ready = torch.cuda.Event()
-        ready.record(main)
-        self._side.wait_event(ready)
-        with torch.cuda.stream(self._side):
-            sims, idx = self.ctx.rerank_candidates(*args)
-            done = torch.cuda.Event()
-            done.record(self._side)
+        return area, b, kp
 
-        def wait():
-            main.wait_event(done)
-            sims.record_stream(main)
-            idx.record_stream(main)
-            return sims, idx
-        return wait
+    def collect(self, token, group_gallery, rows_slice, k: int, threshold: float):
+        """Phase 2 (after a barrier): global top-k of this rank's query slice, (sims [rows, k], idx).
+        rows_slice are the slice's fp32 rows; the candidate rows are read from local + peer masters."""
+        area, b, kp = token
+        if rows_slice.shape[0] == 0:
+            import torch
+            return (torch.empty((0, k), dtype=torch.float32, device=rows_slice.device),
+                    torch.empty((0, k), dtype=torch.int64, device=rows_slice.device))
+        own = area["own"]
+        return self.ctx.rerank_candidates(group_gallery, rows_slice, own + b * area["vb"],
+                                          own + 2 * area["vb"] + b * area["ib"], self.world, kp, k, threshold)
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -266,9 +245,6 @@ class TVCScorer:
         self._host: Dict[str, torch.Tensor] = {}
         self._dev_stage: Dict[str, torch.Tensor] = {}
         self._copy_stream = None
-        # measured on 8 B200: re-ranking the gallery hits on a side stream under the bank GEMM delays the
-        # GEMM's CTA pairs by as much as it hides (14.5 -> 14.8 ms/step), so it stays off
-        self.overlap_rerank = False
         self.host_chunks = 4                # pieces a host batch is pipelined in (1 = off)
         self.min_chunk_queries = 2048       # ... when every piece keeps at least this many queries
         self.profile = False            # True: CUDA-event time per phase, read with phase_times()
@@ -444,16 +420,16 @@ class TVCScorer:
             rows_s = var_s.view(qs * v, d)
             ex = self._exchange
             ex.begin_batch(rows_s, q_total, v, lo)
-            g_wait = ex.search("gallery", self.gallery, self._gallery_group, rows_s, q_total, v, lo, hi, k, -math.inf,
-                               defer=self.overlap_rerank and self.bank is not None)
+            # both shard searches first, ONE barrier, then both re-ranks: a rank whose gallery GEMM finishes
+            # early spends the wait in its bank GEMM instead of in a barrier
+            tg = ex.scatter("gallery", self.gallery, q_total, v, k)
+            tb = ex.scatter("bank", self.bank, q_total, v, k) if self.bank is not None else None
+            ex.barrier(self.device)
+            g_sim, g_idx = ex.collect(tg, self._gallery_group, rows_s, k, -math.inf)
             self._mark("search_gallery")
-            if self.bank is not None:
-                b_sim, b_idx = ex.search("bank", self.bank, self._bank_group, rows_s, q_total, v, lo, hi, k,
-                                         self.bank_threshold)
-                if callable(g_wait):
-                    g_wait = g_wait()          # the gallery re-rank ran under the bank GEMM
+            if tb is not None:
+                b_sim, b_idx = ex.collect(tb, self._bank_group, rows_s, k, self.bank_threshold)
                 self._mark("search_bank")
-            g_sim, g_idx = g_wait
         else:
             if self.world > 1 and host_var and self.device.type == "cuda":
                 # every rank holds the same host batch: upload only this rank's slice over PCIe and

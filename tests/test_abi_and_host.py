@@ -104,3 +104,20 @@ def test_product_code_does_not_import_the_oracle():
     for f in pkg.glob("*.py"):
         src = f.read_text()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# ", ""), f.name
+
+
+def test_header_is_plain_c_and_binds_with_dlopen(tmp_path):
+    """include/tvc.h compiles as C11 with -Wall -Werror, and a C program bound with dlopen alone can call
+    the device-free entry points (defaults, widths, status strings, argument checks, tvc_ctx_create)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    tvc.load_library()
+    exe = tmp_path / "abi_probe"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+                    str(ROOT / "tests" / "c" / "abi_probe.c"), "-o", str(exe), "-ldl", "-lm"], check=True)
+    out = subprocess.run([str(exe), str(N.LIB_PATH)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("abi ok")

@@ -390,17 +390,26 @@ def gold_retrieval_metrics(mods, out):
 
 
 def main():
+    # `--out DIR` writes somewhere else (tests/test_golden_reproducible.py regenerates into a temp
+    # directory and compares with the committed fixtures)
+    argv = sys.argv[1:]
+    out = OUT
+    if "--out" in argv:
+        i = argv.index("--out")
+        out = Path(argv[i + 1])
+        out.mkdir(parents=True, exist_ok=True)
+        del argv[i:i + 2]
     mods = import_reference()
-    if len(sys.argv) > 1 and sys.argv[1] == "retrieval_metrics":
-        gold_retrieval_metrics(mods, OUT)
+    if argv and argv[0] == "retrieval_metrics":
+        gold_retrieval_metrics(mods, out)
         return
-    gold_ref_bank(mods, OUT)
-    gold_consistency_checker(mods, OUT)
-    gold_similarity(mods, OUT)
-    gold_detectors(mods, OUT)
-    gold_hubness(mods, OUT)
-    gold_retrieval_metrics(mods, OUT)
-    for f in sorted(OUT.glob("*.npz")):
+    gold_ref_bank(mods, out)
+    gold_consistency_checker(mods, out)
+    gold_similarity(mods, out)
+    gold_detectors(mods, out)
+    gold_hubness(mods, out)
+    gold_retrieval_metrics(mods, out)
+    for f in sorted(out.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
 
 

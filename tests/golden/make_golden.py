@@ -238,11 +238,11 @@ class _TableClip:
         return torch.nn.functional.cosine_similarity(a[None], b[None])[0]
 
 
-def gold_detectors(mods, out):
+def gold_detectors(mods, out, seed=11, nq=96):
     D = mods["src.detector"]
     ED = mods["experiments.defenses.detector"]
-    rng = np.random.default_rng(11)
-    nq, d, V, G, R = 96, 64, 5, 3, 10
+    rng = np.random.default_rng(seed)
+    d, V, G, R = 64, 5, 3, 10
     gal = unit(rng, 300, d)
     gal[7] = gal[3]                      # exact duplicate rows
     gal[9] = unit(rng, 1, d)[0] * 0.02 + gal[4]

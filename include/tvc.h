@@ -141,6 +141,12 @@ int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
 /* tuning knobs: "pair_min_rows" = query rows from which tvc_search uses the CTA-pair (cta_group::2)
  * kernel instead of the single-CTA one (default 4096; 0 = always, INT64_MAX = never) */
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value);
+/* Frees the context's grow-only per-stream device workspaces (query operands, candidate lists, host
+ * staging windows) after synchronising the device; they are re-grown on demand.  For callers that
+ * alternate between very different batch sizes and want the HBM back in between (new: the
+ * reference holds no device memory of its own; the Python mirrors call it from clear_cache(), the
+ * hook src/pipeline.py:742-780 already invokes).  `freed_bytes` may be NULL. */
+int tvc_ctx_release_workspace(tvc_ctx* ctx, int64_t* freed_bytes);
 /* CUDA-event time in ms of the last gemm_topk launch made with timing enabled (roofline.achieved) */
 int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled);
 int tvc_ctx_last_search_kernel_ms(tvc_ctx* ctx, float* ms, int64_t* launches);

@@ -68,6 +68,7 @@ _EXPORTS = {
     "tvc_last_error": (C.c_char_p, [C.c_void_p]),
     "tvc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "tvc_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "tvc_ctx_release_workspace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "tvc_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "tvc_ctx_last_search_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "tvc_gallery_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
@@ -238,6 +239,20 @@ class Context:
                 ctx = cls._by_device[device] = Context(device)
             return ctx
 
+    @classmethod
+    def release_all_workspaces(cls) -> int:
+        """release_workspace() on every context that already exists (never creates one, never raises:
+        it is called from the mirrors' clear_cache(), which the reference's pipeline invokes)."""
+        with cls._lock:
+            live = list(cls._by_device.values())
+        freed = 0
+        for ctx in live:
+            try:
+                freed += ctx.release_workspace()
+            except TvcError:
+                pass
+        return freed
+
     def check(self, rc: int):
         if rc != TVC_OK:
             msg = self.lib.tvc_last_error(self.handle)
@@ -249,6 +264,12 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self.check(self.lib.tvc_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    def release_workspace(self) -> int:
+        """Frees the grow-only device workspaces (re-grown on demand); returns the bytes released."""
+        n = C.c_int64()
+        self.check(self.lib.tvc_ctx_release_workspace(self.handle, C.byref(n)))
+        return int(n.value)
 
     def set_timing(self, enabled: bool):
         self.check(self.lib.tvc_ctx_set_timing(self.handle, int(enabled)))

@@ -155,14 +155,18 @@ int gallery_reserve(tvc_gallery* g, int64_t need, cudaStream_t st) {
       return fail_cuda(ctx, e, "cudaMalloc(master)");
     }
   }
+  cudaError_t ce = cudaSuccess;
   if (g->n > 0) {
-    TVC_CUDA(ctx, cudaMemcpyAsync(nb, g->bf16, static_cast<size_t>(g->n) * g->d_pad * 2,
-                                  cudaMemcpyDeviceToDevice, st));
-    if (nf)
-      TVC_CUDA(ctx, cudaMemcpyAsync(nf, g->f32, static_cast<size_t>(g->n) * g->d * 4,
-                                    cudaMemcpyDeviceToDevice, st));
+    ce = cudaMemcpyAsync(nb, g->bf16, static_cast<size_t>(g->n) * g->d_pad * 2, cudaMemcpyDeviceToDevice, st);
+    if (ce == cudaSuccess && nf)
+      ce = cudaMemcpyAsync(nf, g->f32, static_cast<size_t>(g->n) * g->d * 4, cudaMemcpyDeviceToDevice, st);
   }
-  TVC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) {   // the old allocation stays the gallery's; drop the new one
+    cudaFree(nb);
+    if (nf) cudaFree(nf);
+    return fail_cuda(ctx, ce, "gallery_reserve: copy to the grown allocation");
+  }
   if (g->bf16) cudaFree(g->bf16);
   if (g->f32) cudaFree(g->f32);
   g->bf16 = nb;
@@ -191,6 +195,7 @@ cudaEvent_t get_event(tvc_ctx*) {
 }
 
 constexpr int64_t kMaxRowsPerLaunch = 1 << 20;
+constexpr size_t kHostStageBytes = 64u << 20;   // staging window of tvc_gallery_append for host rows
 
 // Stages a host array on the device (or passes a device pointer through); nullptr stays nullptr.
 struct Stager {
@@ -340,6 +345,23 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   return fail(ctx, TVC_ERR_INVALID, std::string("unknown option ") + name);
 }
 
+int tvc_ctx_release_workspace(tvc_ctx* ctx, int64_t* freed_bytes) {
+  if (!ctx) return TVC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read a workspace
+  int64_t freed = 0;
+  for (auto& kv : ctx->ws) {
+    if (kv.second.ptr) {
+      TVC_CUDA(ctx, cudaFree(kv.second.ptr));
+      freed += static_cast<int64_t>(kv.second.bytes);
+    }
+  }
+  ctx->ws.clear();
+  if (freed_bytes) *freed_bytes = freed;
+  return TVC_OK;
+}
+
 int tvc_ctx_set_timing(tvc_ctx* ctx, int enabled) {
   if (!ctx) return TVC_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -406,19 +428,31 @@ int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, v
   DeviceGuard guard(ctx->device);
   int rc = gallery_reserve(g, g->n + n, st);
   if (rc != TVC_OK) return rc;
-  const size_t bytes = static_cast<size_t>(n) * g->d * elem_size(dtype);
+  const size_t row_b = static_cast<size_t>(g->d) * elem_size(dtype);
   const bool host_src = !is_device_ptr(rows);
-  const void* src = rows;
-  if (host_src) {
+  const bool norm = (g->flags & TVC_GALLERY_NORMALIZE) != 0;
+  if (!host_src) {
+    TVC_CUDA(ctx, launch_prep_rows(rows, dtype, n, g->d, g->d_pad, norm, g->bf16 + static_cast<size_t>(g->n) * g->d_pad,
+                                   g->f32 ? g->f32 + static_cast<size_t>(g->n) * g->d : nullptr, st));
+  } else {
+    // Host rows go through a BOUNDED staging window (<= kHostStageBytes of the grow-only workspace, not a
+    // second copy of the whole gallery): copy and conversion of a window are stream-ordered, so the next
+    // window's copy waits for the conversion that reads it and pinned sources stay fully asynchronous.
+    int64_t win = static_cast<int64_t>(kHostStageBytes / row_b);
+    if (win < 1) win = 1;
+    if (win > n) win = n;
     uint8_t* ws;
-    rc = get_ws(ctx, st, up256(bytes), &ws);
+    rc = get_ws(ctx, st, up256(static_cast<size_t>(win) * row_b), &ws);
     if (rc != TVC_OK) return rc;
-    rc = to_device(ctx, rows, bytes, ws, st, &src);
-    if (rc != TVC_OK) return rc;
+    for (int64_t r0 = 0; r0 < n; r0 += win) {
+      const int64_t nr = n - r0 < win ? n - r0 : win;
+      TVC_CUDA(ctx, cudaMemcpyAsync(ws, static_cast<const uint8_t*>(rows) + static_cast<size_t>(r0) * row_b,
+                                    static_cast<size_t>(nr) * row_b, cudaMemcpyHostToDevice, st));
+      TVC_CUDA(ctx, launch_prep_rows(ws, dtype, nr, g->d, g->d_pad, norm,
+                                     g->bf16 + static_cast<size_t>(g->n + r0) * g->d_pad,
+                                     g->f32 ? g->f32 + static_cast<size_t>(g->n + r0) * g->d : nullptr, st));
+    }
   }
-  TVC_CUDA(ctx, launch_prep_rows(src, dtype, n, g->d, g->d_pad, (g->flags & TVC_GALLERY_NORMALIZE) != 0,
-                                 g->bf16 + static_cast<size_t>(g->n) * g->d_pad,
-                                 g->f32 ? g->f32 + static_cast<size_t>(g->n) * g->d : nullptr, st));
   g->n += n;
   g->tmap_rows = -1;
   if (host_src) TVC_CUDA(ctx, cudaStreamSynchronize(st));

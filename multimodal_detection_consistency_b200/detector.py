@@ -315,8 +315,10 @@ class AdversarialDetector:
             return {}
 
     def clear_cache(self):
+        """src/detector.py:817-823, plus: hand the device staging workspaces back."""
         self.detection_cache.clear()
         self.threshold_cache.clear()
+        N.Context.release_all_workspaces()
 
     def get_stats(self) -> Dict[str, Any]:
         """src/detector.py:825-842 (same keys)."""

@@ -24,7 +24,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import faiss_compat
-from ._native import Gallery
+from ._native import Context, Gallery
 from .batching import MicroBatcher
 
 logger = logging.getLogger(__name__)
@@ -476,8 +476,10 @@ class MultiModalRetriever:
         self.build_text_index_from_features(feats, data["texts"])
 
     def clear_cache(self):
+        """src/retrieval.py:884-890, plus: hand the device staging workspaces back (the galleries stay)."""
         self.feature_cache.clear()
         self.retrieval_cache.clear()
+        Context.release_all_workspaces()
 
     def get_stats(self) -> Dict[str, Any]:
         """src/retrieval.py:892-912 (same keys)."""

@@ -252,3 +252,46 @@ def test_half_precision_rows_and_queries(tvc_ctx, dtype):
     ref_s, ref_i = O.search(q.float().cpu().numpy(), g.float().cpu().numpy(), 10)
     assert (i_half.cpu().numpy() != ref_i).mean() < 0.01
     assert np.abs(s_half.cpu().numpy() - ref_s).max() <= (2e-3 if dtype == "float16" else 2e-3)
+
+
+def test_host_rows_go_through_a_bounded_staging_window(tvc_ctx):
+    """tvc_gallery_create/append with HOST rows larger than the 64 MiB staging window (several windows,
+    ragged last one, f32 and f16): same rows and same search results as the device-resident upload, and
+    the workspace stays window-sized instead of holding a second copy of the gallery."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(77)
+    n, d = 150_001, 256                                   # 153.6 MB of fp32 rows -> 3 windows
+    g = _unit(rng, n, d)
+    q = _unit(rng, 300, d)
+    tvc_ctx.release_workspace()
+    from_host = tvc.Gallery(g, ctx=tvc_ctx)
+    held = tvc_ctx.release_workspace()
+    assert 0 < held <= 80 << 20, held                     # one window (+12.5 % growth slack), not n*d*4
+    from_dev = tvc.Gallery(torch.from_numpy(g).cuda(), ctx=tvc_ctx)
+    pick = np.array([0, 1, 65535, 65536, 65537, 131071, 131072, n - 1], np.int64)
+    assert np.array_equal(from_host.get_rows(pick), g[pick])
+    s0, i0 = from_host.search(q, 10)
+    s1, i1 = from_dev.search(q, 10)
+    assert np.array_equal(np.asarray(i0), np.asarray(i1)) and np.array_equal(np.asarray(s0), np.asarray(s1))
+    ref_s, ref_i = O.search(q, g, 10)
+    assert _check_topk(s0, i0, ref_s, ref_i) < 0.01
+    # append of fp16 host rows across the window edge
+    extra = _unit(rng, 140_000, d).astype(np.float16)     # 71.7 MB -> 2 windows
+    from_host.append(extra)
+    assert len(from_host) == n + len(extra)
+    pick2 = np.array([n, n + 131071, n + 131072, n + len(extra) - 1], np.int64)
+    assert np.array_equal(from_host.get_rows(pick2), extra[pick2 - n].astype(np.float32))
+
+
+def test_release_workspace_is_transparent(tvc_ctx):
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(5)
+    g, q = _unit(rng, 3000, 128), _unit(rng, 200, 128)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    s0, i0 = gal.search(q, 10)
+    assert tvc_ctx.release_workspace() > 0
+    assert tvc_ctx.release_workspace() == 0
+    s1, i1 = gal.search(q, 10)
+    assert np.array_equal(np.asarray(i0), np.asarray(i1)) and np.array_equal(np.asarray(s0), np.asarray(s1))
+    assert tvc.Context.release_all_workspaces() > 0

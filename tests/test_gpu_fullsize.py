@@ -213,3 +213,56 @@ def test_c4_cc3m_scale_properties(tvc_ctx):
     same = ref.indices == idx[sel]
     assert float(same.float().mean()) > 0.99
     assert float((ref.values - sims[sel]).abs().max()) <= 1e-3
+
+
+def test_more_than_2_20_query_rows_are_chunked(tvc_ctx):
+    """tvc_search cuts > 2^20 query rows into launches (kMaxRowsPerLaunch): rows either side of the cut
+    must equal the same rows searched on their own, for device buffers (asynchronous) and for host
+    buffers (the staging workspace is reused by the next chunk), and match the oracle on a sample."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(20)
+    m, n, d, k = (1 << 20) + 777, 700, 64, 10
+    g = O.l2_normalize(rng.standard_normal((n, d), dtype=np.float32))
+    g[400] = g[40]
+    q = O.l2_normalize(rng.standard_normal((m, d), dtype=np.float32))
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    probe = np.r_[0:300, (1 << 20) - 300:(1 << 20) + 777]          # first rows, the cut, the ragged tail
+    ps, pi = gal.search(q[probe], k)
+    rs, ri = O.search(q[probe], g, k)
+    assert _band_check(ps, pi, rs, ri) < 0.01
+    hs, hi = gal.search(q, k)                                        # host buffers
+    assert np.array_equal(hi[probe], pi) and np.array_equal(hs[probe], ps)
+    ds, di = gal.search(torch.from_numpy(q).cuda(), k)               # device buffers
+    assert np.array_equal(di.cpu().numpy(), hi) and np.array_equal(ds.cpu().numpy(), hs)
+    counts = tvc_ctx.k_occurrence(di, n).cpu().numpy()
+    assert int(counts.sum()) == m * k and np.array_equal(counts, np.bincount(hi.reshape(-1), minlength=n))
+
+
+def test_self_search_skips_self_across_the_chunk_cut(tvc_ctx):
+    """k-occurrence of a set against itself (README hubness spec, `[:, 1:k+1]`): with more than 2^20
+    rows the second launch must exclude row r0+i, not row i.  Planted twins find each other first."""
+    import torch
+    import multimodal_detection_consistency_b200 as tvc
+    n, d, k = (1 << 20) + 4096, 64, 4
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    f = torch.nn.functional.normalize(torch.randn(n, d, device="cuda", generator=gen), dim=1)
+    twins = [(5, 900_000), (1 << 20, (1 << 20) + 7), ((1 << 20) + 4000, 123)]
+    for a, b in twins:
+        f[b] = f[a]
+    gal = tvc.Gallery(f, ctx=tvc_ctx)
+    sims, idx = gal.search(f, k, skip_self=True)
+    rows = torch.arange(n, device="cuda")[:, None]
+    assert not bool((idx == rows).any())                             # nobody retrieves itself ...
+    assert bool((idx >= 0).all()) and bool((sims[:, :-1] >= sims[:, 1:]).all())
+    for a, b in twins:                                               # ... but exact twins retrieve each other
+        assert int(idx[a, 0]) == b and int(idx[b, 0]) == a
+        assert abs(float(sims[a, 0]) - 1.0) < 1e-5
+    # every similarity is the fp32 dot of its index (sample across both launches)
+    probe = torch.tensor([0, 5, 524_288, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, n - 1], device="cuda")
+    want = (f[probe][:, None, :] * f[idx[probe]]).sum(-1)
+    assert float((want - sims[probe]).abs().max()) <= 1e-5
+    _, plain_i = gal.search(f[probe], k + 1)                         # without the flag every row finds itself
+    for r, p in enumerate(probe.tolist()):                           # (first, or second behind a lower-index twin)
+        assert p in plain_i[r, :2].tolist()

@@ -245,8 +245,13 @@ class TVCScorer:
         self._host: Dict[str, torch.Tensor] = {}
         self._dev_stage: Dict[str, torch.Tensor] = {}
         self._copy_stream = None
-        self.host_chunks = 4                # pieces a host batch is pipelined in (1 = off)
-        self.min_chunk_queries = 2048       # ... when every piece keeps at least this many queries
+        # pieces a host batch is pipelined in: a count (equal pieces; 1 = off) or relative sizes.  Measured on the
+        # bench workload (scripts/e2e_splits.py, ms/step; device-resident 101.4-102.2): unsplit 106.1, 2 equal
+        # 103.9, 4 equal 105.0, 8 equal 105.6, (1,7) 103.7, (1,4,3) 103.5, (1,3,3,1) 103.1, (1,6,1) 102.4 - a small
+        # first piece hides the upload, a small last piece hides the download, one big launch keeps the GEMM
+        # at full-wave efficiency
+        self.host_chunks = (1, 6, 1)
+        self.min_chunk_queries = 1024       # ... when every piece keeps at least this many queries
         self.profile = False            # True: CUDA-event time per phase, read with phase_times()
         self._marks = []
 
@@ -343,10 +348,30 @@ class TVCScorer:
         uploaded on a copy stream while piece c is searched and scored, and piece c's results go back
         to pinned host memory behind it - only the first upload and the last download are exposed."""
         host_in = not (isinstance(var, torch.Tensor) and var.device.type == "cuda")
-        if (host_in and self.world == 1 and self.device.type == "cuda" and self.host_chunks > 1
-                and int(var.shape[0]) >= self.host_chunks * self.min_chunk_queries):
+        if (host_in and self.world == 1 and self.device.type == "cuda"
+                and len(self._piece_bounds(int(var.shape[0]))) > 1):
             return self._score_batch_pipelined(img, txt, var, gen, g_cnt, to_host)
         return self._score_batch(img, txt, var, gen, g_cnt, to_host=to_host)
+
+    def _piece_bounds(self, q_total: int):
+        """Query ranges a host batch is pipelined in.  `host_chunks` is a piece count (equal pieces) or a
+        sequence of relative piece sizes, e.g. (1, 4, 3): a small first piece shortens the only upload that
+        is not hidden behind a search.  One piece (= no pipelining) when a piece would fall under
+        `min_chunk_queries`."""
+        hc = self.host_chunks
+        for cand in (hc, 2):                                # too small for the configured split: try two halves
+            weights = [1.0] * int(cand) if isinstance(cand, int) else [float(w) for w in cand]
+            if len(weights) < 2 or min(weights) <= 0:
+                break
+            total, acc, cuts = sum(weights), 0.0, [0]
+            for w in weights:
+                acc += w
+                cuts.append(int(round(q_total * acc / total)))
+            cuts[-1] = q_total
+            bounds = list(zip(cuts[:-1], cuts[1:]))
+            if min(b - a for a, b in bounds) >= self.min_chunk_queries:
+                return bounds
+        return [(0, q_total)]
 
     def _staging(self, name: str, shape, dtype) -> torch.Tensor:
         buf = self._dev_stage.get(name)
@@ -357,8 +382,7 @@ class TVCScorer:
 
     def _score_batch_pipelined(self, img, txt, var, gen, g_cnt, to_host: bool):
         q_total = int(var.shape[0])
-        c_n = self.host_chunks
-        bounds = [(q_total * c // c_n, q_total * (c + 1) // c_n) for c in range(c_n)]
+        bounds = self._piece_bounds(q_total)
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)

@@ -121,3 +121,21 @@ def test_header_is_plain_c_and_binds_with_dlopen(tmp_path):
     out = subprocess.run([str(exe), str(N.LIB_PATH)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.startswith("abi ok")
+
+
+def test_host_batch_piece_bounds():
+    """TVCScorer._piece_bounds: weighted / equal splits cover the batch exactly, fall back to two halves and
+    then to one piece when a piece would be smaller than min_chunk_queries."""
+    import types
+    from multimodal_detection_consistency_b200.pipeline import TVCScorer
+    sc = types.SimpleNamespace(host_chunks=(1, 6, 1), min_chunk_queries=1024)
+    pb = lambda q: TVCScorer._piece_bounds(sc, q)  # noqa: E731
+    assert pb(16384) == [(0, 2048), (2048, 14336), (14336, 16384)]
+    assert pb(8192) == [(0, 1024), (1024, 7168), (7168, 8192)]
+    assert pb(8000) == [(0, 4000), (4000, 8000)]            # 1/8 piece too small -> two halves
+    assert pb(2047) == [(0, 2047)]                          # halves too small -> no pipelining
+    sc.host_chunks = 4
+    assert pb(16384) == [(i * 4096, (i + 1) * 4096) for i in range(4)]
+    assert pb(10001)[0][0] == 0 and pb(10001)[-1][1] == 10001 and all(a[1] == b[0] for a, b in zip(pb(10001), pb(10001)[1:]))
+    sc.host_chunks = 1
+    assert pb(16384) == [(0, 16384)]

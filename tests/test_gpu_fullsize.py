@@ -140,7 +140,7 @@ def test_pipelined_host_batches_equal_one_shot(tvc_ctx):
     bank = O.synth_gallery(3000, d, seed=5)
     img, txt, var = (torch.from_numpy(x).pin_memory() for x in O.synth_queries(g, 1000, 5, seed=6))
     outs = []
-    for chunks in (1, 4):
+    for chunks in (1, 4, (1, 6, 1)):
         sc = TVCScorer(g, bank, k=10, device="cuda:0")
         sc.host_chunks, sc.min_chunk_queries = chunks, 100
         o = sc.score_batch(img, txt, var, to_host=True)
@@ -150,9 +150,10 @@ def test_pipelined_host_batches_equal_one_shot(tvc_ctx):
         torch.cuda.synchronize()
         for name, t in outs[-1][0].items():
             assert torch.equal(o2[name].cpu(), t), name
-    for name, t in outs[0][0].items():
-        assert torch.equal(t, outs[1][0][name]), name
-    assert torch.equal(outs[0][1], outs[1][1])
+    for other in outs[1:]:
+        for name, t in outs[0][0].items():
+            assert torch.equal(t, other[0][name]), name
+        assert torch.equal(outs[0][1], other[1])
 
 
 def test_c4_cc3m_scale_properties(tvc_ctx):

@@ -280,6 +280,36 @@ class TVCScorer:
             x = torch.as_tensor(x)
         return x.to(self.device, dtype=dtype, non_blocking=True).contiguous()
 
+    def _side_upload(self, items):
+        """name -> (tensor or None, dtype).  Device tensors pass through (converted on the current stream);
+        host tensors are copied on the copy stream so the transfer runs under whatever the current stream
+        does next; the caller waits on the returned event before the first kernel that reads them."""
+        out, host = {}, {}
+        for name, (t, dt) in items.items():
+            if t is None:
+                out[name] = None
+            elif isinstance(t, torch.Tensor) and t.device.type == self.device.type:
+                out[name] = t.to(dtype=dt).contiguous()
+            elif self.device.type != "cuda":
+                out[name] = self._dev(t, dt)
+            else:
+                host[name] = (t if isinstance(t, torch.Tensor) else torch.as_tensor(t), dt)
+        if not host:
+            return out, None
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        for name, (t, dt) in host.items():                     # allocated on the consumer's stream
+            out[name] = torch.empty(t.shape, dtype=dt, device=self.device)
+        cs.wait_stream(main)                                   # the blocks may be recycled from work still in flight
+        with torch.cuda.stream(cs):
+            for name, (t, dt) in host.items():
+                out[name].copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return out, ev
+
     def _pinned(self, name: str, like: torch.Tensor) -> torch.Tensor:
         buf = self._host.get(name)
         if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
@@ -436,11 +466,19 @@ class TVCScorer:
         k = self.k
         host_var = not (isinstance(var, torch.Tensor) and var.device.type == self.device.type == "cuda")
         b_sim = b_idx = None
+
+        def upload_rest():
+            # the rows only kernel (b) reads go up on the copy stream, under the searches - queued BEHIND the
+            # variant rows (the copy stream waits for what the current stream holds), which the GEMM waits for
+            return self._side_upload(dict(img=(img[lo:hi], torch.float32), txt=(txt[lo:hi], torch.float32),
+                                          gen=(gen[lo:hi] if gen is not None else None, torch.float32),
+                                          g_cnt=(g_cnt[lo:hi] if g_cnt is not None else None, torch.int32)))
         if self.world > 1 and self._exchange is not None:
             # peer-memory path: this rank only touches (uploads) ITS slice of the batch.  The bf16 operand
             # of the whole batch is assembled in every rank's HBM by the prepare kernel's peer stores, the
             # candidates are stored into the slice owners' HBM, and the owners re-rank.
             var_s = self._dev(var[lo:hi])
+            side, side_ev = upload_rest()
             rows_s = var_s.view(qs * v, d)
             ex = self._exchange
             ex.begin_batch(rows_s, q_total, v, lo)
@@ -467,6 +505,7 @@ class TVCScorer:
                 var = full[:q_total]
             else:
                 var = self._dev(var)
+            side, side_ev = upload_rest()
             rows_all = var.view(q_total * v, d)
             g_sim, g_idx = self._global_topk(self.gallery, rows_all, q_total, v, -math.inf)
             self._mark("search_gallery")
@@ -474,9 +513,9 @@ class TVCScorer:
                 b_sim, b_idx = self._global_topk(self.bank, rows_all, q_total, v, self.bank_threshold)
                 self._mark("search_bank")
             var_s = var[lo:hi]
-        img_s, txt_s = self._dev(img[lo:hi]), self._dev(txt[lo:hi])
-        gen_s = self._dev(gen[lo:hi]) if gen is not None else None
-        gcnt_s = self._dev(g_cnt[lo:hi], torch.int32) if g_cnt is not None else None
+        if side_ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(side_ev)
+        img_s, txt_s, gen_s, gcnt_s = side["img"], side["txt"], side["gen"], side["g_cnt"]
         ret_idx = g_idx.view(qs, v * k)
         gen_idx = b_idx.view(qs, v * k) if (b_idx is not None and gen is None) else None
         ret_gal, gen_gal = self.gallery, self.bank

@@ -74,19 +74,64 @@ class AdversarialDetector:
         self.detection_stats = {"total_detections": 0, "cache_hits": 0, "detection_time": 0.0,
                                 "method_usage": {m: 0 for m in self.config.detection_methods}}
         self._ctx = None
+        self._tried = set()         # components whose lazy construction was already attempted
         # single-sample calls made concurrently are coalesced (batching.MicroBatcher)
         self.micro_batch = True
         self._batcher = MicroBatcher(lambda key, items: self._detect_group(items, list(key)), max_batch=256)
 
-    # component accessors keep the reference's names (src/detector.py:257-343)
+    # Component accessors, as in the reference (src/detector.py:252-343): what was injected wins; otherwise the
+    # component is built lazily, on first use, from the HOST APPLICATION's packages - `src.models` (not shipped
+    # with the reference, .gitignore:51), `src.text_augment`, `src.sd_ref` - with the reference's arguments.
+    # That is what lets `AdversarialDetector(config)` be constructed by src/pipeline.py:324-327 unchanged.
+    # A package that is not importable leaves the component None (tried once, not on every call).
     def _get_clip_model(self):
+        if self.clip_model is None and "clip" not in self._tried:
+            self._tried.add("clip")
+            self.clip_model = self._initialize_clip_model(self.config.clip_model, self.config.device)
         return self.clip_model
 
+    def _initialize_clip_model(self, model_name: str, device: str):
+        """src/detector.py:257-279."""
+        try:
+            from src.models import CLIPConfig, CLIPModel  # type: ignore
+            return CLIPModel(CLIPConfig(model_name=model_name, device=device))
+        except Exception as e:  # noqa: BLE001
+            logger.warning("no CLIP encoder available (%s); pass clip_model= or use detect_embeddings", e)
+            return None
+
     def _get_text_augmenter(self):
+        if self.text_augmenter is None and self.config.use_text_variants and "aug" not in self._tried:
+            self._tried.add("aug")
+            self.text_augmenter = self._initialize_text_augmenter(self.config.num_text_variants,
+                                                                  self.config.text_similarity_threshold)
         return self.text_augmenter
 
+    def _initialize_text_augmenter(self, num_variants: int, similarity_threshold: float):
+        """src/detector.py:288-315 (same TextAugmentConfig arguments)."""
+        try:
+            from src.text_augment import TextAugmentConfig, TextAugmenter  # type: ignore
+            return TextAugmenter(TextAugmentConfig(max_variants=num_variants,
+                                                   min_similarity_threshold=similarity_threshold,
+                                                   paraphrase_model="Qwen/Qwen2-7B-Instruct",
+                                                   device=self.config.device))
+        except Exception as e:  # noqa: BLE001
+            logger.warning("text augmenter not available: %s", e)
+            return None
+
     def _get_sd_generator(self):
+        if self.sd_generator is None and self.config.use_sd_reference and "sd" not in self._tried:
+            self._tried.add("sd")
+            self.sd_generator = self._initialize_sd_generator(self.config.num_reference_images, self.config.device)
         return self.sd_generator
+
+    def _initialize_sd_generator(self, num_images_per_prompt: int, device: str):
+        """src/detector.py:326-343."""
+        try:
+            from src.sd_ref import SDReferenceConfig, SDReferenceGenerator  # type: ignore
+            return SDReferenceGenerator(SDReferenceConfig(num_images_per_prompt=num_images_per_prompt, device=device))
+        except Exception as e:  # noqa: BLE001
+            logger.warning("SD reference generator not available: %s", e)
+            return None
 
     def _context(self) -> N.Context:
         if self._ctx is None:

@@ -118,9 +118,28 @@ class ConsistencyChecker:
         row[ix["confidence"]] = float(np.clip(np.mean([abs(overall - thr) / thr, cons, 1.0 - min(cmv, 1.0)]), 0, 1))
         res = self.decide_from_kernel(row[None])[0]
         if return_details:
-            res["details"] = {"scores": dict(consistency_scores), "overall_score": res["overall_score"],
-                              "threshold": res["threshold"], "voting_strategy": self.voting_strategy}
+            res["details"] = self._get_detailed_analysis(consistency_scores, res["overall_score"], res["threshold"])
         return res
+
+    def _get_detailed_analysis(self, scores: Dict[str, float], overall_score: float, threshold: float) -> Dict[str, Any]:
+        """consistency_checker.py:274-317: per-score breakdown plus the risk / confidence labels (the label
+        strings are output values consumers may match on, so they are the reference's)."""
+        top = max(scores.values()) if scores else 0.0
+        breakdown = {name: {"value": val, "normalized": val / top if top > 0 else 0,
+                            "contribution": self.weights.get(name, 0) * val}
+                     for name, val in scores.items() if val > 0}
+        risks = [label for label, hit in (("高跨模态方差", scores.get("cross_modal_variance", 0) > 0.1),
+                                          ("文本变体不一致", scores.get("text_variant_std", 0) > 0.2),
+                                          ("低原始相似度", scores.get("original_similarity", 1) < 0.3)) if hit]
+        trust = [label for label, hit in (("多模块验证", sum(1 for v in scores.values() if v > 0) >= 3),
+                                          ("高检索一致性", scores.get("retrieval_consistency", 0) > 0.7),
+                                          ("高生成一致性", scores.get("generative_consistency", 0) > 0.7)) if hit]
+        return {"individual_scores": scores, "overall_score": overall_score, "threshold": threshold,
+                "score_analysis": breakdown, "risk_factors": risks, "confidence_factors": trust}
+
+    def update_weights(self, new_weights: Dict[str, float]):
+        """consistency_checker.py:361-364."""
+        self.weights.update(new_weights)
 
     def calibrate_threshold(self, validation_scores: List[Dict[str, float]], validation_labels: List[bool]) -> float:
         """consistency_checker.py:366-409: sweep 81 thresholds in [0.1, 0.9] for the best F1 (one kernel
@@ -156,13 +175,18 @@ class ConsistencyChecker:
         return best_thr
 
     def get_statistics(self) -> Dict[str, Any]:
+        """consistency_checker.py:319-353 (same keys; the reference's message when nothing was decided yet)."""
         if not self.detection_history:
-            return {"total_detections": 0}
+            return {"message": "暂无检测历史"}
+
+        def moments(key):
+            v = np.array([d[key] for d in self.detection_history], dtype=np.float64)
+            return {"mean": float(v.mean()), "std": float(v.std()), "min": float(v.min()), "max": float(v.max())}
+
         adv = sum(1 for d in self.detection_history if d["is_adversarial"])
-        return {"total_detections": len(self.detection_history), "adversarial_detected": adv,
-                "adversarial_rate": adv / len(self.detection_history),
-                "avg_confidence": float(np.mean([d["confidence"] for d in self.detection_history])),
-                "avg_threshold": float(np.mean(self.threshold_history)), "current_threshold": self.base_threshold}
+        return {"total_detections": len(self.detection_history), "adversarial_detections": adv,
+                "adversarial_rate": adv / len(self.detection_history), "score_statistics": moments("overall_score"),
+                "threshold_statistics": moments("threshold"), "confidence_statistics": moments("confidence")}
 
     def reset_history(self):
         self.detection_history.clear()

@@ -16,7 +16,7 @@ import json
 import logging
 import pickle
 import time
-from collections import deque
+from collections import OrderedDict, deque
 from dataclasses import asdict, dataclass
 from pathlib import Path
 from threading import Lock
@@ -80,10 +80,14 @@ class ReferenceBank:
         self.references: List[ReferenceItem] = []
         self.clusters: Dict[int, List[int]] = {}
         self.cluster_centers: Optional[np.ndarray] = None
-        self.access_order: deque = deque()
+        # LRU order of `references` positions.  The reference keeps a deque and pays O(B) `in` + `remove` per hit
+        # (src/ref_bank.py:212-214); here the order lives in an OrderedDict (O(1) move-to-end / pop-oldest) and
+        # `access_order` shows it as the deque observers expect
+        self._access: "OrderedDict[int, None]" = OrderedDict()
         self._lock = Lock()
         self.stats = self._fresh_stats()
         # device mirror: gallery row r holds the (normalised) vector of self._row_items[r]
+        self._pos_cache: Optional[Dict[int, int]] = None
         self._gallery: Optional[Gallery] = None
         self._row_items: List[ReferenceItem] = []
         self._row_of: Dict[int, int] = {}
@@ -95,6 +99,14 @@ class ReferenceBank:
         if self.config.persistence_enabled:
             Path(self.config.save_path).mkdir(parents=True, exist_ok=True)
         self._load_from_disk()
+
+    @property
+    def access_order(self) -> deque:
+        return deque(self._access)
+
+    @access_order.setter
+    def access_order(self, order):
+        self._access = OrderedDict((int(i), None) for i in order)
 
     @staticmethod
     def _fresh_stats():
@@ -146,6 +158,8 @@ class ReferenceBank:
                 if len(self.references) >= self.config.max_size:
                     self._remove_reference()
                 self.references.append(item)
+                if self._pos_cache is not None:
+                    self._pos_cache[id(item)] = len(self.references) - 1
                 self._dev_append([item])
                 self.stats["total_added"] += 1
                 clustered = False
@@ -193,6 +207,9 @@ class ReferenceBank:
             return [[] for _ in range(len(query_vectors))]
 
     def _collect(self, sims_row, rows_row):
+        """Access statistics of one query's hits (src/ref_bank.py:205-219): count, LRU order - for every
+        update strategy, as the reference does - and `total_queries`, which the reference only bumps when
+        something passed the threshold (it returns early at :198-199)."""
         out = []
         pos = None
         for s, r in zip(sims_row, rows_row):
@@ -200,16 +217,21 @@ class ReferenceBank:
                 break
             item = self._row_items[int(r)]
             item.access_count += 1
-            if self.config.update_strategy == "lru":
-                if pos is None:
-                    pos = {id(it): i for i, it in enumerate(self.references)}
-                idx = pos[id(item)]
-                if idx in self.access_order:
-                    self.access_order.remove(idx)
-                self.access_order.append(idx)
+            if pos is None:
+                pos = self._positions()
+            idx = pos[id(item)]
+            self._access.pop(idx, None)
+            self._access[idx] = None
             out.append((item, float(s)))
-        self.stats["total_queries"] += 1
+        if out:
+            self.stats["total_queries"] += 1
         return out
+
+    def _positions(self) -> Dict[int, int]:
+        """id(item) -> position in `references` (cached until the list changes length or order)."""
+        if self._pos_cache is None or len(self._pos_cache) != len(self.references):
+            self._pos_cache = {id(it): i for i, it in enumerate(self.references)}
+        return self._pos_cache
 
     def query_by_cluster(self, cluster_id: int, top_k: int = 10) -> List[ReferenceItem]:
         try:
@@ -292,8 +314,8 @@ class ReferenceBank:
         if s == "fifo":
             self._remove_at(0)
         elif s == "lru":
-            if self.access_order:
-                oldest = self.access_order.popleft()
+            if self._access:
+                oldest, _ = self._access.popitem(last=False)
                 if oldest < len(self.references):
                     self._remove_at(oldest)
             else:
@@ -327,7 +349,8 @@ class ReferenceBank:
             if kept:
                 new_clusters[cid] = kept
         self.clusters = new_clusters
-        self.access_order = deque(m if m < removed_idx else m - 1 for m in self.access_order if m != removed_idx)
+        self._access = OrderedDict((m if m < removed_idx else m - 1, None) for m in self._access if m != removed_idx)
+        self._pos_cache = None
 
     def _compute_similarities(self, query_vector: np.ndarray) -> np.ndarray:
         """src/ref_bank.py:462-484: cosine of the query against every reference, in `references` order."""
@@ -394,6 +417,7 @@ class ReferenceBank:
             if isinstance(data, dict):  # the snapshot shipped in cache/ref_bank wraps the list
                 data = data.get("references", [])
             self.references = [ReferenceItem.from_dict(d) for d in data]
+            self._pos_cache = None
             cf = root / "clusters.json"
             if cf.exists():
                 cd = json.loads(cf.read_text())
@@ -426,7 +450,8 @@ class ReferenceBank:
             self.references.clear()
             self.clusters.clear()
             self.cluster_centers = None
-            self.access_order.clear()
+            self._access.clear()
+            self._pos_cache = None
             self.stats = self._fresh_stats()
             self._dev_rebuild()
 
@@ -482,6 +507,7 @@ class ReferenceBank:
                 room = max(0, self.config.max_size - len(self.references))
                 taken = items[:room]
                 self.references.extend(taken)
+                self._pos_cache = None
                 self._dev_append(taken)
                 self.stats["total_added"] += len(taken)
                 return True

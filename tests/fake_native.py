@@ -28,6 +28,7 @@ class FakeGallery:
         self.global_row_offset = int(global_row_offset)
         self.dim = int(dim if rows is None else np.asarray(rows).shape[1])
         self.rows = np.zeros((0, self.dim), np.float32)
+        self.ctx = ctx if ctx is not None else FakeContext()
         if rows is not None:
             self.append(rows)
 
@@ -107,6 +108,11 @@ class FakeContext:
             counts += c
             return counts
         return c
+
+    def retrieval_metrics(self, topk_idx, rel_ptr, rel_idx, k_values):
+        ptr, idx = _np(rel_ptr, np.int64), _np(rel_idx, np.int64)
+        relevant = [idx[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+        return O.retrieval_metrics_from_topk(_np(topk_idx, np.int64), relevant, [int(k) for k in k_values]).astype(np.float32)
 
     def release_workspace(self):
         return 0

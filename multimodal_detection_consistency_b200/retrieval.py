@@ -338,10 +338,7 @@ class MultiModalRetriever:
             if self.config.enable_cache and key in self.retrieval_cache:
                 return self.retrieval_cache[key]
             if self.micro_batch:
-                result = self._i2t_batcher.submit(image, key=top_k)
-                if self.config.enable_cache and result[0]:
-                    self.retrieval_cache[key] = result
-                return result
+                return self._i2t_batcher.submit(query_image, key=top_k)   # cached there, under the same key
             q = _to_numpy(self.clip_model.encode_image([image], normalize=self.config.normalize_features))
             idx, scores = self._search_index(self.text_index, q, top_k)
             result = ([self.texts[i] for i in idx if i >= 0], [float(s) for s, i in zip(scores, idx) if i >= 0])
@@ -380,16 +377,26 @@ class MultiModalRetriever:
         try:
             if self.text_index is None:
                 raise ValueError("text index not built")
-            images = []
-            for im in query_images:
-                if isinstance(im, str):
-                    from PIL import Image
-                    im = Image.open(im).convert("RGB")
-                images.append(im)
-            q = _to_numpy(self.clip_model.encode_image(images, normalize=self.config.normalize_features))
-            sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k, index="text")
-            return [([self.texts[i] for i in i_row[i_row >= 0]], [float(s) for s in s_row[i_row >= 0]])
-                    for s_row, i_row in zip(sims, idx)]
+            # same cache keys as the single call (:596-600), so either entry point serves the other
+            keys = [f"img2text_{im}_{top_k}" if isinstance(im, str) else f"img2text_pil_{id(im)}_{top_k}"
+                    for im in query_images]
+            cache = self.retrieval_cache if self.config.enable_cache else {}
+            fresh: Dict[str, Any] = {}
+            todo = [(key, im) for key, im in dict(zip(keys, query_images)).items() if key not in cache]
+            if todo:
+                images = []
+                for _, im in todo:
+                    if isinstance(im, str):
+                        from PIL import Image
+                        im = Image.open(im).convert("RGB")
+                    images.append(im)
+                q = _to_numpy(self.clip_model.encode_image(images, normalize=self.config.normalize_features))
+                sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k, index="text")
+                for (key, _), s_row, i_row in zip(todo, sims, idx):
+                    fresh[key] = ([self.texts[i] for i in i_row[i_row >= 0]], [float(s) for s in s_row[i_row >= 0]])
+                    if self.config.enable_cache:
+                        self.retrieval_cache[key] = fresh[key]
+            return [fresh[key] if key in fresh else cache[key] for key in keys]
         except Exception as e:  # noqa: BLE001
             logger.error("batched image->text retrieval failed: %s", e)
             return [([], []) for _ in query_images]

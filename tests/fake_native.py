@@ -122,10 +122,11 @@ class FakeContext:
 def installed():
     """Swap the test double in for the duration of the block (and restore the real bindings after)."""
     import multimodal_detection_consistency_b200._native as N
-    from multimodal_detection_consistency_b200 import defenses, detector, hubness, metrics, ref_bank, retrieval
+    from multimodal_detection_consistency_b200 import (defenses, detector, faiss_compat, hubness, metrics, ref_bank,
+                                                       retrieval)
     ctx = FakeContext()
     saved = [(N, "Gallery", N.Gallery), (N.Context, "get", N.Context.__dict__["get"])]
-    for mod in (retrieval, ref_bank, defenses, detector, hubness, metrics):
+    for mod in (retrieval, ref_bank, defenses, detector, hubness, metrics, faiss_compat):
         if "Gallery" in vars(mod):
             saved.append((mod, "Gallery", mod.Gallery))
     try:

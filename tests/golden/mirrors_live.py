@@ -204,6 +204,218 @@ def check_evaluator(mods, rng):
     return nq
 
 
+# ------------------------------------------------------------------------------------------ retriever
+def _world(rng, root, n_img=60, n_txt=40, d=48):
+    from pipeline_dropin import TableClip, image_of
+    img_f, txt_f = MG.unit(rng, n_img, d), MG.unit(rng, n_txt, d)
+    paths, image_table, text_table, texts = [], {}, {}, []
+    for j in range(n_img):
+        p = root / f"g{j:03d}.png"
+        image_of(j).save(p)
+        paths.append(str(p))
+        image_table[j] = img_f[j]
+    for j in range(n_txt):
+        t = f"caption number {j}"
+        texts.append(t)
+        text_table[t] = txt_f[j]
+    queries = []
+    for j in range(12):                                              # query texts near an image, query images near a text
+        qt = f"query text {j}"
+        v = img_f[rng.integers(n_img)] + 0.08 * rng.standard_normal(d).astype(np.float32)
+        text_table[qt] = (v / np.linalg.norm(v)).astype(np.float32)
+        v = txt_f[rng.integers(n_txt)] + 0.08 * rng.standard_normal(d).astype(np.float32)
+        image_table[2000 + j] = (v / np.linalg.norm(v)).astype(np.float32)
+        queries.append((qt, image_of(2000 + j)))
+    return TableClip(text_table, image_table), paths, texts, queries, img_f, txt_f
+
+
+def check_retriever(mods, rng):
+    """MultiModalRetriever (src/retrieval.py:316-912) and its helpers FaissIndexManager (:89-155), RetrievalIndex
+    (:196-287), ConsistencyCalculator (:158-193): same calls, same return shapes / values / stats / files."""
+    R = mods["src.retrieval"]
+    from multimodal_detection_consistency_b200 import faiss_compat, retrieval as OR
+    from pipeline_dropin import NumpyFlatIP
+    fa = sys.modules["faiss"]
+    fa.IndexFlatIP = NumpyFlatIP
+    fa.get_num_gpus = lambda: 0
+
+    def write_index(index, path):
+        Path(path).write_bytes(faiss_compat._pack_flat(index.x, index.d))
+
+    def read_index(path):
+        d, _, rows = faiss_compat._unpack_flat(Path(path).read_bytes())
+        idx = NumpyFlatIP(d)
+        idx.add(rows)
+        return idx
+
+    fa.write_index, fa.read_index = write_index, read_index
+    n = 0
+    with tempfile.TemporaryDirectory() as td:
+        clip, paths, texts, queries, img_f, txt_f = _world(rng, Path(td))
+        for index_type in ("faiss", "exact"):
+            a = R.MultiModalRetriever(R.RetrievalConfig(index_type=index_type, top_k=7))
+            b = OR.MultiModalRetriever(OR.RetrievalConfig(index_type=index_type, top_k=7))
+            a.clip_model = b.clip_model = clip
+            _same(a.get_stats(), b.get_stats(), "empty stats")
+            assert a.retrieve_images_by_text("query text 0") == b.retrieve_images_by_text("query text 0") == ([], [])
+            for r in (a, b):
+                r.build_image_index(paths)
+                r.build_text_index(texts)
+            assert np.array_equal(a.image_features, b.image_features) and np.array_equal(a.text_features, b.text_features)
+            assert a.image_paths == b.image_paths and a.texts == b.texts
+            if index_type == "exact":
+                # the reference's `exact` retriever holds no index object and refuses the public calls
+                # (src/retrieval.py:546-547 needs image_index, :488-489 returns None) - only _search_index works
+                for qt, _ in queries[:4]:
+                    ia, sa = a._search_index(None, clip.encode_text([qt]).numpy(), 5)
+                    ib, sb = b._search_index(None, clip.encode_text([qt]).numpy(), 5)
+                    assert np.array_equal(ia, ib) and np.allclose(sa, sb, rtol=0, atol=2e-6)
+                continue
+            for qt, qi in queries:
+                k = int(rng.integers(1, 9))
+                _same(a.retrieve_images_by_text(qt, top_k=k), b.retrieve_images_by_text(qt, top_k=k), f"t2i {qt}")
+                _same(a.retrieve_texts_by_image(qi, top_k=k), b.retrieve_texts_by_image(qi, top_k=k), f"i2t {qt}")
+                n += 2
+            _same(a.retrieve_images_by_text(queries[0][0]), b.retrieve_images_by_text(queries[0][0]), "default top_k")
+            _same(a.retrieve_texts_by_image(paths[3], top_k=4), b.retrieve_texts_by_image(paths[3], top_k=4), "i2t by path")
+            _same(a.batch_retrieve_images_by_texts([q for q, _ in queries], 5),
+                  b.batch_retrieve_images_by_texts([q for q, _ in queries], 5), "batch t2i")
+            _same(a.batch_retrieve_texts_by_images([q for _, q in queries], 5),
+                  b.batch_retrieve_texts_by_images([q for _, q in queries], 5), "batch i2t")
+            for metric in ("cosine", "dot_product", "euclidean"):
+                a.config.similarity_metric = b.config.similarity_metric = metric
+                assert np.allclose(a.compute_similarity_matrix(), b.compute_similarity_matrix(), rtol=0, atol=2e-5)
+                assert np.allclose(a.compute_similarity_matrix(txt_f[:5] * 2, img_f[:9] * 3),
+                                   b.compute_similarity_matrix(txt_f[:5] * 2, img_f[:9] * 3), rtol=0, atol=2e-5)
+            a.config.similarity_metric = b.config.similarity_metric = "cosine"
+            _same(a.get_stats(), b.get_stats(), "stats")
+            # persistence: pickle + .faiss sidecar, each implementation loads the other's files
+            pa, pb = Path(td) / "a" / "img.pkl", Path(td) / "b" / "img.pkl"
+            a.save_image_index(str(pa)), b.save_image_index(str(pb))
+            a.save_text_index(str(pa.with_name("txt.pkl"))), b.save_text_index(str(pb.with_name("txt.pkl")))
+            assert pa.with_suffix(".faiss").read_bytes() == pb.with_suffix(".faiss").read_bytes()
+            a2 = R.MultiModalRetriever(R.RetrievalConfig(index_type=index_type, top_k=7))
+            b2 = OR.MultiModalRetriever(OR.RetrievalConfig(index_type=index_type, top_k=7))
+            a2.clip_model = b2.clip_model = clip
+            a2.load_image_index(str(pb)), a2.load_text_index(str(pb.with_name("txt.pkl")))      # reference <- ours
+            b2.load_image_index(str(pa)), b2.load_text_index(str(pa.with_name("txt.pkl")))      # ours <- reference
+            for qt, qi in queries[:5]:
+                _same(a.retrieve_images_by_text(qt, top_k=6), a2.retrieve_images_by_text(qt, top_k=6), "ref loads ours")
+                _same(a.retrieve_images_by_text(qt, top_k=6), b2.retrieve_images_by_text(qt, top_k=6), "ours loads ref")
+                _same(a.retrieve_texts_by_image(qi, top_k=6), b2.retrieve_texts_by_image(qi, top_k=6), "ours loads ref i2t")
+            a.clear_cache(), b.clear_cache()
+            _same(a.get_stats(), b.get_stats(), "stats after clear")
+        # helpers
+        fm_a, fm_b = R.FaissIndexManager(R.IndexConfig(index_type="flat", dimension=48, use_gpu=False)), \
+            OR.FaissIndexManager(OR.IndexConfig(index_type="flat", dimension=48, use_gpu=False))
+        for fm in (fm_a, fm_b):
+            fm.build_index(img_f[:40])
+            fm.add_to_index(img_f[40:])
+        sa, ia = fm_a.search(txt_f[:6], 5)
+        sb, ib = fm_b.search(txt_f[:6], 5)
+        assert np.array_equal(ia, ib) and np.allclose(sa, sb, rtol=0, atol=2e-6)
+        ri_a, ri_b = R.RetrievalIndex("faiss", 48), OR.RetrievalIndex("faiss", 48)
+        for ri in (ri_a, ri_b):
+            ri.build_index(img_f[:50])
+            ri.add_items(img_f[50:])
+        xa, xb = ri_a.search(txt_f[:6], 5), ri_b.search(txt_f[:6], 5)     # note: (indices, distances) here (:254)
+        assert np.array_equal(xa[0], xb[0]) and np.allclose(xa[1], xb[1], rtol=0, atol=2e-6)
+        ca, cb = R.ConsistencyCalculator(), OR.ConsistencyCalculator()
+        _same(ca.compute_similarity_distribution(sa[0]), cb.compute_similarity_distribution(sb[0]), "distribution")
+        assert abs(ca.compute_consistency_score(sa[0], sa[1]) - cb.compute_consistency_score(sb[0], sb[1])) < 1e-6
+        assert ca.compute_top_k_consistency(ia[0], ia[1], 5) == cb.compute_top_k_consistency(ib[0], ib[1], 5)
+        assert abs(ca.compute_rank_correlation(ia[0], ia[1]) - cb.compute_rank_correlation(ib[0], ib[1])) < 1e-9
+    return n
+
+
+# ------------------------------------------------------------------------------------------ detector
+def check_detector(mods, rng):
+    """AdversarialDetector (src/detector.py:216-860): detect_adversarial for every method subset and aggregation,
+    batch_detect, compute_optimal_threshold, update_threshold, evaluate_detection_performance, get_stats,
+    save_model / load_model, caches."""
+    D = mods["src.detector"]
+    import types as _t
+    from multimodal_detection_consistency_b200 import detector as OD
+    from pipeline_dropin import TableClip, image_of
+    d, nq, V, G = 48, 20, 5, 3
+    sd = 1.0 / np.sqrt(d)
+    text_table, image_table, samples = {}, {}, []
+    for i in range(nq):
+        base = MG.unit(rng, 1, d)[0]
+        text = f"sample text {i}"
+        text_table[text] = base
+        for v in range(V):
+            tv = base + 0.3 * sd * rng.standard_normal(d).astype(np.float32)
+            text_table[f"{text} ~v{v}"] = (tv / np.linalg.norm(tv)).astype(np.float32)
+        attacked = bool(rng.uniform() < 0.45)
+        im = MG.unit(rng, 1, d)[0] if attacked else base + 0.6 * sd * rng.standard_normal(d).astype(np.float32)
+        image_table[100 + i] = (im / np.linalg.norm(im)).astype(np.float32)
+        for g in range(G):
+            ref = 0.7 * image_table[100 + i] + 2.0 * sd * rng.standard_normal(d).astype(np.float32)
+            image_table[500 + G * i + g] = (ref / np.linalg.norm(ref)).astype(np.float32)
+        samples.append((image_of(100 + i), text, attacked))
+    index_of = {s[1]: i for i, s in enumerate(samples)}
+    clip = TableClip(text_table, image_table)
+    aug = _t.SimpleNamespace(generate_variants=lambda t: [f"{t} ~v{v}" for v in range(V)])
+    few = _t.SimpleNamespace(generate_variants=lambda t: [f"{t} ~v{v}" for v in range(2 + index_of[t] % 3)])
+    gen = _t.SimpleNamespace(generate_reference_images=lambda text, num_images=G: {
+        "images": [image_of(500 + G * index_of[text] + g) for g in range(min(num_images, 1 + index_of[text] % 3))],
+        "generation_time": 0.0})
+    n = 0
+    for agg in ("weighted_mean", "mean", "max", "min"):
+        for methods in (None, ["consistency"], ["text_variants", "consistency"], ["sd_reference"]):
+            a = D.AdversarialDetector(D.DetectorConfig(score_aggregation=agg, detection_threshold=0.42))
+            b = OD.AdversarialDetector(OD.DetectorConfig(score_aggregation=agg, detection_threshold=0.42))
+            for det in (a, b):
+                det.clip_model, det.text_augmenter, det.sd_generator = clip, (few if agg == "mean" else aug), gen
+            for im, text, _ in samples:
+                ra, rb = a.detect_adversarial(im, text, methods), b.detect_adversarial(im, text, methods)
+                assert "error" not in ra and "error" not in rb, (ra.get("error"), rb.get("error"))
+                if abs(ra["aggregated_score"] - 0.42) < 1e-5:
+                    rb["is_adversarial"] = ra["is_adversarial"]
+                _same({k: v for k, v in ra.items() if k != "detection_time"},
+                      {k: v for k, v in rb.items() if k != "detection_time"}, f"{agg} {methods} {text}", tol=3e-6)
+                n += 1
+            sa, sb = a.get_stats(), b.get_stats()
+            sa["detection_stats"].pop("detection_time"), sb["detection_stats"].pop("detection_time")
+            _same(sa, sb, "detector stats")
+    a = D.AdversarialDetector(D.DetectorConfig())
+    b = OD.AdversarialDetector(OD.DetectorConfig())
+    for det in (a, b):
+        det.clip_model, det.text_augmenter, det.sd_generator = clip, aug, gen
+    ims, txts = [s[0] for s in samples], [s[1] for s in samples]
+    ba, bb = a.batch_detect(ims, txts), b.batch_detect(ims, txts)
+    for x, y in zip(ba, bb):
+        _same({k: v for k, v in x.items() if k != "detection_time"}, {k: v for k, v in y.items() if k != "detection_time"},
+              "batch_detect", tol=3e-6)
+    ta, tb = a.compute_optimal_threshold(samples), b.compute_optimal_threshold(samples)
+    assert abs(ta - tb) <= 3e-6, (ta, tb)
+    a.update_threshold(ta), b.update_threshold(ta)
+    a.clear_cache(), b.clear_cache()
+    pa, pb = a.evaluate_detection_performance(samples), b.evaluate_detection_performance(samples)
+    # the reference calls DetectionEvaluator.compute_metrics, which does not exist (src/detector.py:806 vs
+    # src/utils/metrics.py:285), so its method always returns {}; the mirror returns the confusion counts
+    assert pa == {} and sorted(pb) == ["accuracy", "f1", "fn", "fp", "precision", "recall", "tn", "tp"]
+    pred = np.array([b.detect_adversarial(im, tx)["is_adversarial"] for im, tx, _ in samples])
+    lab = np.array([x[2] for x in samples])
+    assert pb["tp"] == int((pred & lab).sum()) and pb["fp"] == int((pred & ~lab).sum())
+    assert pb["fn"] == int((~pred & lab).sum()) and pb["tn"] == int((~pred & ~lab).sum())
+    assert abs(pb["accuracy"] - float((pred == lab).mean())) < 1e-12
+    with tempfile.TemporaryDirectory() as td:
+        a.save_model(f"{td}/a.json"), b.save_model(f"{td}/b.json")
+        ja, jb = json.loads(Path(f"{td}/a.json").read_text()), json.loads(Path(f"{td}/b.json").read_text())
+        assert sorted(ja) == sorted(jb) and sorted(ja["config"]) == sorted(jb["config"])
+        a2, b2 = D.AdversarialDetector(D.DetectorConfig()), OD.AdversarialDetector(OD.DetectorConfig())
+        a2.load_model(f"{td}/b.json"), b2.load_model(f"{td}/a.json")              # each loads the other's file
+        assert abs(a2.config.detection_threshold - ta) < 1e-12 and abs(b2.config.detection_threshold - ta) < 1e-12
+    # error convention: no encoder at all -> the documented dict, never an exception (src/detector.py:428-439)
+    bare = OD.AdversarialDetector(OD.DetectorConfig())
+    bare._tried.update({"clip", "aug", "sd"})
+    r = bare.detect_adversarial(ims[0], txts[0])
+    assert r["is_adversarial"] is False and r["aggregated_score"] == 0.0 and "error" in r
+    return n
+
+
 def main():
     seeds = [int(s) for s in sys.argv[1:]] or [31, 32]
     mods = MG.import_reference()
@@ -212,7 +424,7 @@ def main():
             rng = np.random.default_rng(seed)
             np.random.seed(seed)
             done = {f.__name__[6:]: f(mods, rng) for f in (check_ref_bank, check_consistency_checker, check_hubness,
-                                                           check_evaluator)}
+                                                           check_evaluator, check_retriever, check_detector)}
             print(f"seed {seed}: " + ", ".join(f"{k} {v}" for k, v in done.items()))
     print("mirrors live check ok")
 

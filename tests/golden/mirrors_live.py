@@ -416,6 +416,127 @@ def check_detector(mods, rng):
     return n
 
 
+# ------------------------------------------------------------------------------------------ retrieval references (a8)
+def check_retrieval_reference(mods, rng):
+    """RetrievalReferenceGenerator.retrieve_references (experiments/defenses/retrieval_ref.py:173-290: features.npy
+    database, top-`rerank_top_k` inner-product search, similarity floor, cut to `reference_count`) on its NumPy
+    branch and on its FAISS branch (NumPy IndexFlatIP stand-in), next to defenses.RetrievalReferenceIndex."""
+    import importlib.util
+    from multimodal_detection_consistency_b200 import defenses as ODf
+    from pipeline_dropin import NumpyFlatIP
+    spec = importlib.util.spec_from_file_location("ref_retrieval_ref", MG.REF / "experiments" / "defenses" / "retrieval_ref.py")
+    RR = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RR)
+    sys.modules["faiss"].IndexFlatIP = NumpyFlatIP
+    n, d = 300, 40
+    feats = MG.unit(rng, n, d)
+    meta = [{"path": f"ref_{j}.jpg", "j": j} for j in range(n - 5)]              # shorter than the features (:255)
+    texts = {f"reference query {j}": (lambda v: (v / np.linalg.norm(v)).astype(np.float32))(
+        feats[rng.integers(n)] + rng.uniform(0.05, 0.6) * rng.standard_normal(d).astype(np.float32)) for j in range(20)}
+    clip = type("Clip", (), {"encode_text": lambda self, ts: torch.stack([torch.from_numpy(texts[t]) for t in ts])})()
+    done = 0
+    with tempfile.TemporaryDirectory() as td:
+        np.save(Path(td) / "features.npy", feats)
+        (Path(td) / "metadata.json").write_text(json.dumps(meta))
+        for use_faiss in (False, True):
+            for count, floor, rerank in ((5, 0.3, True), (3, 0.55, True), (8, 0.0, False)):
+                cfg = RR.RetrievalConfig(reference_count=count, similarity_threshold=floor, use_faiss=use_faiss,
+                                         faiss_index_type="Flat", device="cpu", enable_reranking=rerank, rerank_top_k=20)
+                ref = RR.RetrievalReferenceGenerator(clip, td, cfg)
+                assert (ref.faiss_index is not None) == use_faiss
+                ours = ODf.RetrievalReferenceIndex(feats, meta, reference_count=count, similarity_threshold=floor,
+                                                   rerank_top_k=20, enable_reranking=rerank)
+                for t, q in texts.items():
+                    a, b = ref.retrieve_references(t), ours.retrieve_references(q)
+                    assert [x["index"] for x in a] == [x["index"] for x in b], (use_faiss, count, floor, t)
+                    assert np.allclose([x["similarity"] for x in a], [x["similarity"] for x in b], rtol=0, atol=2e-6)
+                    assert [x["metadata"] for x in a] == [x["metadata"] for x in b]
+                    assert all(np.array_equal(x["features"], y["features"]) for x, y in zip(a, b))
+                    done += len(a)
+    assert done > 0
+    return done
+
+
+# ------------------------------------------------------------------------------------------ defense detector (a14)
+def check_defense_detector(mods, rng):
+    """MultiModalDefenseDetector.detect (experiments/defenses/detector.py:117-325): variants -> retrieval references
+    of every variant, de-duplicated at cosine 0.95 and cut to 10 -> generated references -> 9 consistency scores
+    -> ConsistencyChecker decision.  The reference object is assembled as tests/golden/make_golden.py does (its
+    constructor does not match its own collaborators' signatures, :87-103); its retrieval collaborator returns
+    the ids our RetrievalReferenceIndex returns (check_retrieval_reference pins that equivalence)."""
+    import types as _t
+    ED = mods["experiments.defenses.detector"]
+    CC = mods["experiments.defenses.consistency_checker"]
+    from multimodal_detection_consistency_b200 import defenses as ODf
+    from oracle import tvc_oracle as O
+    d, n_gal, nq, V, G = 40, 200, 16, 4, 3
+    sd = 1.0 / np.sqrt(d)
+    cent = MG.unit(rng, 8, d)
+    gal = cent[rng.integers(0, 8, n_gal)] + 0.5 * sd * rng.standard_normal((n_gal, d)).astype(np.float32)
+    gal = (gal / np.linalg.norm(gal, axis=1, keepdims=True)).astype(np.float32)
+    gal[11], gal[12] = gal[10], (gal[10] + 0.01 * sd * rng.standard_normal(d)).astype(np.float32)   # exact + near duplicate
+    gal[12] /= np.linalg.norm(gal[12])
+    text_table, image_table = {}, {j: gal[j] for j in range(n_gal)}
+    samples = []
+    for i in range(nq):
+        pick = 10 if i < 3 else int(rng.integers(n_gal))                       # the duplicated rows get retrieved
+        text = f"defense sample {i}"
+        t = gal[pick] + 0.4 * sd * rng.standard_normal(d).astype(np.float32)
+        text_table[text] = (t / np.linalg.norm(t)).astype(np.float32)
+        for v in range(V):
+            tv = text_table[text] + 0.3 * sd * rng.standard_normal(d).astype(np.float32)
+            text_table[f"{text} ~v{v}"] = (tv / np.linalg.norm(tv)).astype(np.float32)
+        im = MG.unit(rng, 1, d)[0] if rng.uniform() < 0.4 else gal[pick] + 0.5 * sd * rng.standard_normal(d).astype(np.float32)
+        image_table[1000 + i] = (im / np.linalg.norm(im)).astype(np.float32)
+        for g in range(G):
+            r = 0.7 * image_table[1000 + i] + 1.5 * sd * rng.standard_normal(d).astype(np.float32)
+            image_table[5000 + G * i + g] = (r / np.linalg.norm(r)).astype(np.float32)
+        samples.append((torch.tensor(1000 + i), text))
+    index_of = {s[1]: i for i, s in enumerate(samples)}
+    clip = MG._TableClip(text_table, image_table)
+    clip_b = _t.SimpleNamespace(
+        encode_text=lambda ts: torch.stack([torch.from_numpy(text_table[t]) for t in ts]),
+        encode_image=lambda im: torch.from_numpy(image_table[int(torch.as_tensor(im).reshape(-1)[0])])[None])
+    variants = _t.SimpleNamespace(generate_variants=lambda t: [f"{t} ~v{v}" for v in range(V)])
+    root_of = lambda t: t.split(" ~v")[0]                                         # noqa: E731
+    generator = _t.SimpleNamespace(generate_references=lambda t: [torch.tensor(5000 + G * index_of[root_of(t)] + g)
+                                                                  for g in range(2 if "~v" in t else 1)])
+
+    def retrieve(text):
+        s, i = O.search(text_table[text][None], gal, 5, threshold=0.3)
+        return [torch.tensor(int(j)) for j in i[0] if j >= 0]
+
+    done = 0
+    for voting in ("weighted", "adaptive", "simple"):
+        ref = object.__new__(ED.MultiModalDefenseDetector)
+        ref.clip_model, ref.config, ref.device = clip, ED.DetectionConfig(voting_strategy=voting), torch.device("cpu")
+        ref.text_variant_generator, ref.generative_generator = variants, generator
+        ref.retrieval_generator = _t.SimpleNamespace(retrieve_references=retrieve)
+        ref.consistency_checker = CC.ConsistencyChecker(threshold=0.5, adaptive_threshold=True, voting_strategy=voting)
+        ours = ODf.MultiModalDefenseDetector(
+            clip_model=clip_b, config=ODf.DetectionConfig(voting_strategy=voting), text_variant_generator=variants,
+            retrieval_index=ODf.RetrievalReferenceIndex(gal, reference_count=5, similarity_threshold=0.3),
+            generative_generator=generator)
+        for image, text in samples:                                               # sequential: the checker's history builds up
+            a, b = ref.detect(image, text, return_details=True), ours.detect(image, text, return_details=True)
+            for key in ("confidence", "consistency_score"):
+                assert abs(float(a[key]) - float(b[key])) <= 3e-6, (voting, text, key, a[key], b[key])
+            dd = a["details"]["detection_details"]
+            if abs(dd["overall_score"] - dd["threshold"]) > 1e-5:
+                assert bool(a["is_adversarial"]) == bool(b["is_adversarial"]), (voting, text)
+            assert a["details"]["text_variants"] == b["details"]["text_variants"]
+            for key, val in a["details"]["consistency_scores"].items():
+                assert abs(float(val) - b["details"]["consistency_scores"][key]) <= 3e-6, (voting, text, key)
+            n_ref = len(a["details"]["retrieval_references"])
+            assert n_ref == int(b["details"]["consistency_scores"]["n_retrieval"]), (voting, text, n_ref)
+            done += 1
+        kept = {int(x) for x in ref._generate_retrieval_references(samples[0][1], [samples[0][1]] + variants.generate_variants(samples[0][1]))}
+        assert 10 in kept and 11 not in kept and 12 not in kept                   # duplicates of row 10 were dropped
+        ba = ours.batch_detect([s[0] for s in samples[:6]], [s[1] for s in samples[:6]])
+        assert len(ba) == 6 and all(sorted(r) == ["confidence", "consistency_score", "is_adversarial"] for r in ba)
+    return done
+
+
 def main():
     seeds = [int(s) for s in sys.argv[1:]] or [31, 32]
     mods = MG.import_reference()
@@ -424,7 +545,8 @@ def main():
             rng = np.random.default_rng(seed)
             np.random.seed(seed)
             done = {f.__name__[6:]: f(mods, rng) for f in (check_ref_bank, check_consistency_checker, check_hubness,
-                                                           check_evaluator, check_retriever, check_detector)}
+                                                           check_evaluator, check_retriever, check_detector,
+                                                           check_retrieval_reference, check_defense_detector)}
             print(f"seed {seed}: " + ", ".join(f"{k} {v}" for k, v in done.items()))
     print("mirrors live check ok")
 

@@ -6,6 +6,8 @@ clear_cache, get_stats) is imported unmodified and run twice on the same seeded 
   (A) with the reference's MultiModalRetriever / AdversarialDetector.  faiss is not installable here, so
       `faiss.IndexFlatIP` is a 15-line NumPy stand-in (exact inner product, descending) - the published
       contract the reference relies on (src/retrieval.py:495-518, 652-656);
+  (C) with the reference's own classes and only the `faiss` module replaced by faiss_compat (INTEGRATION.md
+      level 1: no source change at all);
   (B) with this repo's mirrors swapped in exactly as INTEGRATION.md level 2 says - the two import lines
       of src/pipeline.py:19,21 - and NOTHING else changed.  This container has no GPU, so the native
       layer under the mirrors is the oracle-backed test double tests/fake_native.py; what is exercised
@@ -200,6 +202,23 @@ def main():
             P.AdversarialDetector, P.DetectorConfig = our_det.AdversarialDetector, our_det.DetectorConfig
             with fake_native.installed() as ctx:
                 b = run_arm(P, world, swap=True)
+            # ---- arm (C), INTEGRATION.md level 1: the reference's OWN classes, only `faiss` swapped for
+            # faiss_compat (sys.modules["faiss"] = faiss_compat before `import src.retrieval`) ----
+            for n, v in ref_names.items():
+                setattr(P, n, v)
+            from multimodal_detection_consistency_b200 import faiss_compat
+            fa = sys.modules["faiss"]
+            for name in ("IndexFlatIP", "IndexIVFFlat", "IndexHNSWFlat", "StandardGpuResources", "index_cpu_to_gpu",
+                         "get_num_gpus", "write_index", "read_index"):
+                setattr(fa, name, getattr(faiss_compat, name))
+            with fake_native.installed():
+                c = run_arm(P, world, swap=False)
+                assert type(c["pipe"].retriever).__module__ == "src.retrieval"
+                assert isinstance(c["pipe"].retriever.image_index, faiss_compat.IndexFlatIP)
+            fa.IndexFlatIP = NumpyFlatIP
+            compare(a["first"], c["first"], "faiss_compat first")
+            for ra, rc in zip(a["batch"], c["batch"]):
+                compare(ra, rc, f"faiss_compat batch[{ra.original_text}]")
             assert type(b["pipe"].retriever).__module__.startswith("multimodal_detection_consistency_b200")
             assert type(b["pipe"].detector).__module__.startswith("multimodal_detection_consistency_b200")
             compare(a["first"], b["first"], "first")

@@ -71,7 +71,8 @@ class FakeGallery:
 
 
 class FakeContext:
-    launches = 0
+    def __init__(self):
+        self.launches = 0
 
     def consistency_emb(self, params, img, txt, var=None, ret_gallery=None, ret_idx=None, gen=None, g_cnt=None,
                         gen_gallery=None, gen_idx=None, return_sims=False):
@@ -83,7 +84,7 @@ class FakeContext:
             gen_idx=_np(gen_idx, np.int64).reshape(len(img), -1) if gen_idx is not None else None, params=p,
             ret_offset=ret_gallery.global_row_offset if ret_gallery is not None else 0,
             gen_offset=gen_gallery.global_row_offset if gen_gallery is not None else 0)
-        FakeContext.launches += 1
+        self.launches += 1
         scores = scores.astype(np.float32)
         if not return_sims:
             return scores, flags

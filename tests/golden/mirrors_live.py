@@ -172,7 +172,14 @@ def check_hubness(mods, rng):
     im = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((ni, d)).astype(np.float32)), dim=1)
     tx = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)), dim=1)
     im[0] = torch.nn.functional.normalize(tx[: max(1, nq // 3)].mean(0), dim=0)
-    assert OH.compute_hubness(im.numpy(), tx.numpy(), 10) == float(H.HubnessAttack.compute_hubness(None, im, tx, 10))
+    want = float(H.HubnessAttack.compute_hubness(None, im, tx, 10))
+    assert OH.compute_hubness(im.numpy(), tx.numpy(), 10) == want
+    original = OH.install(H.HubnessAttack)                  # the reference class itself, routed through the mirror
+    try:
+        attacker = object.__new__(H.HubnessAttack)
+        assert attacker.compute_hubness(im, tx) == want and attacker.compute_hubness(im, tx, k=5) == want
+    finally:
+        H.HubnessAttack.compute_hubness = original
     md = (MG.REF / "references" / "Adversarial_Hubness_Multi_Modal_Retrieval" / "README.md").read_text()
     block = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "def compute_hubness" in b][0]
     from sklearn.metrics.pairwise import cosine_similarity

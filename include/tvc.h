@@ -153,7 +153,11 @@ int tvc_ctx_last_search_kernel_ms(tvc_ctx* ctx, float* ms, int64_t* launches);
 
 /* Gallery: N rows of dimension d resident in HBM as bf16 [N, d_pad] (GEMM operand, d_pad = d
  * rounded up to 64) plus an fp32 master [N, d] used to re-rank the bf16 candidates.
- * `global_row_offset` is added to every returned index (row-sharded galleries). */
+ * `global_row_offset` is added to every returned index (row-sharded galleries).
+ * Replaces: faiss.IndexFlatIP(d) + index.add(features)  src/retrieval.py:477-525 (FaissIndexManager
+ * .build_index/.add_to_index :117-155, RetrievalIndex.build_index/.add_items :212-287,
+ * experiments/defenses/retrieval_ref.py:140-156); the per-query np.array([ref.vector ...]) of
+ * ReferenceBank  src/ref_bank.py:475; references.append / pop  src/ref_bank.py:143-151, 365-399. */
 int tvc_gallery_create(tvc_ctx* ctx, const void* rows, int dtype, int64_t n, int32_t d,
                        int64_t global_row_offset, uint32_t flags, int64_t capacity_hint, void* stream,
                        tvc_gallery** out);
@@ -188,7 +192,13 @@ int tvc_gallery_import_ipc(tvc_ctx* ctx, const void* handle, int64_t n, int32_t 
 int tvc_gallery_group_create(tvc_ctx* ctx, tvc_gallery** parts, int32_t n_parts, tvc_gallery** out);
 
 /* Exact top-k of every query row against the gallery: out_sim [m, k] f32, out_idx [m, k] i64.
- * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K. */
+ * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K.
+ * Replaces: index.search(q, k)  src/retrieval.py:652-656 (:130-137, :235-264); sklearn
+ * cosine_similarity + argsort  src/retrieval.py:669-671; ReferenceBank._compute_similarities + `>= thr`
+ * + argsort  src/ref_bank.py:462-484, 191-203; _faiss_retrieve / _numpy_retrieve
+ * experiments/defenses/retrieval_ref.py:246-290; F.cosine_similarity + topk(.,1)
+ * src/attacks/hubness_attack.py:482-489; the k-NN of the hubness spec
+ * references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:43-47 (TVC_SEARCH_SKIP_SELF). */
 int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m, int32_t d,
                int32_t k, float threshold, uint32_t flags, float* out_sim, int64_t* out_idx,
                void* stream);
@@ -237,16 +247,24 @@ int tvc_peer_close(tvc_ctx* ctx, void* ptr);
 int tvc_peer_free(tvc_ctx* ctx, void* ptr);
 
 /* Dense [m, N] fp32 similarity matrix (tcgen05 GEMM, plain store epilogue). Only for sizes that
- * fit; the search path never materialises it. */
+ * fit; the search path never materialises it.
+ * Replaces: MultiModalRetriever.compute_similarity_matrix  src/retrieval.py:682-722;
+ * SimilarityCalculator.batch_cosine_similarity  src/utils/metrics.py:144-164. */
 int tvc_similarity_matrix(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, int64_t m,
                           int32_t d, uint32_t flags, float* out, void* stream);
 
-/* Merge `parts` candidate lists per row (the all-gathered per-shard top-k): in_sim/in_idx
+/* (new: the reference has no multi-GPU retrieval, src/retrieval.py:112,508 are single-device)
+ * Merge `parts` candidate lists per row (the all-gathered per-shard top-k): in_sim/in_idx
  * [m, parts, k] -> out [m, k], ordered (sim desc, idx asc); idx < 0 entries are ignored. */
 int tvc_merge_topk(tvc_ctx* ctx, const float* in_sim, const int64_t* in_idx, int64_t m,
                    int32_t parts, int32_t k, float* out_sim, int64_t* out_idx, void* stream);
 
 /* Variant-consistency reduction fed precomputed similarities.
+ * Replaces (per query, all three decision stacks in one pass): AdversarialDetector
+ * ._detect_by_text_variants / _sd_reference / _consistency, _aggregate_scores and the `> threshold`
+ * decision  src/detector.py:441-590, 643-682, 399; ConsistencyChecker.make_decision (voting, stateless
+ * adaptive threshold, `<`, confidence)  experiments/defenses/consistency_checker.py:74-272;
+ * _compute_cross_modal_variance  experiments/defenses/detector.py:295-300.
  *  s0 [Q]; sv [Q,V]; sr [Q,R] with r_cnt [Q] (NULL = all R valid); sg [Q,G] with g_cnt [Q];
  *  sxv [Q, V*(V-1)/2] variant<->variant cosines (may be NULL).  scores [Q, TVC_NSCORES]; flags [Q]. */
 int tvc_consistency_sims(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, const float* s0,
@@ -255,6 +273,8 @@ int tvc_consistency_sims(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, 
                          void* stream);
 
 /* Variant-consistency reduction fed embedding rows (fp32, L2-normalised by the encoders).
+ * Replaces: MultiModalDefenseDetector._compute_consistency_scores and _deduplicate_references
+ * experiments/defenses/detector.py:228-325 (plus everything tvc_consistency_sims replaces).
  *  img [Q,d]; txt [Q,d]; var [Q,V,d];
  *  retrieval refs: ret_idx [Q, n_ret_cand] global indices into `ret_gallery` (the search output,
  *  variant-major), greedily de-duplicated (index, then cosine > dedup_threshold) and cut to R;
@@ -289,6 +309,10 @@ int tvc_retrieval_metrics(tvc_ctx* ctx, const int64_t* topk_idx, int64_t q, int3
                           void* stream);
 
 /* k-occurrence histogram N_k(j) = #{rows i : j in idx[i, :k]}; idx < 0 or >= n_bins ignored.
+ * Replaces: the `hubness_counts[j] += 1` double loop
+ * references/Adversarial_Hubness_Multi_Modal_Retrieval/README.md:48-57; `(top1 == 0).sum()`
+ * src/attacks/hubness_attack.py:492-496; the per-image scores of
+ * benchmarks/hubness_attack_benchmark.py:335-348.
  * counts [n_bins] int32; zero_first != 0 clears it before accumulating. `idx_base` is subtracted
  * from every index first (a rank histogramming global indices into its own slice passes 0). */
 int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int64_t idx_base,

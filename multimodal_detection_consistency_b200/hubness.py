@@ -14,11 +14,9 @@ numpy in -> numpy out; torch cuda in -> torch cuda out (no host round trip).
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 
-from ._native import Context, Gallery, _is_torch
+from ._native import Gallery, _is_torch
 
 
 def _gallery(rows, normalize=True) -> Gallery:

@@ -1,12 +1,10 @@
 """On-disk formats: the FAISS flat-index sidecar layout, retriever pickles written
 by the reference's own class names, and the ReferenceBank 4-file JSON layout incl. the snapshot the
 reference ships (cache/ref_bank)."""
-import json
 import pickle
 import struct
 import sys
 import types
-from pathlib import Path
 
 import numpy as np
 import pytest

@@ -106,6 +106,27 @@ def check_ref_bank(mods, rng):
             q = vecs[5] + 0.1 * rng.standard_normal(d)
             assert [it.metadata["i"] for it, _ in cross_a.query_similar(q, 4, 0.2)] == \
                    [it.metadata["i"] for it, _ in cross_b.query_similar(q, 4, 0.2)]
+            # export / import (src/ref_bank.py:618-715): each implementation imports what the other exported,
+            # into a bank with room for only 12 more
+            for fmt, name in (("json", "x.json"), ("numpy", "x.npz")):
+                assert ref.export_references(f"{ta}/exp/{name}", fmt) and ours.export_references(f"{tb}/exp/{name}", fmt)
+                small = []
+                for mod, src_dir in ((RB, tb), (OB, ta)):
+                    bank = mod.ReferenceBank(mod.ReferenceBankConfig(max_size=12, similarity_threshold=0.9,
+                                                                     persistence_enabled=False, auto_clustering=False,
+                                                                     save_path=f"{ta}/unused", feature_dim=d))
+                    assert bank.import_references(f"{src_dir}/exp/{name}", fmt)
+                    assert not bank.import_references(f"{src_dir}/exp/missing.{fmt}", fmt)
+                    small.append(bank)
+                assert [r.metadata["i"] for r in small[0].references] == [r.metadata["i"] for r in small[1].references] \
+                    == [r.metadata["i"] for r in ref.references[:12]]
+                assert small[0].stats["total_added"] == small[1].stats["total_added"] == 12
+                ra, rb = small[0].query_similar(q, 3, 0.1), small[1].query_similar(q, 3, 0.1)
+                assert [it.metadata["i"] for it, _ in ra] == [it.metadata["i"] for it, _ in rb]
+                assert np.allclose([s_ for _, s_ in ra], [s_ for _, s_ in rb], rtol=0, atol=2e-6)
+            assert not ours.export_references(f"{tb}/exp/x.bin", "parquet") and not ref.export_references(f"{ta}/exp/x.bin", "parquet")
+            ref.clear(), ours.clear()
+            assert ref.get_statistics() == ours.get_statistics() and ours.query_similar(q) == ref.query_similar(q) == []
     return total
 
 

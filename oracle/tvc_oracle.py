@@ -526,8 +526,10 @@ def retrieval_metrics_from_topk(topk_idx: np.ndarray, relevant: Sequence[Sequenc
 
 
 # --------------------------------------------------------------------------------------------
-# The documented reference-vector rule (README.md:474-482, 846; the reference has prose and pseudo-code
-# only, no executable form - parity for this mode is against this restatement, unpinned):
+# The documented reference-vector rule (README.md:474-482, 846; prose only in the reference - parity for
+# this per-variant form is against this restatement, UNPINNED.  The flat form of the same rule, std over
+# cos(image, every reference), is consistency_one's S_REF_SIGMA and IS pinned: tests/golden/live_check.py
+# exec's the pseudo-code of README.md:225-319 next to it):
 #   per variant: mean of its top-k retrieved rows and its m generated rows -> r_v; mean_v r_v -> r;
 #   S_v = cos(image, r_v); sigma = std(S) (population); adversarial iff sigma > threshold.
 def reference_vector_rule(img: np.ndarray, ret_rows: Optional[np.ndarray], ret_idx: Optional[np.ndarray],

@@ -195,13 +195,81 @@ def check_detectors(mods, rng):
     return len(img) * 5
 
 
+def check_readme_sigma_rule(mods, rng):
+    """The documented detection flow, README.md:225-319 (the reference's only executable statement of the
+    TVC rule), exec'd from the markdown with table collaborators: its `img_std` over cos(query image, every
+    retrieved / generated reference), the `img_std > adaptive_threshold` vote (recommended 0.30, README.md:846)
+    and `cross_modal` are the oracle's S_REF_SIGMA, FLAG_SIGMA_ADV and S_ORIGINAL of the similarity-fed mode."""
+    import types
+    md = (MG.REF / "README.md").read_text()
+    block = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "def detect_adversarial(image, text)" in b][0]
+    d, n_gal, V, K, M = 48, 120, 3, 3, 1
+    cent = MG.unit(rng, 5, d)
+    gal = MG.unit(rng, n_gal, d) * 0.6 + cent[rng.integers(0, 5, n_gal)]
+    gal = (gal / np.linalg.norm(gal, axis=1, keepdims=True)).astype(np.float32)
+    table = {}
+    checked = flagged = 0
+    for i in range(24):
+        text = f"t{i}"
+        base = gal[rng.integers(n_gal)]
+        table[text] = O.l2_normalize((base + 0.05 * rng.standard_normal(d))[None].astype(np.float32))[0]
+        variants = [f"{text}/v{v}" for v in range(V)]
+        for vtxt in variants:
+            table[vtxt] = O.l2_normalize((table[text] + rng.uniform(0.02, 1.2) * rng.standard_normal(d))[None].astype(np.float32))[0]
+        image = O.l2_normalize((base + rng.uniform(0.05, 1.5) * rng.standard_normal(d))[None].astype(np.float32))[0]
+        sign = -1.0 if i % 2 else 0.5                                 # odd samples: generated references oppose the image
+        sd = {vtxt: [O.l2_normalize((image * sign + 0.1 * rng.standard_normal(d))[None].astype(np.float32))[0] for _ in range(M)]
+              for vtxt in variants}
+
+        def retrieve(variant, top_k=5, **_):
+            _, idx = O.search(table[variant][None], gal, K)
+            return [("gal", int(j)) for j in idx[0]]
+
+        ns = {
+            "np": np,
+            "text_augmenter": types.SimpleNamespace(generate_variants=lambda t, **kw: list(variants)),
+            "retriever": types.SimpleNamespace(retrieve_images_by_text=retrieve),
+            "sd_generator": types.SimpleNamespace(generate_reference_images=lambda prompt, **kw: [("sd", prompt, m) for m in range(M)]),
+            "clip_model": types.SimpleNamespace(
+                encode_image=lambda im: image if isinstance(im, str) else (gal[im[1]] if im[0] == "gal" else sd[im[1]][im[2]]),
+                encode_text=lambda t: table[t]),
+            "cosine_similarity": lambda a, b: float(O.scalar_cosine(a, b)),
+            "adaptive_threshold": 0.30,
+            "anomaly_classifier": types.SimpleNamespace(predict=lambda x: [False]),
+        }
+        exec(block, ns)
+        want = ns["detect_adversarial"]("query-image", text)
+        # the same references, in the pseudo-code's order, as similarity lists for the oracle
+        sr, sg = [], []
+        for vtxt in variants:
+            sr += [O.scalar_cosine(image, gal[j]) for _, j in retrieve(vtxt)]
+            sg += [O.scalar_cosine(image, r) for r in sd[vtxt]]
+        s0 = O.scalar_cosine(image, table[text])
+        row, flag = O.consistency_one(s0, [], sr, sg, params=dict(n_variants=0, n_retrieval=len(sr), n_generative=len(sg),
+                                                                  sigma_threshold=0.30))
+        cs = want["consistency_scores"]
+        # the pseudo-code interleaves retrieved and generated references per variant; a population std does not
+        # depend on the order
+        assert abs(row[O.S_REF_SIGMA] - cs["image_std"]) <= 1e-12, (row[O.S_REF_SIGMA], cs["image_std"])
+        assert abs(row[O.S_ORIGINAL] - cs["cross_modal"]) <= 1e-12
+        n = len(sr) + len(sg)
+        assert abs((row[O.S_RET_MEAN] * len(sr) + row[O.S_GEN_MEAN] * len(sg)) / n - cs["image_mean"]) <= 1e-12
+        if abs(cs["image_std"] - 0.30) > 1e-9:
+            assert bool(flag & O.FLAG_SIGMA_ADV) == bool(want["detection_votes"][0])
+        flagged += bool(flag & O.FLAG_SIGMA_ADV)
+        checked += 1
+    assert 0 < flagged < checked, flagged                              # both sides of the 0.30 vote were exercised
+    return checked
+
+
 def main():
     seeds = [int(s) for s in sys.argv[1:]] or [1001, 1002, 1003]
     mods = MG.import_reference()
     for seed in seeds:
         rng = np.random.default_rng(seed)
         done = {f.__name__[6:]: f(mods, rng) for f in (check_ref_bank, check_consistency_checker, check_search,
-                                                       check_hubness, check_metrics, check_detectors)}
+                                                       check_hubness, check_metrics, check_detectors,
+                                                       check_readme_sigma_rule)}
         print(f"seed {seed}: " + ", ".join(f"{k} {v}" for k, v in done.items()))
     print("live reference check ok")
 

@@ -6,7 +6,7 @@ Reference-shaped classes (same names / configs / result shapes as the reference'
   detector.AdversarialDetector, DetectorConfig
   defenses.ConsistencyChecker, MultiModalDefenseDetector, DetectionConfig, RetrievalReferenceIndex
   hubness.compute_hubness, k_occurrence, hubness_scores
-  metrics.RetrievalEvaluator, RetrievalMetrics;  batching.MicroBatcher
+  metrics.RetrievalEvaluator, RetrievalMetrics, SimilarityCalculator;  batching.MicroBatcher
   faiss_compat  (install as sys.modules["faiss"] to route the reference's own files here)
 Batched engine: pipeline.TVCScorer;  raw kernels: Context, Gallery.
 """
@@ -27,7 +27,7 @@ _LAZY = {
     "compute_hubness": "hubness", "k_occurrence": "hubness", "hubness_scores": "hubness",
     "compute_hubness_loss": "hubness",
     "TVCScorer": "pipeline",
-    "RetrievalEvaluator": "metrics", "RetrievalMetrics": "metrics",
+    "RetrievalEvaluator": "metrics", "RetrievalMetrics": "metrics", "SimilarityCalculator": "metrics",
     "MicroBatcher": "batching",
 }
 

@@ -92,3 +92,34 @@ class RetrievalEvaluator:
         k = min(max(int(x) for x in k_values), MAX_LIST, len(gallery))
         _, idx = gallery.search(query_features, k, normalize_queries=normalize_queries)
         return RetrievalEvaluator.from_topk(idx, relevant, k_values, ctx=gallery.ctx)
+
+
+def _host(x) -> np.ndarray:
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class SimilarityCalculator:
+    """src/utils/metrics.py:107-164.  `cosine_similarity` of two vectors is a few hundred flops and stays on
+    the host (same zero-vector guard, same fp64 arithmetic as scipy's `1 - cosine`); `batch_cosine_similarity`
+    is the [N, D] x [M, D] cosine matrix and runs as kernel (a)'s GEMM with the plain-store epilogue
+    (tvc_similarity_matrix: bf16 operands, fp32 accumulate - within 2e-3 of the reference's fp32 `mm`)."""
+
+    @staticmethod
+    def cosine_similarity(x, y) -> float:
+        a, b = _host(x).astype(np.float64).ravel(), _host(y).astype(np.float64).ravel()
+        na, nb = np.linalg.norm(a), np.linalg.norm(b)
+        if na == 0 or nb == 0:
+            return 0.0
+        return float(np.dot(a, b) / (na * nb))
+
+    @staticmethod
+    def batch_cosine_similarity(x, y) -> np.ndarray:
+        rows = np.ascontiguousarray(_host(y), dtype=np.float32)
+        queries = np.ascontiguousarray(_host(x), dtype=np.float32)
+        gal = N.Gallery(rows, normalize=True)
+        try:
+            return np.asarray(gal.similarity_matrix(queries, normalize_queries=True))
+        finally:
+            gal.close()

@@ -229,6 +229,18 @@ def check_evaluator(mods, rng):
         assert abs(want.ndcg_at_k[k] - got.ndcg_at_k[k]) < 1e-6
     assert abs(want.mrr - got.mrr) < 1e-6 and abs(want.map_score - got.map_score) < 1e-6
     assert sorted(want.to_dict()) == sorted(got.to_dict())
+    # SimilarityCalculator (src/utils/metrics.py:107-164)
+    x, y = rng.standard_normal((9, 33)).astype(np.float32) * 3, rng.standard_normal((14, 33)).astype(np.float32) * 0.2
+    x[2] = 0.0
+    for i in range(9):
+        a, b = M.SimilarityCalculator.cosine_similarity(x[i], y[i]), OM.SimilarityCalculator.cosine_similarity(x[i], y[i])
+        assert abs(a - b) <= 5e-7, (i, a, b)
+    assert OM.SimilarityCalculator.cosine_similarity(torch.from_numpy(x[2]), list(y[0])) == 0.0
+    want_m = M.SimilarityCalculator.batch_cosine_similarity(x[3:], y)
+    assert np.allclose(OM.SimilarityCalculator.batch_cosine_similarity(x[3:], y), want_m, rtol=0, atol=2e-6)
+    assert np.allclose(OM.SimilarityCalculator.batch_cosine_similarity(torch.from_numpy(x[3:]), torch.from_numpy(y)),
+                       M.SimilarityCalculator.batch_cosine_similarity(torch.from_numpy(x[3:]), torch.from_numpy(y)),
+                       rtol=0, atol=2e-6)
     return nq
 
 
@@ -559,7 +571,7 @@ def check_defense_detector(mods, rng):
             assert n_ref == int(b["details"]["consistency_scores"]["n_retrieval"]), (voting, text, n_ref)
             done += 1
         kept = {int(x) for x in ref._generate_retrieval_references(samples[0][1], [samples[0][1]] + variants.generate_variants(samples[0][1]))}
-        assert 10 in kept and 11 not in kept and 12 not in kept                   # duplicates of row 10 were dropped
+        assert len(kept & {10, 11, 12}) == 1                                      # one of the (near-)duplicate rows survives
         ba = ours.batch_detect([s[0] for s in samples[:6]], [s[1] for s in samples[:6]])
         assert len(ba) == 6 and all(sorted(r) == ["confidence", "consistency_score", "is_adversarial"] for r in ba)
     return done

@@ -4,7 +4,8 @@ Reference-shaped classes (same names / configs / result shapes as the reference'
   retrieval.MultiModalRetriever, RetrievalConfig, FaissIndexManager, RetrievalIndex, ConsistencyCalculator
   ref_bank.ReferenceBank, ReferenceBankConfig, ReferenceItem
   detector.AdversarialDetector, DetectorConfig
-  defenses.ConsistencyChecker, MultiModalDefenseDetector, DetectionConfig, RetrievalReferenceIndex
+  defenses.ConsistencyChecker, MultiModalDefenseDetector, DetectionConfig, RetrievalReferenceIndex,
+           RetrievalReferenceGenerator, RetrievalRefConfig
   hubness.compute_hubness, k_occurrence, hubness_scores
   metrics.RetrievalEvaluator, RetrievalMetrics, SimilarityCalculator;  batching.MicroBatcher
   faiss_compat  (install as sys.modules["faiss"] to route the reference's own files here)
@@ -23,7 +24,7 @@ _LAZY = {
     "create_reference_bank": "ref_bank",
     "AdversarialDetector": "detector", "DetectorConfig": "detector", "create_adversarial_detector": "detector",
     "ConsistencyChecker": "defenses", "MultiModalDefenseDetector": "defenses", "DetectionConfig": "defenses",
-    "RetrievalReferenceIndex": "defenses",
+    "RetrievalReferenceIndex": "defenses", "RetrievalReferenceGenerator": "defenses", "RetrievalRefConfig": "defenses",
     "compute_hubness": "hubness", "k_occurrence": "hubness", "hubness_scores": "hubness",
     "compute_hubness_loss": "hubness",
     "TVCScorer": "pipeline",

@@ -234,13 +234,235 @@ class RetrievalReferenceIndex:
     def retrieve_references(self, query_features) -> List[Dict[str, Any]]:
         """One query row -> the reference's list of dicts (:250-262)."""
         sims, idx = self.retrieve_batch(_np(query_features).reshape(1, -1))
+        return self.rows_to_dicts(sims[0], idx[0])
+
+    def rows_to_dicts(self, sims_row, idx_row) -> List[Dict[str, Any]]:
         out = []
-        for s, i in zip(sims[0], idx[0]):
+        for s, i in zip(sims_row, idx_row):
             if i >= 0:
                 out.append({"index": int(i), "similarity": float(s),
                             "metadata": self.reference_metadata[i] if i < len(self.reference_metadata) else {},
                             "features": self.reference_features[i]})
         return out
+
+
+@dataclass
+class RetrievalRefConfig:
+    """`RetrievalConfig` of experiments/defenses/retrieval_ref.py:20-31 (field for field; named apart from
+    retrieval.RetrievalConfig of src/retrieval.py, which lives in this package too).  `use_faiss`,
+    `faiss_index_type`, `nlist`, `nprobe` are accepted and reported; the search itself is always the exact
+    inner-product search on the GPU (IVF / HNSW would be approximations of it)."""
+    reference_count: int = 5
+    similarity_threshold: float = 0.3
+    use_faiss: bool = True
+    faiss_index_type: str = "IVF"
+    nlist: int = 100
+    nprobe: int = 10
+    device: str = "cuda"
+    cache_size: int = 1000
+    enable_reranking: bool = True
+    rerank_top_k: int = 20
+
+
+class RetrievalReferenceGenerator:
+    """experiments/defenses/retrieval_ref.py:34-600 with the database resident in HBM: same constructor,
+    `features.npy` + `metadata.json` database (:85-124, 442-457), result dicts (:250-262), cache, statistics
+    keys (:542-570) and never-raise behaviour (:233-236).  `retrieve_references` is one exact search;
+    `batch_retrieve_references` - a Python loop in the reference (:318-333) - encodes the uncached texts in
+    ONE encoder call and searches them in ONE launch, then books them in order as the loop would."""
+
+    def __init__(self, clip_model, reference_db_path: str, config: Optional[RetrievalRefConfig] = None):
+        from pathlib import Path
+        self.clip_model = clip_model
+        self.config = config or RetrievalRefConfig()
+        self.reference_db_path = Path(reference_db_path)
+        self.reference_features: np.ndarray = np.empty((0, 512), np.float32)
+        self.reference_metadata: List[Dict[str, Any]] = []
+        self.feature_cache: Dict[int, List[Dict[str, Any]]] = {}
+        self._index: Optional[RetrievalReferenceIndex] = None
+        self.reset_statistics()
+        self._load_reference_database()
+
+    # -- database ---------------------------------------------------------------------------------
+    def _load_reference_database(self):
+        import json
+        try:
+            fp, mp = self.reference_db_path / "features.npy", self.reference_db_path / "metadata.json"
+            if not fp.exists() or not mp.exists():
+                logger.warning("reference database not found at %s: starting empty", self.reference_db_path)
+                self._create_empty_database()
+                return
+            self.reference_features = np.load(fp)
+            self.reference_metadata = json.loads(mp.read_text(encoding="utf-8"))
+            self._rebuild_index()
+        except Exception as e:  # noqa: BLE001
+            logger.error("loading the reference database failed: %s", e)
+            self._create_empty_database()
+
+    def _create_empty_database(self):
+        self.reference_features = np.empty((0, 512), np.float32)
+        self.reference_metadata = []
+        self._index = None
+
+    def _rebuild_index(self):
+        if self._index is not None:
+            self._index.gallery.close()
+        self._index = None
+        if self.reference_features.shape[0] > 0:
+            c = self.config
+            self._index = RetrievalReferenceIndex(self.reference_features, self.reference_metadata, c.reference_count,
+                                                  c.similarity_threshold, c.rerank_top_k, c.enable_reranking)
+            self._index.reference_features = self.reference_features      # results hand out the stored rows
+
+    def _save_reference_database(self):
+        import json
+        try:
+            self.reference_db_path.mkdir(parents=True, exist_ok=True)
+            np.save(self.reference_db_path / "features.npy", self.reference_features)
+            (self.reference_db_path / "metadata.json").write_text(
+                json.dumps(self.reference_metadata, ensure_ascii=False, indent=2), encoding="utf-8")
+        except Exception as e:  # noqa: BLE001
+            logger.error("saving the reference database failed: %s", e)
+
+    def add_reference_features(self, features, metadata_list: Sequence[Dict[str, Any]]) -> bool:
+        """Embedding-level insert (what add_reference_images does after its encoder calls, :419-438)."""
+        try:
+            new = np.asarray(_np(features)).reshape(len(metadata_list), -1)
+            self.reference_features = new if self.reference_features.shape[0] == 0 else \
+                np.vstack([self.reference_features, new.astype(self.reference_features.dtype)])
+            self.reference_metadata.extend(metadata_list)
+            self._rebuild_index()
+            self._save_reference_database()
+            return True
+        except Exception as e:  # noqa: BLE001
+            logger.error("adding references failed: %s", e)
+            return False
+
+    def add_reference_images(self, images, texts: List[str],
+                             metadata_list: Optional[List[Dict[str, Any]]] = None) -> bool:
+        """:366-440.  Tensors go to `clip_model.encode_image(t.unsqueeze(0))` as in the reference; paths and PIL
+        images are handed to the encoder as they are (its own preprocessing applies; the reference's torchvision
+        transform is upstream of the path)."""
+        try:
+            if len(images) != len(texts):
+                raise ValueError("images and texts differ in number")
+            feats, metas = [], []
+            for i, (image, text) in enumerate(zip(images, texts)):
+                if isinstance(image, str):
+                    from PIL import Image
+                    f = self.clip_model.encode_image([Image.open(image).convert("RGB")])
+                elif hasattr(image, "unsqueeze"):
+                    f = self.clip_model.encode_image(image.unsqueeze(0))
+                else:
+                    f = self.clip_model.encode_image([image])
+                f = _np(f).reshape(1, -1)
+                feats.append(f / np.linalg.norm(f, axis=-1, keepdims=True))
+                meta = {"text": text, "image_path": str(image) if isinstance(image, str) else None,
+                        "index": len(self.reference_metadata) + i}
+                if metadata_list and i < len(metadata_list):
+                    meta.update(metadata_list[i])
+                metas.append(meta)
+            return self.add_reference_features(np.vstack(feats), metas)
+        except Exception as e:  # noqa: BLE001
+            logger.error("adding reference images failed: %s", e)
+            return False
+
+    # -- retrieval --------------------------------------------------------------------------------
+    def _encode_texts(self, texts: List[str]) -> np.ndarray:
+        """:238-244 for a list: encode, L2-normalise, fp32."""
+        f = _np(self.clip_model.encode_text(list(texts))).reshape(len(texts), -1)
+        return (f / np.linalg.norm(f, axis=-1, keepdims=True)).astype(np.float32)
+
+    def _encode_text(self, text: str) -> np.ndarray:
+        return self._encode_texts([text])
+
+    def _book(self, text: str, refs: List[Dict[str, Any]], seconds: float):
+        """:218-231: running averages (over the count BEFORE this query), cache while there is room, counters."""
+        st = self.retrieval_stats
+        n = st["total_queries"]
+        st["average_retrieval_time"] = (st["average_retrieval_time"] * n + seconds) / (n + 1)
+        if refs:
+            st["average_similarity"] = (st["average_similarity"] * n + float(np.mean([r["similarity"] for r in refs]))) / (n + 1)
+        if len(self.feature_cache) < self.config.cache_size:
+            self.feature_cache[hash(text)] = refs
+        st["total_queries"] += 1
+        if refs:
+            st["successful_retrievals"] += 1
+
+    def retrieve_references(self, text: str) -> List[Dict[str, Any]]:
+        """:173-236."""
+        import time
+        t0 = time.time()
+        key = hash(text)
+        if key in self.feature_cache:
+            self.retrieval_stats["cache_hits"] += 1
+            return self.feature_cache[key]
+        try:
+            q = self._encode_text(text)
+            if self._index is None:
+                logger.warning("the reference database is empty")
+                return []
+            refs = self._index.retrieve_references(q)
+            self._book(text, refs, time.time() - t0)
+            return refs
+        except Exception as e:  # noqa: BLE001
+            logger.error("retrieving references failed: %s", e)
+            return []
+
+    def batch_retrieve_references(self, texts: List[str]) -> List[List[Dict[str, Any]]]:
+        """:318-333 with one encoder call and one search launch for the texts the cache does not hold."""
+        import time
+        try:
+            t0 = time.time()
+            fresh: Dict[str, List[Dict[str, Any]]] = {}
+            todo = [t for t in dict.fromkeys(texts) if hash(t) not in self.feature_cache]
+            if todo and self._index is not None:
+                q = self._encode_texts(todo)
+                sims, idx = self._index.retrieve_batch(q)
+                for t, s_row, i_row in zip(todo, sims, idx):
+                    fresh[t] = self._index.rows_to_dicts(s_row, i_row)
+            per_text = (time.time() - t0) / max(1, len(todo))
+            out = []
+            for t in texts:                                   # booked in order, exactly as the reference's loop would
+                if hash(t) in self.feature_cache:
+                    self.retrieval_stats["cache_hits"] += 1
+                    out.append(self.feature_cache[hash(t)])
+                elif t in fresh:
+                    self._book(t, fresh[t], per_text)
+                    out.append(fresh[t])
+                else:
+                    out.append([])
+            return out
+        except Exception as e:  # noqa: BLE001
+            logger.error("batched reference retrieval failed: %s", e)
+            return [self.retrieve_references(t) for t in texts]
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    def get_statistics(self) -> Dict[str, Any]:
+        """:542-570 (same keys)."""
+        st = dict(self.retrieval_stats)
+        st["database_info"] = {"total_references": int(self.reference_features.shape[0]),
+                               "feature_dimension": int(self.reference_features.shape[1]),
+                               "use_faiss": self.config.use_faiss,
+                               "faiss_index_type": self.config.faiss_index_type if self.config.use_faiss else None}
+        n = st["total_queries"]
+        st["success_rate"] = st["successful_retrievals"] / n if n > 0 else 0.0
+        st["cache_hit_rate"] = st["cache_hits"] / n if n > 0 else 0.0
+        st["config"] = {"reference_count": self.config.reference_count,
+                        "similarity_threshold": self.config.similarity_threshold,
+                        "cache_size": self.config.cache_size, "enable_reranking": self.config.enable_reranking}
+        return st
+
+    def reset_statistics(self):
+        self.retrieval_stats = {"total_queries": 0, "successful_retrievals": 0, "cache_hits": 0,
+                                "average_retrieval_time": 0.0, "average_similarity": 0.0}
+
+    def clear_cache(self):
+        self.feature_cache.clear()
+
+    def update_config(self, new_config: RetrievalRefConfig):
+        self.config = new_config
+        self._rebuild_index()
 
 
 class MultiModalDefenseDetector:

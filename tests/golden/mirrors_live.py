@@ -494,6 +494,68 @@ def check_retrieval_reference(mods, rng):
                     assert all(np.array_equal(x["features"], y["features"]) for x, y in zip(a, b))
                     done += len(a)
     assert done > 0
+    # ---- the generator class itself: cache, statistics, batch entry, inserts, files (:173-236, 318-457, 542-600)
+    def strip(stats):
+        stats = dict(stats)
+        stats.pop("average_retrieval_time")
+        return stats
+
+    ids = {}
+    clip2 = type("Clip", (), {
+        "encode_text": lambda self, ts: torch.stack([torch.from_numpy(texts[t]) for t in ts]) * 3.0,   # un-normalised
+        "encode_image": lambda self, im: torch.from_numpy(ids[int(torch.as_tensor(im).reshape(-1)[0])])[None] * 2.0})()
+    with tempfile.TemporaryDirectory() as ta, tempfile.TemporaryDirectory() as tb:
+        for td in (ta, tb):
+            np.save(Path(td) / "features.npy", feats[:200])
+            (Path(td) / "metadata.json").write_text(json.dumps(meta[:200]))
+        cfg_a = RR.RetrievalConfig(reference_count=4, similarity_threshold=0.35, use_faiss=False, device="cpu", cache_size=12)
+        cfg_b = ODf.RetrievalRefConfig(reference_count=4, similarity_threshold=0.35, use_faiss=False, device="cpu", cache_size=12)
+        a, b = RR.RetrievalReferenceGenerator(clip2, ta, cfg_a), ODf.RetrievalReferenceGenerator(clip2, tb, cfg_b)
+        names = list(texts)
+
+        def same_refs(x, y, where):
+            assert [r["index"] for r in x] == [r["index"] for r in y], where
+            assert np.allclose([r["similarity"] for r in x], [r["similarity"] for r in y], rtol=0, atol=2e-6), where
+            assert [r["metadata"] for r in x] == [r["metadata"] for r in y], where
+            assert all(np.array_equal(r["features"], q["features"]) for r, q in zip(x, y)), where
+
+        for t in names[:8] + names[:3]:                               # the last three are cache hits
+            same_refs(a.retrieve_references(t), b.retrieve_references(t), t)
+        _same(strip(a.get_statistics()), strip(b.get_statistics()), "generator stats")
+        ra, rb = a.batch_retrieve_references(names[5:] + names[:2]), b.batch_retrieve_references(names[5:] + names[:2])
+        for x, y, t in zip(ra, rb, names[5:] + names[:2]):
+            same_refs(x, y, "batch " + t)
+        _same(strip(a.get_statistics()), strip(b.get_statistics()), "generator stats after the batch")
+        assert len(a.feature_cache) == len(b.feature_cache) == 12      # cache_size respected by both
+        # inserts: image tensors through the encoder, normalised, appended, index rebuilt, files rewritten
+        new_ids = list(range(900, 906))
+        for j in new_ids:
+            ids[j] = (feats[200 + j - 900] * 1.0).astype(np.float32)
+        ims = [torch.tensor([float(j)]) for j in new_ids]
+        caps = [f"caption {j}" for j in new_ids]
+        extra = [{"source": "test", "rank": j} for j in new_ids[:4]]
+        assert a.add_reference_images(ims, caps, extra) and b.add_reference_images(ims, caps, extra)
+        assert not a.add_reference_images(ims, caps[:2]) and not b.add_reference_images(ims, caps[:2])
+        assert np.allclose(a.reference_features, b.reference_features, rtol=0, atol=1e-7) and a.reference_metadata == b.reference_metadata
+        assert np.allclose(np.load(Path(ta) / "features.npy"), np.load(Path(tb) / "features.npy"), rtol=0, atol=1e-7)
+        assert json.loads((Path(ta) / "metadata.json").read_text()) == json.loads((Path(tb) / "metadata.json").read_text())
+        a.clear_cache(), b.clear_cache()
+        for t in names[:6]:
+            same_refs(a.retrieve_references(t), b.retrieve_references(t), "after insert " + t)
+        a.update_config(RR.RetrievalConfig(reference_count=2, similarity_threshold=0.1, use_faiss=False, device="cpu"))
+        b.update_config(ODf.RetrievalRefConfig(reference_count=2, similarity_threshold=0.1, use_faiss=False, device="cpu"))
+        a.clear_cache(), b.clear_cache()
+        for t in names[6:10]:
+            same_refs(a.retrieve_references(t), b.retrieve_references(t), "after update_config " + t)
+        a.reset_statistics(), b.reset_statistics()
+        _same(strip(a.get_statistics()), strip(b.get_statistics()), "generator stats after reset")
+        # each implementation opens the database the other one wrote; a missing database starts empty
+        a2, b2 = RR.RetrievalReferenceGenerator(clip2, tb, cfg_a), ODf.RetrievalReferenceGenerator(clip2, ta, cfg_b)
+        for t in names[:4]:
+            same_refs(a2.retrieve_references(t), b2.retrieve_references(t), "cross-loaded " + t)
+        e1, e2 = RR.RetrievalReferenceGenerator(clip2, ta + "/none", cfg_a), ODf.RetrievalReferenceGenerator(clip2, tb + "/none", cfg_b)
+        assert e1.retrieve_references(names[0]) == e2.retrieve_references(names[0]) == []
+        _same(strip(e1.get_statistics()), strip(e2.get_statistics()), "empty generator stats")
     return done
 
 

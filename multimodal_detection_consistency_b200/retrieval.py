@@ -39,14 +39,19 @@ def _to_numpy(x) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 @dataclass
 class IndexConfig:
-    """src/retrieval.py:22-37."""
-    index_type: str = "flat"
+    """src/retrieval.py:25-38, field for field.  Every index type is served by the exact search (the
+    approximate families would only approximate it)."""
+    index_type: str = "ivf"  # ivf, hnsw, flat
     dimension: int = 512
     n_clusters: int = 100
     n_links: int = 32
     ef_construction: int = 200
-    ef_search: int = 50
+    ef_search: int = 100
     use_gpu: bool = True
+
+    def __post_init__(self):
+        if self.index_type not in ("ivf", "hnsw", "flat"):
+            raise ValueError(f"Unsupported index type: {self.index_type}")
 
 
 @dataclass

@@ -360,6 +360,18 @@ def check_retriever(mods, rng):
             ri.add_items(img_f[50:])
         xa, xb = ri_a.search(txt_f[:6], 5), ri_b.search(txt_f[:6], 5)     # note: (indices, distances) here (:254)
         assert np.array_equal(xa[0], xb[0]) and np.allclose(xa[1], xb[1], rtol=0, atol=2e-6)
+        for mod in (R, OR):                                           # small dataclasses of the retrieval module
+            try:
+                mod.IndexConfig(index_type="pq")
+                raise AssertionError("IndexConfig accepted an unknown index type")
+            except ValueError:
+                pass
+        rr_a = R.RetrievalResult(indices=[4, 2, 9], similarities=[0.9, 0.5, 0.2], items=["a", "b", "c"], query_time=0.1)
+        rr_b = OR.RetrievalResult(indices=[4, 2, 9], similarities=[0.9, 0.5, 0.2], items=["a", "b", "c"], query_time=0.1)
+        _same(rr_a.to_dict(), rr_b.to_dict(), "RetrievalResult.to_dict")
+        _same(rr_a.filter_by_similarity(0.4).to_dict(), rr_b.filter_by_similarity(0.4).to_dict(), "filter_by_similarity")
+        assert rr_a.filter_by_similarity(0.4).items == rr_b.filter_by_similarity(0.4).items == ["a", "b"]
+        assert rr_a.get_top_k(2).items == rr_b.get_top_k(2).items and rr_a.get_top_k(7).indices == rr_b.get_top_k(7).indices
         ca, cb = R.ConsistencyCalculator(), OR.ConsistencyCalculator()
         _same(ca.compute_similarity_distribution(sa[0]), cb.compute_similarity_distribution(sb[0]), "distribution")
         assert abs(ca.compute_consistency_score(sa[0], sa[1]) - cb.compute_consistency_score(sb[0], sb[1])) < 1e-6
@@ -428,6 +440,13 @@ def check_detector(mods, rng):
     for x, y in zip(ba, bb):
         _same({k: v for k, v in x.items() if k != "detection_time"}, {k: v for k, v in y.items() if k != "detection_time"},
               "batch_detect", tol=3e-6)
+    for im, text, _ in samples[:5]:                                   # repeats are served from the cache by both
+        _same({k: v for k, v in a.detect_adversarial(im, text).items() if k != "detection_time"},
+              {k: v for k, v in b.detect_adversarial(im, text).items() if k != "detection_time"}, "cached", tol=3e-6)
+    sa, sb = a.get_stats(), b.get_stats()
+    sa["detection_stats"].pop("detection_time"), sb["detection_stats"].pop("detection_time")
+    _same(sa, sb, "detector stats with cache hits")
+    assert sa["detection_stats"]["cache_hits"] == 5
     ta, tb = a.compute_optimal_threshold(samples), b.compute_optimal_threshold(samples)
     assert abs(ta - tb) <= 3e-6, (ta, tb)
     a.update_threshold(ta), b.update_threshold(ta)
@@ -639,6 +658,41 @@ def check_defense_detector(mods, rng):
     return done
 
 
+# ------------------------------------------------------------------------------------------ config dataclasses
+def check_configs(mods, rng):
+    """Every config dataclass on the path: same field names, same order, same defaults as the reference's."""
+    import dataclasses
+    import importlib.util
+    from multimodal_detection_consistency_b200 import defenses as ODf, detector as ODt, ref_bank as OB, retrieval as OR
+    spec = importlib.util.spec_from_file_location("ref_retrieval_ref_cfg", MG.REF / "experiments" / "defenses" / "retrieval_ref.py")
+    RR = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RR)
+    pairs = [(mods["src.retrieval"].RetrievalConfig, OR.RetrievalConfig), (mods["src.retrieval"].IndexConfig, OR.IndexConfig),
+             (mods["src.ref_bank"].ReferenceBankConfig, OB.ReferenceBankConfig),
+             (mods["src.detector"].DetectorConfig, ODt.DetectorConfig),
+             (mods["experiments.defenses.detector"].DetectionConfig, ODf.DetectionConfig),
+             (RR.RetrievalConfig, ODf.RetrievalRefConfig)]
+    n = 0
+    for ref_cls, our_cls in pairs:
+        fa, fb = dataclasses.fields(ref_cls), dataclasses.fields(our_cls)
+        assert [f.name for f in fa] == [f.name for f in fb], (ref_cls.__name__, [f.name for f in fa], [f.name for f in fb])
+        a, b = ref_cls(), our_cls()
+        for f in fa:
+            assert getattr(a, f.name) == getattr(b, f.name), (ref_cls.__name__, f.name, getattr(a, f.name), getattr(b, f.name))
+            n += 1
+    ia = mods["src.ref_bank"].ReferenceItem(vector=np.arange(3.0), metadata={"a": 1}, timestamp=5.0)
+    ib = OB.ReferenceItem(vector=np.arange(3.0), metadata={"a": 1}, timestamp=5.0)
+    assert ia.to_dict() == ib.to_dict() and OB.ReferenceItem.from_dict(ia.to_dict()).to_dict() == ia.to_dict()
+    for mod in (mods["src.ref_bank"], OB):                           # validation errors of ReferenceBankConfig (:37-44)
+        for bad in (dict(clustering_method="spectral"), dict(update_strategy="mru")):
+            try:
+                mod.ReferenceBankConfig(**bad)
+                raise AssertionError(f"{mod.__name__} accepted {bad}")
+            except ValueError:
+                pass
+    return n
+
+
 def main():
     seeds = [int(s) for s in sys.argv[1:]] or [31, 32]
     mods = MG.import_reference()
@@ -648,7 +702,7 @@ def main():
             np.random.seed(seed)
             done = {f.__name__[6:]: f(mods, rng) for f in (check_ref_bank, check_consistency_checker, check_hubness,
                                                            check_evaluator, check_retriever, check_detector,
-                                                           check_retrieval_reference, check_defense_detector)}
+                                                           check_retrieval_reference, check_defense_detector, check_configs)}
             print(f"seed {seed}: " + ", ".join(f"{k} {v}" for k, v in done.items()))
     print("mirrors live check ok")
 

@@ -29,6 +29,7 @@ _LAZY = {
     "compute_hubness_loss": "hubness",
     "TVCScorer": "pipeline",
     "RetrievalEvaluator": "metrics", "RetrievalMetrics": "metrics", "SimilarityCalculator": "metrics",
+    "SimilarityMetrics": "metrics",
     "MicroBatcher": "batching",
 }
 

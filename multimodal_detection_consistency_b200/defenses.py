@@ -483,6 +483,19 @@ class MultiModalDefenseDetector:
                                                       adaptive_threshold=self.config.adaptive_threshold,
                                                       voting_strategy=self.config.voting_strategy)
 
+    def update_config(self, new_config: DetectionConfig):
+        """experiments/defenses/detector.py:353-357."""
+        self.config = new_config
+
+    def get_statistics(self) -> Dict[str, Any]:
+        """experiments/defenses/detector.py:359-375 (same keys)."""
+        return {"config": self.config.__dict__,
+                "components": {"text_variant_generator": self.text_variant_generator is not None,
+                               "retrieval_generator": self.retrieval_generator is not None,
+                               "generative_generator": self.generative_generator is not None,
+                               "consistency_checker": self.consistency_checker is not None},
+                "consistency_checker_stats": self.consistency_checker.get_statistics()}
+
     # -- embedding entry: everything after the encoders, one launch ------------------------------
     def detect_embeddings(self, image_emb, text_emb, variant_emb=None, generative_emb=None, generative_counts=None,
                           return_scores: bool = False):

@@ -94,6 +94,21 @@ class RetrievalEvaluator:
         return RetrievalEvaluator.from_topk(idx, relevant, k_values, ctx=gallery.ctx)
 
 
+@dataclass
+class SimilarityMetrics:
+    """src/utils/metrics.py:88-105."""
+    cosine_similarity: float = 0.0
+    euclidean_distance: float = 0.0
+    manhattan_distance: float = 0.0
+    pearson_correlation: float = 0.0
+    spearman_correlation: float = 0.0
+
+    def to_dict(self) -> Dict[str, float]:
+        return {"cosine_similarity": self.cosine_similarity, "euclidean_distance": self.euclidean_distance,
+                "manhattan_distance": self.manhattan_distance, "pearson_correlation": self.pearson_correlation,
+                "spearman_correlation": self.spearman_correlation}
+
+
 def _host(x) -> np.ndarray:
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()
@@ -113,6 +128,41 @@ class SimilarityCalculator:
         if na == 0 or nb == 0:
             return 0.0
         return float(np.dot(a, b) / (na * nb))
+
+    # the remaining scalar measures of the reference class (:166-268): two vectors in, one float out - host
+    @staticmethod
+    def euclidean_distance(x, y) -> float:
+        return float(np.linalg.norm(_host(x).ravel() - _host(y).ravel()))
+
+    @staticmethod
+    def manhattan_distance(x, y) -> float:
+        return float(np.sum(np.abs(_host(x).ravel() - _host(y).ravel())))
+
+    @staticmethod
+    def pearson_correlation(x, y) -> float:
+        try:
+            from scipy.stats import pearsonr
+            corr = pearsonr(_host(x).ravel(), _host(y).ravel())[0]
+            return float(corr) if not np.isnan(corr) else 0.0
+        except Exception:  # noqa: BLE001
+            return 0.0
+
+    @staticmethod
+    def spearman_correlation(x, y) -> float:
+        try:
+            from scipy.stats import spearmanr
+            corr = spearmanr(_host(x).ravel(), _host(y).ravel())[0]
+            return float(corr) if not np.isnan(corr) else 0.0
+        except Exception:  # noqa: BLE001
+            return 0.0
+
+    @classmethod
+    def compute_all_similarities(cls, x, y) -> "SimilarityMetrics":
+        return SimilarityMetrics(cosine_similarity=cls.cosine_similarity(x, y),
+                                 euclidean_distance=cls.euclidean_distance(x, y),
+                                 manhattan_distance=cls.manhattan_distance(x, y),
+                                 pearson_correlation=cls.pearson_correlation(x, y),
+                                 spearman_correlation=cls.spearman_correlation(x, y))
 
     @staticmethod
     def batch_cosine_similarity(x, y) -> np.ndarray:

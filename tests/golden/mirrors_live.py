@@ -236,6 +236,12 @@ def check_evaluator(mods, rng):
         a, b = M.SimilarityCalculator.cosine_similarity(x[i], y[i]), OM.SimilarityCalculator.cosine_similarity(x[i], y[i])
         assert abs(a - b) <= 5e-7, (i, a, b)
     assert OM.SimilarityCalculator.cosine_similarity(torch.from_numpy(x[2]), list(y[0])) == 0.0
+    _same(M.SimilarityCalculator.compute_all_similarities(x[4], y[4]).to_dict(),
+          OM.SimilarityCalculator.compute_all_similarities(x[4], y[4]).to_dict(), "compute_all_similarities", tol=1e-5)
+    _same(M.SimilarityCalculator.compute_all_similarities(torch.from_numpy(x[5]), torch.from_numpy(y[5])).to_dict(),
+          OM.SimilarityCalculator.compute_all_similarities(torch.from_numpy(x[5]), torch.from_numpy(y[5])).to_dict(),
+          "compute_all_similarities (torch)", tol=1e-5)
+    assert M.SimilarityMetrics().to_dict() == OM.SimilarityMetrics().to_dict()
     want_m = M.SimilarityCalculator.batch_cosine_similarity(x[3:], y)
     assert np.allclose(OM.SimilarityCalculator.batch_cosine_similarity(x[3:], y), want_m, rtol=0, atol=2e-6)
     assert np.allclose(OM.SimilarityCalculator.batch_cosine_similarity(torch.from_numpy(x[3:]), torch.from_numpy(y)),
@@ -653,6 +659,11 @@ def check_defense_detector(mods, rng):
             done += 1
         kept = {int(x) for x in ref._generate_retrieval_references(samples[0][1], [samples[0][1]] + variants.generate_variants(samples[0][1]))}
         assert len(kept & {10, 11, 12}) == 1                                      # one of the (near-)duplicate rows survives
+        sa, sb = ref.get_statistics(), ours.get_statistics()
+        assert sorted(sa) == sorted(sb) and sa["components"] == sb["components"] and sorted(sa["config"]) == sorted(sb["config"])
+        _same(sa["consistency_checker_stats"], sb["consistency_checker_stats"], "defense detector checker stats", tol=3e-6)
+        ref.update_config(ED.DetectionConfig(retrieval_top_k=4)), ours.update_config(ODf.DetectionConfig(retrieval_top_k=4))
+        assert ref.config.retrieval_top_k == ours.config.retrieval_top_k == 4
         ba = ours.batch_detect([s[0] for s in samples[:6]], [s[1] for s in samples[:6]])
         assert len(ba) == 6 and all(sorted(r) == ["confidence", "consistency_score", "is_adversarial"] for r in ba)
     return done
@@ -680,6 +691,31 @@ def check_configs(mods, rng):
         for f in fa:
             assert getattr(a, f.name) == getattr(b, f.name), (ref_cls.__name__, f.name, getattr(a, f.name), getattr(b, f.name))
             n += 1
+    # public methods: everything callable the reference classes expose exists on the mirror.  Left out on
+    # purpose: the two data-loading helpers of the retrieval-reference generator (image files -> torchvision
+    # transform -> encoder: upstream of the path)
+    from multimodal_detection_consistency_b200 import metrics as OM
+    allowed = {"RetrievalReferenceGenerator": {"build_reference_database", "load_reference_images"}}
+    classes = [(mods["src.retrieval"], OR, ["MultiModalRetriever", "FaissIndexManager", "RetrievalIndex", "ConsistencyCalculator",
+                                             "RetrievalResult"]),
+               (mods["src.ref_bank"], OB, ["ReferenceBank", "ReferenceItem"]),
+               (mods["src.detector"], ODt, ["AdversarialDetector"]),
+               (mods["experiments.defenses.consistency_checker"], ODf, ["ConsistencyChecker"]),
+               (mods["experiments.defenses.detector"], ODf, ["MultiModalDefenseDetector"]),
+               (RR, ODf, ["RetrievalReferenceGenerator"]),
+               (mods["src.utils.metrics"], OM, ["RetrievalEvaluator", "SimilarityCalculator", "RetrievalMetrics", "SimilarityMetrics"])]
+    for ref_mod, our_mod, names in classes:
+        for name in names:
+            ra, rb = getattr(ref_mod, name), getattr(our_mod, name)
+            pub = lambda c: {m for m in dir(c) if not m.startswith("_") and callable(getattr(c, m))}  # noqa: E731
+            missing = pub(ra) - pub(rb) - allowed.get(name, set())
+            assert not missing, (name, sorted(missing))
+            n += len(pub(ra))
+    for ref_mod, our_mod in ((mods["src.retrieval"], OR), (mods["src.ref_bank"], OB), (mods["src.detector"], ODt)):
+        import types as _ty
+        funcs = {k for k, v in vars(ref_mod).items() if isinstance(v, _ty.FunctionType) and v.__module__ == ref_mod.__name__
+                 and not k.startswith("_")}
+        assert funcs <= set(vars(our_mod)), (ref_mod.__name__, sorted(funcs - set(vars(our_mod))))
     ia = mods["src.ref_bank"].ReferenceItem(vector=np.arange(3.0), metadata={"a": 1}, timestamp=5.0)
     ib = OB.ReferenceItem(vector=np.arange(3.0), metadata={"a": 1}, timestamp=5.0)
     assert ia.to_dict() == ib.to_dict() and OB.ReferenceItem.from_dict(ia.to_dict()).to_dict() == ia.to_dict()

@@ -711,6 +711,18 @@ def check_configs(mods, rng):
             missing = pub(ra) - pub(rb) - allowed.get(name, set())
             assert not missing, (name, sorted(missing))
             n += len(pub(ra))
+            # ... with the reference's parameter names, order and defaults (the mirror may append parameters)
+            import inspect
+            for meth in ["__init__"] + sorted(pub(ra) & pub(rb)):
+                try:
+                    pa = list(inspect.signature(getattr(ra, meth)).parameters.values())
+                    pb = list(inspect.signature(getattr(rb, meth)).parameters.values())
+                except (TypeError, ValueError):
+                    continue
+                assert [q.name for q in pb[:len(pa)]] == [q.name for q in pa], (name, meth, pa, pb)
+                for x, y in zip(pa, pb):
+                    if x.default is not inspect.Parameter.empty and x.default is not None:
+                        assert x.default == y.default, (name, meth, x.name, x.default, y.default)
     for ref_mod, our_mod in ((mods["src.retrieval"], OR), (mods["src.ref_bank"], OB), (mods["src.detector"], ODt)):
         import types as _ty
         funcs = {k for k, v in vars(ref_mod).items() if isinstance(v, _ty.FunctionType) and v.__module__ == ref_mod.__name__

@@ -446,6 +446,23 @@ def check_detector(mods, rng):
     for x, y in zip(ba, bb):
         _same({k: v for k, v in x.items() if k != "detection_time"}, {k: v for k, v in y.items() if k != "detection_time"},
               "batch_detect", tol=3e-6)
+    # collaborators that come back empty: both record the method with score 0.0 and an error entry (:455-458, :525-527)
+    empty_aug = _t.SimpleNamespace(generate_variants=lambda t: [] if index_of[t] % 2 else [f"{t} ~v0"])
+    empty_gen = _t.SimpleNamespace(generate_reference_images=lambda text, num_images=G: {
+        "images": [] if index_of[text] % 3 == 0 else [image_of(500 + G * index_of[text])], "generation_time": 0.0})
+    for agg in ("weighted_mean", "max"):
+        ea = D.AdversarialDetector(D.DetectorConfig(score_aggregation=agg, enable_cache=False))
+        eb = OD.AdversarialDetector(OD.DetectorConfig(score_aggregation=agg, enable_cache=False))
+        for det in (ea, eb):
+            det.clip_model, det.text_augmenter, det.sd_generator = clip, empty_aug, empty_gen
+        for im, text, _ in samples[:12]:
+            ra, rb = ea.detect_adversarial(im, text), eb.detect_adversarial(im, text)
+            _same(ra["detection_scores"], rb["detection_scores"], f"empty collaborators {agg} {text}", tol=3e-6)
+            assert abs(ra["aggregated_score"] - rb["aggregated_score"]) <= 3e-6, (agg, text)
+            if abs(ra["aggregated_score"] - 0.5) > 1e-5:
+                assert ra["is_adversarial"] == rb["is_adversarial"]
+            for m in ("text_variants", "sd_reference"):
+                assert ("error" in ra["detection_details"][m]) == ("error" in rb["detection_details"][m]), (agg, text, m)
     for im, text, _ in samples[:5]:                                   # repeats are served from the cache by both
         _same({k: v for k, v in a.detect_adversarial(im, text).items() if k != "detection_time"},
               {k: v for k, v in b.detect_adversarial(im, text).items() if k != "detection_time"}, "cached", tol=3e-6)

@@ -210,9 +210,12 @@ def run_cpu_sample(torch, args, g_host, b_host, img, txt, var, sample_q, reps=1)
 
 
 def auto_sample(torch, args, g_host, b_host, img, txt, var):
-    """Probe with 8 queries, then size the sample for ~12 s of CPU work."""
+    """Size the CPU sample for ~15 s of work (the contract asks for 10-30 s).  Two probes: 8 queries are
+    dominated by per-chunk overheads and under-estimate the rate, so a second probe at ~1.5 s refines it."""
     qps, _, _, _ = run_cpu_sample(torch, args, g_host, b_host, img, txt, var, 8)
-    return int(max(16, min(img.shape[0], qps * 12.0)))
+    second = int(max(16, min(img.shape[0], qps * 1.5)))
+    qps, _, _, _ = run_cpu_sample(torch, args, g_host, b_host, img, txt, var, second)
+    return int(max(16, min(img.shape[0], qps * 15.0)))
 
 
 # ----------------------------------------------------------------------------------------------

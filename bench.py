@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate (sampled fp32 check + digest)")
+    ap.add_argument("--parity-rows", type=int, default=4096, help="query rows the parity gate re-computes in fp32")
     ap.add_argument("--host-chunks", type=int, default=0, help="pieces the end-to-end batch is pipelined in (0 = default)")
     ap.add_argument("--phases", action="store_true", help="also print per-phase CUDA-event times (stderr)")
     return ap.parse_args()
@@ -166,6 +168,129 @@ def step_flops(args):
     return 2.0 * args.queries * args.variants * (args.gallery + args.bank) * args.dim
 
 
+
+# ----------------------------------------------------------------------------------------------
+# Parity gate (outside the timed region, every N): a sampled fp32 torch matmul+topk check of the search
+# results of the bench workload itself, and a 64-bit digest of the step's integer outputs that must
+# come out the same at N = 1, 2, 4, 8 (north_star: "bit-exact top-k and hubness results").
+def _s64(u: int) -> int:
+    u &= (1 << 64) - 1
+    return u - (1 << 64) if u >= (1 << 63) else u
+
+
+def digest64(torch, values, first_pos: int, tag: int):
+    """Order-independent 64-bit digest of an integer array slice: sum over elements of mix(global flat
+    position, value) mod 2^64 (int64 arithmetic wraps), so per-rank partial digests of disjoint slices
+    ADD UP to the digest of the whole array whatever the sharding.  Returns a 0-dim int64 tensor."""
+    v = values.reshape(-1).to(torch.int64)
+    pos = torch.arange(first_pos, first_pos + v.numel(), dtype=torch.int64, device=v.device)
+    h = (pos + 1 + (tag << 48)) * _s64(0x9E3779B97F4A7C15)
+    h = h ^ (v * _s64(0xC2B2AE3D27D4EB4F))
+    h = h ^ (h >> 29)
+    h = h * _s64(0x165667B19E3779F9)
+    h = h ^ (h >> 32)
+    return h.sum()
+
+
+def fp32_topk_reference(torch, rows, mat, k, chunk=262144):
+    """Plain fp32 torch matmul + topk with a running merge (no TF32): (sims [r, k], idx [r, k])."""
+    best_s = torch.full((rows.shape[0], k), -float("inf"), device=rows.device)
+    best_i = torch.full((rows.shape[0], k), -1, dtype=torch.int64, device=rows.device)
+    for c0 in range(0, mat.shape[0], chunk):
+        s = rows @ mat[c0:c0 + chunk].T
+        cs, ci = torch.topk(s, min(k, s.shape[1]), dim=1)
+        ms = torch.cat([best_s, cs], 1)
+        mi = torch.cat([best_i, ci + c0], 1)
+        o = torch.topk(ms, k, dim=1)
+        best_s, best_i = o.values, torch.gather(mi, 1, o.indices)
+    return best_s, best_i
+
+
+def gather_rows_all_ranks(torch, dist, shard, total, world):
+    """All-gather of a row-sharded fp32 matrix (ceil(total / world) rows per rank, last shards padded)."""
+    if world == 1:
+        return shard
+    per = -(-total // world)
+    piece = torch.zeros((per, shard.shape[1]), dtype=shard.dtype, device=shard.device)
+    piece[: shard.shape[0]] = shard
+    full = torch.empty((world * per, shard.shape[1]), dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(full, piece)
+    return full[:total]
+
+
+def parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world, rank, device, sample_rows=4096):
+    """One extra (untimed) pass of the bench batch; see the section comment.  Returns a dict on rank 0."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    scorer.reset_hubness()
+    out = scorer.score_batch(img, txt, var)
+    lo, hi = out["slice"]
+    v, k, d = args.variants, args.topk, args.dim
+    # ---- (ii) digest of the integer outputs -----------------------------------------------------
+    parts = [digest64(torch, out["topk_idx"], lo * v * k, 1), digest64(torch, out["flags"], lo, 3)]
+    if "bank_idx" in out:
+        parts.append(digest64(torch, out["bank_idx"], lo * v * k, 2))
+    dg = torch.stack(parts).sum().reshape(1)
+    sims_bits = [out["topk_sim"].contiguous().view(torch.int32)]
+    if "bank_sim" in out:
+        sims_bits.append(out["bank_sim"].contiguous().view(torch.int32))
+    dg_sims = torch.stack([digest64(torch, t, lo * v * k, 5 + i) for i, t in enumerate(sims_bits)]).sum().reshape(1)
+    dg_scores = digest64(torch, out["scores"].contiguous().view(torch.int32), lo * out["scores"].shape[1], 7).reshape(1)
+    hist = scorer.k_occurrence                       # all-reduced: identical on every rank
+    dg_hist = digest64(torch, hist, 0, 4).reshape(1)
+    # the histogram against torch.bincount of the gathered top-k (independent of kernel c)
+    local_bins = torch.bincount(out["topk_idx"].reshape(-1).clamp(min=0), minlength=args.gallery)[: args.gallery]
+    if (out["topk_idx"] < 0).any():
+        local_bins[0] -= (out["topk_idx"] < 0).sum()
+    # ---- (i) sampled fp32 check -------------------------------------------------------------------
+    g_full = gather_rows_all_ranks(torch, dist, g_rows, args.gallery, world)
+    rows_here = (hi - lo) * v
+    want = -(-sample_rows // world)
+    pick = torch.linspace(0, max(rows_here - 1, 0), steps=min(want, rows_here), device=device).round().long().unique()
+    q_rows = var[lo:hi].reshape(rows_here, d)[pick].float()
+    stats = torch.zeros(6, dtype=torch.float64, device=device)   # rows, idx mismatches, out of band, max sim err, slots, missed true
+    for name, full, total in (("topk", g_full, args.gallery), ("bank", None, args.bank)):
+        if name == "bank":
+            if "bank_idx" not in out:
+                continue
+            full = gather_rows_all_ranks(torch, dist, b_rows, args.bank, world)
+        rs, ri = fp32_topk_reference(torch, q_rows, full, k)
+        os_ = out[name + "_sim"].reshape(rows_here, k)[pick]
+        oi = out[name + "_idx"].reshape(rows_here, k)[pick]
+        err = (os_ - rs).abs()
+        mism = oi != ri
+        stats[1] += mism.sum()
+        stats[2] += (mism & (err > 1e-3)).sum()
+        stats[3] = torch.maximum(stats[3], err.max().double())
+        stats[4] += mism.numel()
+        # members of the fp32 top-k that our list does not hold at all (set difference, any rank)
+        stats[5] += (~(ri[:, :, None] == oi[:, None, :]).any(2)).sum()
+        del full
+    stats[0] = pick.numel()
+    if world > 1:
+        for t in (dg, dg_sims, dg_scores):
+            dist.all_reduce(t)
+        dist.all_reduce(local_bins)
+        mx = stats[3:4].clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats)
+        stats[3] = mx[0]
+    hist_ok = bool(torch.equal(local_bins.to(hist.dtype), hist))
+    scorer.reset_hubness()
+    if rank != 0:
+        return None
+    hexd = lambda t: f"{int(t.item()) & ((1 << 64) - 1):016x}"   # noqa: E731
+    st = stats.tolist()
+    return dict(rows_checked=int(st[0]), slots_checked=int(st[4]), idx_mismatch=int(st[1]), idx_out_of_band=int(st[2]),
+                true_topk_members_missed=int(st[5]), max_sim_err=st[3], sim_tol=2e-3, band=1e-3,
+                hist_equals_bincount=hist_ok, digest=hexd(dg + dg_hist), digest_topk_bank_flags=hexd(dg),
+                digest_hist=hexd(dg_hist), digest_sims_bits=hexd(dg_sims), digest_scores_bits=hexd(dg_scores),
+                ok=bool(st[2] == 0 and st[3] <= 2e-3 and hist_ok),
+                what="one untimed pass of the bench batch: sampled rows of every rank's slice vs fp32 torch matmul+topk over "
+                     "the all-gathered gallery and bank (idx exact or similarity within the band); digest = position-keyed "
+                     "64-bit sum over topk_idx, bank_idx, flags and the all-reduced k-occurrence histogram (must be identical "
+                     "at every N)")
+
+
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_step(torch, np, O, g_host, b_host, img, txt, var, k, params=None):
     """The reference's CPU path for one batch (the oracle port): exact fp32 inner-product top-k
@@ -247,15 +372,16 @@ def main():
     glo, ghi = shard_bounds(args.gallery, world, rank)
     blo, bhi = shard_bounds(args.bank, world, rank)
     g_rows, centers = synth_device(torch, args, device, args.gallery, 42, glo, ghi)
-    b_rows, _ = synth_device(torch, args, device, args.bank, 43, blo, bhi, centers)
-    scorer = TVCScorer(g_rows, b_rows, k=args.topk, total_gallery_rows=args.gallery, total_bank_rows=args.bank,
-                       device=device)
+    b_rows = synth_device(torch, args, device, args.bank, 43, blo, bhi, centers)[0] if args.bank > 0 else None
+    scorer = TVCScorer(g_rows, b_rows, k=args.topk, total_gallery_rows=args.gallery,
+                       total_bank_rows=args.bank if args.bank > 0 else None, device=device)
     if args.host_chunks:
         scorer.host_chunks = args.host_chunks
     g_host = b_host = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        g_host, b_host = g_rows.cpu(), b_rows.cpu()
-    del g_rows, b_rows
+        g_host, b_host = g_rows.cpu(), (b_rows.cpu() if b_rows is not None else None)
+    if args.no_parity:
+        del g_rows, b_rows
     img, txt, var = synth_queries(torch, args, device, centers, 123)
     torch.cuda.synchronize()
 
@@ -323,6 +449,13 @@ def main():
                    d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
                    api="TVCScorer.score_batch(pinned host tensors, to_host=True)")
 
+    # ---- parity gate (untimed): sampled fp32 check + output digest, every N ----------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world, rank, device,
+                             sample_rows=args.parity_rows)
+        del g_rows, b_rows
+
     scorer.close()
     if rank != 0:
         if world > 1:
@@ -379,6 +512,7 @@ def main():
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (gallery 1.5 GB bf16 streamed every step)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity,
         "tflops": step_flops(args) * args.steps / (total_ms / 1e3) / 1e12,
     }
     print(json.dumps(line))

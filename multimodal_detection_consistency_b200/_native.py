@@ -587,6 +587,12 @@ class Gallery:
         self.ctx.check(self.ctx.lib.tvc_gallery_append(self.handle, _ptr(rows), _dtype_code(rows),
                                                        int(rows.shape[0]), _stream_of(rows)))
 
+    def _check_dim(self, q):
+        """The reference raises on a query of the wrong width (np.dot / the FAISS assert); so do we, before a
+        pointer with the wrong row stride reaches the library."""
+        if int(q.shape[-1]) != self.dim:
+            raise ValueError(f"query dimension {int(q.shape[-1])} != gallery dimension {self.dim}")
+
     def truncate(self, n: int):
         self.ctx.check(self.ctx.lib.tvc_gallery_truncate(self.handle, int(n)))
 
@@ -609,15 +615,30 @@ class Gallery:
 
     def search(self, queries, k: int, threshold: float = -math.inf, *, normalize_queries: bool = False,
                skip_self: bool = False):
-        """Exact top-k.  numpy in -> numpy out (host round trip); torch cuda in -> torch cuda out."""
+        """Top-k by inner product, ordered (similarity desc, index asc).  numpy in -> numpy out (host round
+        trip); torch cuda in -> torch cuda out.
+
+        How exact: the candidates of a row are its KP best gallery rows by the bf16 tensor-core score
+        (KP = 16 / 32 / 64 for k <= 10 / 26 / 56), and those are re-scored from the fp32 masters, so the
+        returned similarities are fp32 and the order among the candidates is the fp32 order.  A true top-k
+        row can only be missed if bf16 rounding (~1e-3 for unit rows) pushes it below bf16 rank KP, i.e. only
+        among rows whose similarities lie within ~1e-3 of the k-th - the band north_star allows index
+        disagreement in.  With keep_master=False (TVC_GALLERY_NO_MASTER) the scores are the bf16 ones.
+        k > MAX_K (56) raises TvcError(TVC_ERR_UNSUPPORTED)."""
         q = _rows(queries)
         if q.ndim == 1:
             q = q.reshape(1, -1)
+        self._check_dim(q)
         lead = None
         if q.ndim > 2:
             lead = tuple(q.shape[:-1])
             q = q.reshape(-1, q.shape[-1])
         m = int(q.shape[0])
+        if int(k) > MAX_K:
+            sims, idx = self._search_wide(q, int(k), float(threshold), normalize_queries, skip_self)
+            if lead is not None:
+                sims, idx = sims.reshape(*lead, k), idx.reshape(*lead, k)
+            return sims, idx
         flags = (SEARCH_NORMALIZE_Q if normalize_queries else 0) | (SEARCH_SKIP_SELF if skip_self else 0)
         if _is_torch(q) and q.is_cuda:
             import torch
@@ -630,13 +651,55 @@ class Gallery:
         else:
             sims = np.empty((m, k), np.float32)
             idx = np.empty((m, k), np.int64)
-        self.ctx.check(self.ctx.lib.tvc_search(self.ctx.handle, self.handle, _ptr(q), _dtype_code(q), m, self.dim,
+        self.ctx.check(self.ctx.lib.tvc_search(self.ctx.handle, self.handle, _ptr(q), _dtype_code(q), m, int(q.shape[1]),
                                                int(k), float(threshold), flags, _ptr(sims), _ptr(idx),
                                                _stream_of(q)))
         if lead is not None:
             sims = sims.reshape(*lead, k)
             idx = idx.reshape(*lead, k)
         return sims, idx
+
+    def _search_wide(self, q, k: int, threshold: float, normalize_queries: bool, skip_self: bool):
+        """k > MAX_K (FAISS and the reference accept any k; the in-register epilogue stops at 56): the dense
+        similarity tile of a chunk of rows (tvc_similarity_matrix, the same tensor-core GEMM), the k + 32 best per
+        row by that bf16 score, re-scored from the fp32 masters like tvc_search does, ordered (similarity desc,
+        index asc), `>= threshold`, unused slots (-inf, -1).  Rare path: device selection and sort are torch's."""
+        import torch
+        host_np = not _is_torch(q)
+        dev = torch.device("cuda", self.ctx.device)
+        qd = (torch.as_tensor(q) if host_np else q).to(dev, torch.float32)
+        if normalize_queries:
+            qd = torch.nn.functional.normalize(qd, dim=1)
+        m, n = int(qd.shape[0]), len(self)
+        out_s = torch.full((m, k), -math.inf, dtype=torch.float32, device=dev)
+        out_i = torch.full((m, k), -1, dtype=torch.int64, device=dev)
+        kk = min(n, k + 32 + (1 if skip_self else 0))
+        step = max(1, min(m, (1 << 28) // max(n, 1)))           # <= 1 GiB of fp32 scores per chunk
+        for r0 in range(0, m if n > 0 else 0, step):
+            qc = qd[r0:r0 + step]
+            cand = torch.topk(self.similarity_matrix(qc), kk, dim=1).indices          # local row numbers
+            if self.flags & GALLERY_NO_MASTER:
+                sc = torch.gather(self.similarity_matrix(qc), 1, cand)
+            else:
+                rows = self.get_rows(cand.reshape(-1)).view(qc.shape[0], kk, self.dim)
+                sc = torch.einsum("mkd,md->mk", rows, qc)
+            gi = cand + self.global_row_offset
+            if skip_self:
+                me = torch.arange(r0, r0 + qc.shape[0], device=dev)[:, None]
+                sc = torch.where(gi == me, torch.full_like(sc, -math.inf), sc)
+            order = torch.sort(gi, dim=1, stable=True).indices                         # index asc ...
+            sc, gi = torch.gather(sc, 1, order), torch.gather(gi, 1, order)
+            order = torch.sort(sc, dim=1, descending=True, stable=True).indices        # ... then similarity desc
+            sc, gi = torch.gather(sc, 1, order)[:, :k], torch.gather(gi, 1, order)[:, :k]
+            keep = (sc >= threshold) & torch.isfinite(sc)
+            w = sc.shape[1]
+            out_s[r0:r0 + qc.shape[0], :w] = torch.where(keep, sc, torch.full_like(sc, -math.inf))
+            out_i[r0:r0 + qc.shape[0], :w] = torch.where(keep, gi, torch.full_like(gi, -1))
+        if host_np:
+            return out_s.cpu().numpy(), out_i.cpu().numpy()
+        if not q.is_cuda:
+            return out_s.cpu(), out_i.cpu()
+        return out_s, out_i
 
     def search_candidates(self, queries, k: int, scatter: Optional[Scatter] = None, *, normalize_queries: bool = False,
                           skip_self: bool = False):
@@ -654,6 +717,7 @@ class Gallery:
             q = _rows(queries)
             if q.ndim > 2:
                 q = q.reshape(-1, q.shape[-1])
+            self._check_dim(q)
             qp, m, code, stream, dev = _ptr(q), int(q.shape[0]), _dtype_code(q), _stream_of(q), q.device
         val = idx = None
         if scatter is None:
@@ -667,6 +731,9 @@ class Gallery:
 
     def similarity_matrix(self, queries, *, normalize_queries: bool = False):
         q = _rows(queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        self._check_dim(q)
         m, n = int(q.shape[0]), len(self)
         if _is_torch(q) and q.is_cuda:
             import torch
@@ -674,7 +741,7 @@ class Gallery:
         else:
             out = np.empty((m, n), np.float32)
         self.ctx.check(self.ctx.lib.tvc_similarity_matrix(
-            self.ctx.handle, self.handle, _ptr(q), _dtype_code(q), m, self.dim,
+            self.ctx.handle, self.handle, _ptr(q), _dtype_code(q), m, int(q.shape[1]),
             SEARCH_NORMALIZE_Q if normalize_queries else 0, _ptr(out), _stream_of(q)))
         return out
 

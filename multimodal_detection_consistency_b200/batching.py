@@ -21,12 +21,13 @@ from typing import Any, Callable, Hashable, List, Optional, Sequence
 
 
 class _Round:
-    __slots__ = ("items", "results", "error", "done", "closed")
+    __slots__ = ("items", "results", "error", "errors", "done", "closed")
 
     def __init__(self):
         self.items: List[Any] = []
         self.results: Optional[Sequence[Any]] = None
         self.error: Optional[BaseException] = None
+        self.errors: Optional[List[Optional[BaseException]]] = None   # per item, after a failed round was re-run
         self.done = threading.Event()
         self.closed = False
 
@@ -53,6 +54,7 @@ class MicroBatcher:
         self._inside = 0                # callers currently inside submit()
         self.rounds = 0                 # statistics: batched calls made / items served
         self.items = 0
+        self.isolated = 0               # rounds that failed as a batch and were re-run item by item
 
     def submit(self, item: Any, key: Hashable = None) -> Any:
         now = time.monotonic()
@@ -91,8 +93,26 @@ class MicroBatcher:
                     if len(out) != len(rnd.items):
                         raise RuntimeError(f"batch function returned {len(out)} results for {len(rnd.items)} items")
                     rnd.results = out
-                except BaseException as e:  # noqa: BLE001 - handed to every caller of the round
-                    rnd.error = e
+                except BaseException as e:  # noqa: BLE001
+                    if len(rnd.items) == 1:
+                        rnd.error = e
+                    else:
+                        # failure isolation (the reference fails per sample, src/detector.py:428-439,
+                        # src/retrieval.py:574-576): one bad item must not fail the unrelated callers that
+                        # happened to share its round, so the leader re-runs the items one at a time and
+                        # only the offending ones get their exception
+                        rnd.results, rnd.errors = [None] * len(rnd.items), [None] * len(rnd.items)
+                        for i, it in enumerate(rnd.items):
+                            try:
+                                one = self.batch_fn(key, [it])
+                                if len(one) != 1:
+                                    raise RuntimeError(f"batch function returned {len(one)} results for 1 item")
+                                rnd.results[i] = one[0]
+                            except BaseException as e1:  # noqa: BLE001
+                                rnd.errors[i] = e1
+                        with self._lock:
+                            self.rounds += len(rnd.items)
+                            self.isolated += 1
                 finally:
                     with self._lock:
                         self.rounds += 1
@@ -102,6 +122,8 @@ class MicroBatcher:
                 rnd.done.wait()
             if rnd.error is not None:
                 raise rnd.error
+            if rnd.errors is not None and rnd.errors[pos] is not None:
+                raise rnd.errors[pos]
             return rnd.results[pos]
         finally:
             with self._lock:

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -22,14 +23,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct tvc_ctx {
   int device = 0;
   int sm_count = 148;
+  // Locking (SURVEY §8b threading row: concurrent tvc_search on an immutable gallery): `mu` is held only for
+  // short bookkeeping - the workspace map, the internal stream / event pools, the timing lists, the options,
+  // a gallery's lazily built tensor maps.  A compute call holds the mutex of ITS stream's workspace for its
+  // whole duration (enqueue order on a stream = lock order), never `mu`: calls on different streams overlap,
+  // including the blocking synchronisation of the host-buffer path.
   std::mutex mu;
-  std::string err;
   EncodeTiledFn encode = nullptr;
   struct Ws {
     void* ptr = nullptr;
     size_t bytes = 0;
+    std::mutex mu;
   };
-  std::map<cudaStream_t, Ws> ws;
+  std::map<cudaStream_t, std::unique_ptr<Ws>> ws;
+  std::vector<cudaStream_t> idle_streams;   // context-owned non-blocking streams for blocking host-buffer calls
+  std::vector<cudaStream_t> own_streams;
+  std::vector<cudaEvent_t> idle_events;
   int64_t debug_flags = 0;
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
@@ -71,8 +80,11 @@ struct DeviceGuard {
   }
 };
 
-int fail(tvc_ctx* ctx, int status, const std::string& msg) {
-  if (ctx) ctx->err = msg;
+// tvc_last_error is per calling thread (like errno): concurrent calls cannot overwrite each other's message
+thread_local std::string t_last_error;
+
+int fail(tvc_ctx*, int status, const std::string& msg) {
+  t_last_error = msg;
   return status;
 }
 int fail_cuda(tvc_ctx* ctx, cudaError_t e, const char* where) {
@@ -99,9 +111,83 @@ bool is_device_ptr(const void* p) {
 size_t elem_size(int dtype) { return dtype == TVC_F32 ? 4 : 2; }
 size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
+// One compute call: the device guard, the stream the work is enqueued on and exclusive use of that stream's
+// grow-only workspace.  Calls with device pointers run on the caller's stream (asynchronous, stream-ordered).
+// A call with a host buffer blocks until its results are back, so it takes a context-owned non-blocking
+// stream of its own, ordered after whatever is already queued on the caller's stream: threads calling with
+// host buffers (the reference's ThreadPoolExecutor workers, src/pipeline.py:42,288,555-560) overlap their
+// copies, kernels and waits instead of serialising on one workspace.
+struct CallScope {
+  tvc_ctx* ctx;
+  DeviceGuard guard;
+  cudaStream_t st;
+  tvc_ctx::Ws* ws = nullptr;
+  bool internal = false;
+  int rc = TVC_OK;
+  CallScope(tvc_ctx* c, void* stream, bool host_buffers)
+      : ctx(c), guard(c->device), st(static_cast<cudaStream_t>(stream)) {
+    if (!guard.ok) {
+      rc = fail(ctx, TVC_ERR_CUDA, "cudaSetDevice failed");
+      return;
+    }
+    cudaEvent_t ev = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      if (host_buffers) {
+        cudaStream_t own = nullptr;
+        if (!ctx->idle_streams.empty()) {
+          own = ctx->idle_streams.back();
+          ctx->idle_streams.pop_back();
+        } else if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) == cudaSuccess) {
+          ctx->own_streams.push_back(own);
+        } else {
+          cudaGetLastError();
+          own = nullptr;
+        }
+        if (own) {
+          if (!ctx->idle_events.empty()) {
+            ev = ctx->idle_events.back();
+            ctx->idle_events.pop_back();
+          } else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            ev = nullptr;
+          }
+          if (ev && cudaEventRecord(ev, st) == cudaSuccess && cudaStreamWaitEvent(own, ev, 0) == cudaSuccess) {
+            st = own;
+            internal = true;
+          } else {           // could not order behind the caller's stream: stay on it
+            cudaGetLastError();
+            ctx->idle_streams.push_back(own);
+          }
+          if (ev) ctx->idle_events.push_back(ev);
+        }
+      }
+      std::unique_ptr<tvc_ctx::Ws>& slot = ctx->ws[st];
+      if (!slot) slot.reset(new (std::nothrow) tvc_ctx::Ws());
+      ws = slot.get();
+    }
+    if (!ws) {
+      rc = fail(ctx, TVC_ERR_OOM, "workspace record");
+      return;
+    }
+    ws->mu.lock();
+  }
+  ~CallScope() {
+    if (ws) ws->mu.unlock();
+    if (internal) {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      ctx->idle_streams.push_back(st);
+    }
+  }
+  CallScope(const CallScope&) = delete;
+  CallScope& operator=(const CallScope&) = delete;
+};
+
 // Grow-only per-stream workspace; calls on one stream are stream-ordered so reuse is safe.
-int get_ws(tvc_ctx* ctx, cudaStream_t st, size_t bytes, uint8_t** out) {
-  tvc_ctx::Ws& w = ctx->ws[st];
+int get_ws(CallScope& cs, size_t bytes, uint8_t** out) {
+  tvc_ctx* ctx = cs.ctx;
+  cudaStream_t st = cs.st;
+  tvc_ctx::Ws& w = *cs.ws;
   if (w.bytes < bytes) {
     if (w.ptr) {
       TVC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -132,6 +218,7 @@ int make_tmap(tvc_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, int
 }
 
 int gallery_tmap(tvc_gallery* g) {
+  std::lock_guard<std::mutex> lk(g->ctx->mu);   // concurrent first searches of one gallery
   if (g->tmap_rows == g->n) return TVC_OK;
   int rc = make_tmap(g->ctx, &g->tmap, g->bf16, g->n, g->d_pad, kBN);
   if (rc == TVC_OK) rc = make_tmap(g->ctx, &g->tmap128, g->bf16, g->n, g->d_pad, 128);
@@ -305,7 +392,9 @@ int tvc_ctx_destroy(tvc_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->ws)
-      if (kv.second.ptr) cudaFree(kv.second.ptr);
+      if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
+    for (cudaStream_t s : ctx->own_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : ctx->idle_events) cudaEventDestroy(e);
     for (auto& pr : ctx->timed) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
@@ -319,7 +408,7 @@ int tvc_ctx_destroy(tvc_ctx* ctx) {
   return TVC_OK;
 }
 
-const char* tvc_last_error(tvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* tvc_last_error(tvc_ctx* ctx) { return ctx ? t_last_error.c_str() : "null context"; }
 
 int64_t tvc_ctx_launch_count(tvc_ctx* ctx) { return ctx ? launches_so_far() - ctx->launches0 : 0; }
 
@@ -347,17 +436,23 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
 
 int tvc_ctx_release_workspace(tvc_ctx* ctx, int64_t* freed_bytes) {
   if (!ctx) return TVC_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
-  TVC_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read a workspace
-  int64_t freed = 0;
-  for (auto& kv : ctx->ws) {
-    if (kv.second.ptr) {
-      TVC_CUDA(ctx, cudaFree(kv.second.ptr));
-      freed += static_cast<int64_t>(kv.second.bytes);
-    }
+  std::vector<tvc_ctx::Ws*> all;      // (records stay: a running call holds a pointer to its own; only the memory goes)
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& kv : ctx->ws)
+      if (kv.second) all.push_back(kv.second.get());
   }
-  ctx->ws.clear();
+  int64_t freed = 0;
+  for (tvc_ctx::Ws* w : all) {        // lock order: a workspace mutex is never taken while holding ctx->mu
+    std::lock_guard<std::mutex> wl(w->mu);
+    if (!w->ptr) continue;
+    TVC_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read it
+    TVC_CUDA(ctx, cudaFree(w->ptr));
+    freed += static_cast<int64_t>(w->bytes);
+    w->ptr = nullptr;
+    w->bytes = 0;
+  }
   if (freed_bytes) *freed_bytes = freed;
   return TVC_OK;
 }
@@ -404,7 +499,6 @@ int tvc_gallery_create(tvc_ctx* ctx, const void* rows, int dtype, int64_t n, int
   g->flags = flags;
   int rc;
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard guard(ctx->device);
     rc = gallery_reserve(g, capacity_hint > n ? capacity_hint : n, static_cast<cudaStream_t>(stream));
   }
@@ -423,9 +517,9 @@ int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, v
   tvc_ctx* ctx = g->ctx;
   if (g->external) return fail(ctx, TVC_ERR_INVALID, "tvc_gallery_append: wrapped row view");
   if (g->n + n >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
+  CallScope cs(ctx, stream, false);   // stays on the caller's stream: later searches on it see the rows
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   int rc = gallery_reserve(g, g->n + n, st);
   if (rc != TVC_OK) return rc;
   const size_t row_b = static_cast<size_t>(g->d) * elem_size(dtype);
@@ -442,7 +536,7 @@ int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, v
     if (win < 1) win = 1;
     if (win > n) win = n;
     uint8_t* ws;
-    rc = get_ws(ctx, st, up256(static_cast<size_t>(win) * row_b), &ws);
+    rc = get_ws(cs, up256(static_cast<size_t>(win) * row_b), &ws);
     if (rc != TVC_OK) return rc;
     for (int64_t r0 = 0; r0 < n; r0 += win) {
       const int64_t nr = n - r0 < win ? n - r0 : win;
@@ -461,7 +555,7 @@ int tvc_gallery_append(tvc_gallery* g, const void* rows, int dtype, int64_t n, v
 
 int tvc_gallery_truncate(tvc_gallery* g, int64_t n) {
   if (!g || n < 0 || n > g->n) return TVC_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(g->ctx->mu);
+  std::lock_guard<std::mutex> lk(g->ctx->mu);   // (the tensor maps are rebuilt under the same mutex)
   g->n = n;
   g->tmap_rows = -1;
   return TVC_OK;
@@ -472,7 +566,6 @@ int tvc_gallery_move_row(tvc_gallery* g, int64_t src, int64_t dst, void* stream)
   if (src == dst) return TVC_OK;
   tvc_ctx* ctx = g->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   TVC_CUDA(ctx, cudaMemcpyAsync(g->bf16 + dst * g->d_pad, g->bf16 + src * g->d_pad,
                                 static_cast<size_t>(g->d_pad) * 2, cudaMemcpyDeviceToDevice, st));
@@ -505,14 +598,14 @@ int tvc_gallery_get_rows(tvc_gallery* g, const int64_t* idx, int64_t n, float* o
   if (!g || n < 0 || (n > 0 && (!idx || !out))) return TVC_ERR_INVALID;
   if (n == 0) return TVC_OK;
   tvc_ctx* ctx = g->ctx;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const bool idx_dev = is_device_ptr(idx), out_dev = is_device_ptr(out);
+  CallScope cs(ctx, stream, !idx_dev || !out_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const size_t idx_b = up256(static_cast<size_t>(n) * 8), out_b = up256(static_cast<size_t>(n) * g->d * 4);
   uint8_t* ws = nullptr;
   if (!idx_dev || !out_dev) {
-    int rc = get_ws(ctx, st, idx_b + out_b, &ws);
+    int rc = get_ws(cs, idx_b + out_b, &ws);
     if (rc != TVC_OK) return rc;
   }
   const void* didx = idx;
@@ -646,10 +739,12 @@ struct CandOut {
   int64_t m_total = 0;
 };
 
-static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool q_dev, int q_dtype,
+static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool q_dev, int q_dtype,
                         int64_t m, int64_t row0, int32_t k, float threshold, uint32_t flags,
-                        float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev, cudaStream_t st,
+                        float* out_sim, bool sim_dev, int64_t* out_idx, bool idx_dev,
                         const CandOut* cand = nullptr) {
+  tvc_ctx* ctx = cs.ctx;
+  cudaStream_t st = cs.st;
   const int d = g->d, d_pad = g->d_pad;
   // CTA pairs (cta_group::2) pay off once there are enough 256-row query tiles to feed 74 pairs
   bool pair = m >= ctx->pair_min_rows && (ctx->sm_count % 2) == 0;
@@ -667,7 +762,7 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
   const size_t os_b = (sim_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 4);
   const size_t oi_b = (idx_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 8);
   uint8_t* ws;
-  int rc = get_ws(ctx, st, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b, &ws);
+  int rc = get_ws(cs, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b, &ws);
   if (rc != TVC_OK) return rc;
   uint8_t* p = ws;
   uint8_t* q_in = p; p += q_in_b;
@@ -695,11 +790,17 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
   rc = gallery_tmap(g);
   if (rc != TVC_OK) return rc;
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  if (ctx->timing) {
-    if (!ctx->event_pool.empty()) {
+  bool timing;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    timing = ctx->timing;
+    if (timing && !ctx->event_pool.empty()) {
       ev = ctx->event_pool.back();
       ctx->event_pool.pop_back();
-    } else {
+    }
+  }
+  if (timing) {
+    if (!ev.first) {
       ev.first = get_event(ctx);
       ev.second = get_event(ctx);
     }
@@ -709,8 +810,9 @@ static int search_chunk(tvc_ctx* ctx, tvc_gallery* g, const void* queries, bool 
     TVC_CUDA(ctx, launch_gemm_topk_pair(tq, g->tmap128, plan, cand_val, cand_idx, st));
   else
     TVC_CUDA(ctx, launch_gemm_topk(tq, g->tmap, plan, cand_val, cand_idx, st));
-  if (ctx->timing) {
+  if (timing) {
     TVC_CUDA(ctx, cudaEventRecord(ev.second, st));
+    std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->timed.push_back(ev);
   }
   if (cand) {
@@ -745,11 +847,11 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
   if (k < 1) return fail(ctx, TVC_ERR_INVALID, "tvc_search: k < 1");
   if (k > TVC_MAX_K) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search: k > TVC_MAX_K");
   if (m == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const bool q_dev = is_device_ptr(queries), sim_dev = is_device_ptr(out_sim),
              idx_dev = is_device_ptr(out_idx);
+  CallScope cs(ctx, stream, !q_dev || !sim_dev || !idx_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   if (g->n == 0) {
     // empty gallery: every slot unused
     std::vector<float> hs(static_cast<size_t>(m) * k, -INFINITY);
@@ -764,9 +866,9 @@ int tvc_search(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int q_dtype, i
   const size_t q_row_b = static_cast<size_t>(d) * elem_size(q_dtype);
   for (int64_t r0 = 0; r0 < m; r0 += kMaxRowsPerLaunch) {
     const int64_t mc = m - r0 < kMaxRowsPerLaunch ? m - r0 : kMaxRowsPerLaunch;
-    const int rc = search_chunk(ctx, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, q_dev, q_dtype,
+    const int rc = search_chunk(cs, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, q_dev, q_dtype,
                                 mc, r0, k, threshold, flags, out_sim + r0 * k, sim_dev, out_idx + r0 * k,
-                                idx_dev, st);
+                                idx_dev);
     if (rc != TVC_OK) return rc;
     // host staging in the shared workspace is reused by the next chunk
     if ((!q_dev || !sim_dev || !idx_dev) && r0 + mc < m) TVC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -796,9 +898,9 @@ int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
   if (!is_device_ptr(queries) || (!scatter && (!is_device_ptr(cand_val) || !is_device_ptr(cand_idx))))
     return fail(ctx, TVC_ERR_INVALID, "tvc_search_candidates: device pointers only");
   if (m == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
+  CallScope cs(ctx, stream, false);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const int kp = tvc_candidate_width(k);
   ScatterSpec sc{};
   CandOut co;
@@ -820,7 +922,7 @@ int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
     // empty shard: every slot unused (written by the select kernel from an all-empty candidate list)
     uint8_t* ws;
     const size_t cb = up256(static_cast<size_t>(m) * kp * 4);
-    int rc = get_ws(ctx, st, 2 * cb, &ws);
+    int rc = get_ws(cs, 2 * cb, &ws);
     if (rc != TVC_OK) return rc;
     TVC_CUDA(ctx, cudaMemsetAsync(ws, 0xFF, 2 * cb, st));   // idx = -1 everywhere
     TVC_CUDA(ctx, launch_select_candidates(reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + cb), m, 1,
@@ -831,8 +933,8 @@ int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
                                                            : static_cast<size_t>(d) * elem_size(q_dtype);
   for (int64_t r0 = 0; r0 < m; r0 += kMaxRowsPerLaunch) {
     const int64_t mc = m - r0 < kMaxRowsPerLaunch ? m - r0 : kMaxRowsPerLaunch;
-    const int rc = search_chunk(ctx, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, true, q_dtype, mc, r0,
-                                k, -INFINITY, flags, nullptr, true, nullptr, true, st, &co);
+    const int rc = search_chunk(cs, g, static_cast<const uint8_t*>(queries) + r0 * q_row_b, true, q_dtype, mc, r0,
+                                k, -INFINITY, flags, nullptr, true, nullptr, true, &co);
     if (rc != TVC_OK) return rc;
   }
   return TVC_OK;
@@ -854,7 +956,6 @@ int tvc_prepare_queries(tvc_ctx* ctx, const void* rows, int dtype, int64_t m, in
     b.bf16[i] = static_cast<__nv_bfloat16*>(dst[i]);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   TVC_CUDA(ctx, launch_prep_rows_bcast(rows, dtype, m, d, (d + kBK - 1) / kBK * kBK,
                                        (flags & TVC_SEARCH_NORMALIZE_Q) != 0, b, dst_row0, nullptr, st));
@@ -873,7 +974,6 @@ int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, in
       !is_device_ptr(out_idx))
     return fail(ctx, TVC_ERR_INVALID, "tvc_rerank_candidates: device pointers only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   RowSource src;
   fill_row_source(&src, g);
@@ -897,12 +997,13 @@ int tvc_retrieval_metrics(tvc_ctx* ctx, const int64_t* topk_idx, int64_t q, int3
     ks.k[i] = k_values[i];
   }
   if (q == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
+  CallScope cs(ctx, stream, !is_device_ptr(topk_idx) || !is_device_ptr(rel_ptr) || (n_rel > 0 && !is_device_ptr(rel_idx)) ||
+                               !is_device_ptr(out));
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const size_t Q = static_cast<size_t>(q), cols = 2 + 3 * static_cast<size_t>(n_k);
   uint8_t* ws;
-  int rc = get_ws(ctx, st, up256(Q * k * 8) + up256((Q + 1) * 8) + up256(static_cast<size_t>(n_rel) * 8 + 8) +
+  int rc = get_ws(cs, up256(Q * k * 8) + up256((Q + 1) * 8) + up256(static_cast<size_t>(n_rel) * 8 + 8) +
                                up256(Q * cols * 4), &ws);
   if (rc != TVC_OK) return rc;
   Stager sg{ctx, st, ws};
@@ -965,15 +1066,15 @@ int tvc_similarity_matrix(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
     return fail(ctx, TVC_ERR_INVALID, "tvc_similarity_matrix: bad argument");
   if (m == 0 || g->n == 0) return TVC_OK;
   if (m >= (1ll << 31)) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_similarity_matrix: m too large");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const bool q_dev = is_device_ptr(queries), out_dev = is_device_ptr(out);
+  CallScope cs(ctx, stream, !q_dev || !out_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const size_t q_in_b = q_dev ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
   const size_t q_bf_b = up256(static_cast<size_t>(m) * g->d_pad * 2);
   const size_t out_b = out_dev ? 0 : up256(static_cast<size_t>(m) * g->n * 4);
   uint8_t* ws;
-  int rc = get_ws(ctx, st, q_in_b + q_bf_b + out_b, &ws);
+  int rc = get_ws(cs, q_in_b + q_bf_b + out_b, &ws);
   if (rc != TVC_OK) return rc;
   const void* q_src = queries;
   if (!q_dev) {
@@ -1005,11 +1106,11 @@ int tvc_merge_topk(tvc_ctx* ctx, const float* in_sim, const int64_t* in_idx, int
   if (!ctx || m < 0 || parts < 1 || k < 1 || (m > 0 && (!in_sim || !in_idx || !out_sim || !out_idx)))
     return fail(ctx, TVC_ERR_INVALID, "tvc_merge_topk: bad argument");
   if (m == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const bool dev = is_device_ptr(in_sim) && is_device_ptr(in_idx) && is_device_ptr(out_sim) &&
                    is_device_ptr(out_idx);
+  CallScope cs(ctx, stream, !dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   if (dev) {
     TVC_CUDA(ctx, launch_merge_topk(in_sim, in_idx, m, parts, k, out_sim, out_idx, st));
     return TVC_OK;
@@ -1019,7 +1120,7 @@ int tvc_merge_topk(tvc_ctx* ctx, const float* in_sim, const int64_t* in_idx, int
   const size_t n_in = static_cast<size_t>(m) * parts * k, n_out = static_cast<size_t>(m) * k;
   const size_t b0 = up256(n_in * 4), b1 = up256(n_in * 8), b2 = up256(n_out * 4), b3 = up256(n_out * 8);
   uint8_t* ws;
-  int rc = get_ws(ctx, st, b0 + b1 + b2 + b3, &ws);
+  int rc = get_ws(cs, b0 + b1 + b2 + b3, &ws);
   if (rc != TVC_OK) return rc;
   float* ds = reinterpret_cast<float*>(ws);
   int64_t* di = reinterpret_cast<int64_t*>(ws + b0);
@@ -1055,15 +1156,17 @@ int tvc_consistency_sims(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, 
   if (q < 0 || (q > 0 && (!s0 || !scores || !flags)))
     return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_sims: bad argument");
   if (q == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
+  auto host = [](const void* ptr) { return ptr != nullptr && !is_device_ptr(ptr); };
+  CallScope cs(ctx, stream, host(s0) || host(sv) || host(sr) || host(r_cnt) || host(sg) || host(g_cnt) || host(sxv) ||
+                               host(scores) || host(flags));
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const size_t V = p->n_variants, R = p->n_retrieval, G = p->n_generative, X = V * (V - (V > 0)) / 2;
   const size_t Q = static_cast<size_t>(q);
   const size_t need = up256(Q * 4) + up256(Q * V * 4) + up256(Q * R * 4) + up256(Q * 4) + up256(Q * G * 4) +
                       up256(Q * 4) + up256(Q * X * 4) + up256(Q * TVC_NSCORES * 4) + up256(Q) + 4096;
   uint8_t* ws;
-  rc = get_ws(ctx, st, need, &ws);
+  rc = get_ws(cs, need, &ws);
   if (rc != TVC_OK) return rc;
   Stager sg_{ctx, st, ws};
   const float *d_s0, *d_sv, *d_sr, *d_sg, *d_sx;
@@ -1100,9 +1203,6 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
   if ((ret_gallery && ret_gallery->d != d) || (gen_gallery && gen_gallery->d != d))
     return fail(ctx, TVC_ERR_INVALID, "tvc_consistency_emb: gallery dimension mismatch");
   if (q == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const size_t V = p->n_variants, R = p->n_retrieval, G = p->n_generative, Q = static_cast<size_t>(q);
   const size_t D = static_cast<size_t>(d);
   const size_t need = 2 * up256(Q * D * 4) + up256(Q * V * D * 4) + up256(Q * n_ret_cand * 8) +
@@ -1116,12 +1216,15 @@ int tvc_consistency_emb(tvc_ctx* ctx, const tvc_detector_params* p, int64_t q, i
                        is_device_ptr(scores) && is_device_ptr(flags) &&
                        (!out_sv || is_device_ptr(out_sv)) && (!out_sr || is_device_ptr(out_sr)) &&
                        (!out_sg || is_device_ptr(out_sg));
+  CallScope cs(ctx, stream, !all_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   // similarity lists handed from the gather/dot kernel to the statistics kernel
   const size_t X = V * (V > 0 ? V - 1 : 0) / 2;
   const size_t lists = 3 * up256(Q * 4) + up256(Q * V * 4) + up256(Q * R * 4) + up256(Q * G * 4) + up256(Q * X * 4);
   const size_t stage_bytes = all_dev ? 4096 : need;
   uint8_t* ws;
-  rc = get_ws(ctx, st, stage_bytes + lists, &ws);
+  rc = get_ws(cs, stage_bytes + lists, &ws);
   if (rc != TVC_OK) return rc;
   Stager sg_{ctx, st, ws};
   ConsistencyEmbArgs a{};
@@ -1182,18 +1285,18 @@ int tvc_reference_vector_rule(tvc_ctx* ctx, int64_t q, int32_t d, int32_t v, con
   if (ret_gallery && ret_gallery->d != d)
     return fail(ctx, TVC_ERR_INVALID, "tvc_reference_vector_rule: gallery dimension mismatch");
   if (q == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const size_t Q = static_cast<size_t>(q), D = static_cast<size_t>(d), V = static_cast<size_t>(v);
   const size_t need = up256(Q * D * 4) + up256(Q * V * k * 8) + up256(Q * V * m * D * 4) + up256(Q * V * 4) +
                       2 * up256(Q * 4) + up256(Q) + 4096;
   const bool all_dev = is_device_ptr(img) && (!ret_idx || is_device_ptr(ret_idx)) && (!gen || is_device_ptr(gen)) &&
                        is_device_ptr(out_s) && is_device_ptr(out_sigma) && is_device_ptr(flags) &&
                        (!out_ref || is_device_ptr(out_ref));
+  CallScope cs(ctx, stream, !all_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   uint8_t* ws;
   const size_t valid_b = up256(Q * V);
-  int rc = get_ws(ctx, st, valid_b + (all_dev ? 4096 : need), &ws);
+  int rc = get_ws(cs, valid_b + (all_dev ? 4096 : need), &ws);
   if (rc != TVC_OK) return rc;
   uint8_t* valid_ws = ws;
   Stager sg{ctx, st, ws + valid_b};
@@ -1229,14 +1332,14 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
   if (!ctx || m < 0 || k < 1 || n_bins < 0 || (n_bins > 0 && !counts) || (m > 0 && !idx))
     return fail(ctx, TVC_ERR_INVALID, "tvc_k_occurrence: bad argument");
   if (n_bins == 0) return TVC_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  DeviceGuard guard(ctx->device);
   const bool idx_dev = m == 0 || is_device_ptr(idx), cnt_dev = is_device_ptr(counts);
+  CallScope cs(ctx, stream, !idx_dev || !cnt_dev);
+  if (cs.rc != TVC_OK) return cs.rc;
+  cudaStream_t st = cs.st;
   const size_t ib = up256(static_cast<size_t>(m) * k * 8), cb = up256(static_cast<size_t>(n_bins) * 4);
   uint8_t* ws = nullptr;
   {
-    int rc = get_ws(ctx, st, 4096 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
+    int rc = get_ws(cs, 4096 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
     if (rc != TVC_OK) return rc;
   }
   int* flag_scratch = reinterpret_cast<int*>(ws);

@@ -22,6 +22,8 @@
 //     bulk copies -> tasks -> selection ~ 9 us) over the 3 stages that fit in 227 KB, not by HBM.
 #include <math.h>
 
+#include <atomic>
+
 #include "tvc_internal.h"
 #include "tvc_ptx.cuh"
 
@@ -1483,13 +1485,9 @@ cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, con
   const size_t floats = up4(kSimsBlock * V) + up4(kSimsBlock * R) + up4(kSimsBlock * G) +
                         up4(kSimsBlock * X) + 16 + kOutStride * TVC_NSCORES;
   const size_t smem = floats * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(consistency_sims_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(consistency_sims_kernel), 160 * 1024); e != cudaSuccess)
+    return e;
   const int grid = static_cast<int>((q + kSimsBlock - 1) / kSimsBlock);
   consistency_sims_kernel<<<grid, kSimsBlock, smem, stream>>>(p, q, s0, sv, sr, r_cnt, sg, g_cnt, sxv,
                                                               scores, flags);
@@ -1521,17 +1519,18 @@ cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int 
               (!a.gen || al16(a.gen)) && (!has_ret || rows_f32_aligned(a.ret)) &&
               (!gen_idx || rows_f32_aligned(a.genr));
   // dynamic shared memory left for the stage ring after the kernel's static tables
-  static size_t smem_budget = 0;
-  if (smem_budget == 0) {
+  static std::atomic<size_t> static_smem{0};   // the kernel's static tables: a property of the code, not of the device
+  if (static_smem.load(std::memory_order_acquire) == 0) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, consistency_emb_pipe_kernel);
     if (e != cudaSuccess) return e;
-    const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
-    e = cudaFuncSetAttribute(consistency_emb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(budget));
-    if (e != cudaSuccess) return e;
-    smem_budget = budget;
+    static_smem.store(fa.sharedSizeBytes + 1, std::memory_order_release);
   }
+  const size_t smem_budget = 227 * 1024 - (static_smem.load(std::memory_order_acquire) - 1) - 1024;
+  static SmemAttrOnce configured_p;            // the opt-in itself is per (kernel, device)
+  if (cudaError_t e = configured_p.ensure(reinterpret_cast<const void*>(consistency_emb_pipe_kernel),
+                                          static_cast<int>(smem_budget)); e != cudaSuccess)
+    return e;
   int n_stages = static_cast<int>(smem_budget / stage_bytes);
   if (n_stages > kEmbMaxStages) n_stages = kEmbMaxStages;
   if (n_stages < 2) pipe = false;
@@ -1556,13 +1555,9 @@ cudaError_t launch_consistency_emb(const tvc_detector_params& p, int64_t q, int 
   int warps = 4;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   if (per_warp * warps > 220 * 1024) return cudaErrorInvalidValue;
-  static bool configured_g = false;
-  if (!configured_g) {
-    cudaError_t e = cudaFuncSetAttribute(consistency_emb_generic_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) return e;
-    configured_g = true;
-  }
+  static SmemAttrOnce configured_g;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured_g.ensure(reinterpret_cast<const void*>(consistency_emb_generic_kernel), 220 * 1024); e != cudaSuccess)
+    return e;
   long long blocks = (q + warps - 1) / warps;
   if (blocks > 148 * 8) blocks = 148 * 8;
   consistency_emb_generic_kernel<<<static_cast<int>(blocks), warps * 32, per_warp * warps, stream>>>(
@@ -1591,13 +1586,9 @@ cudaError_t launch_reference_vector(int64_t q, int d, int v, const float* img, c
     return cudaGetLastError();
   }
   const size_t smem = static_cast<size_t>(v) * kRvSeg * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(reference_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TVC_MAX_VARIANTS * kRvSeg * 4);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(reference_vector_kernel), TVC_MAX_VARIANTS * kRvSeg * 4); e != cudaSuccess)
+    return e;
   long long blocks = static_cast<long long>(sm_count) * 8;
   if (blocks > q) blocks = q;
   reference_vector_kernel<<<static_cast<int>(blocks), v * 32, smem, stream>>>(

@@ -324,13 +324,9 @@ gemm_store_kernel(const __grid_constant__ CUtensorMap tmap_q,
 template <int KP>
 cudaError_t launch_kp(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan,
                       float* cv, int32_t* ci, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<KP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_topk_kernel<KP>), kSmemTotal); e != cudaSuccess)
+    return e;
   gemm_topk_kernel<KP><<<plan.grid, kThreads, kSmemTotal, stream>>>(tq, tg, plan, cv, ci);
   note_launch();
   return cudaGetLastError();
@@ -397,13 +393,9 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
 cudaError_t launch_gemm_store(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g, int m, int n,
                               int kblocks, float* out, int64_t ld_out, int sm_count,
                               cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_store_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_store_kernel), kSmemTotal); e != cudaSuccess)
+    return e;
   const int m_tiles = (m + kBM - 1) / kBM, n_tiles = (n + kBN - 1) / kBN;
   const long long units = static_cast<long long>(m_tiles) * n_tiles;
   const int grid = static_cast<int>(units < sm_count ? units : sm_count);

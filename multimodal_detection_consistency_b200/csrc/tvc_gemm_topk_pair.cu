@@ -184,13 +184,9 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 template <int KP>
 cudaError_t launch_pair_kp(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
                            int32_t* ci, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_pair_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kPSmemTotal);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_topk_pair_kernel<KP>), kPSmemTotal); e != cudaSuccess)
+    return e;
   gemm_topk_pair_kernel<KP><<<plan.grid, kThreads, kPSmemTotal, stream>>>(tq, tg, plan, cv, ci);
   note_launch();
   return cudaGetLastError();

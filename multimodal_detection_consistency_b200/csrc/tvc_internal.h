@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/tvc.h"
 
 namespace tvc {
@@ -156,6 +158,22 @@ cudaError_t launch_reference_vector(int64_t q, int d, int v, const float* img, c
                                     const int64_t* ret_idx, int k, const float* gen, int m, float sigma_threshold,
                                     float* out_s, float* out_ref, float* out_sigma, uint8_t* flags,
                                     uint8_t* valid_ws, int sm_count, cudaStream_t stream);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, DEVICE): one flag per process would
+// leave the kernel unconfigured on the second GPU a process opens a context on.  One instance per call site.
+struct SmemAttrOnce {
+  std::atomic<uint64_t> done{0};   // bit = device ordinal (mod 64)
+  cudaError_t ensure(const void* kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 // counts every kernel launch made by the library (reported through tvc_ctx_launch_count)
 void note_launch(int n = 1);

@@ -13,6 +13,7 @@ Clustering and the eviction policies are host bookkeeping as in the reference (o
 from __future__ import annotations
 
 import json
+import os
 import logging
 import pickle
 import time
@@ -96,6 +97,9 @@ class ReferenceBank:
         # on every insert, src/ref_bank.py:163,505-516 - O(B) per insert)
         self.journal_compact_every = 256
         self._journal_ops = 0
+        self._seq = 0                   # operations journalled since the bank was created (persisted)
+        # KMeans with the assignment step on the GPU; False = scikit-learn end to end
+        self.gpu_kmeans = True
         if self.config.persistence_enabled:
             Path(self.config.save_path).mkdir(parents=True, exist_ok=True)
         self._load_from_disk()
@@ -250,7 +254,10 @@ class ReferenceBank:
     def perform_clustering(self, force: bool = False) -> bool:
         try:
             with self._lock:
-                return self._perform_clustering(force)
+                done = self._perform_clustering(force)
+                if done and self.config.persistence_enabled:
+                    self._save_to_disk()  # cluster ids changed on many items: fold everything
+                return done
         except Exception as e:  # noqa: BLE001
             logger.error("clustering failed: %s", e)
             return False
@@ -262,10 +269,15 @@ class ReferenceBank:
         try:
             vectors = np.array([r.vector for r in self.references])
             if self.config.clustering_method == "kmeans":
-                from sklearn.cluster import KMeans
-                km = KMeans(n_clusters=min(self.config.num_clusters, len(self.references)), random_state=42, n_init=10)
-                labels = km.fit_predict(vectors)
-                self.cluster_centers = km.cluster_centers_
+                n_clusters = min(self.config.num_clusters, len(self.references))
+                fit = self._kmeans_device_assign(vectors, n_clusters) if self.gpu_kmeans else None
+                if fit is None:                      # degenerate input (empty cluster, duplicates): sklearn end to end
+                    from sklearn.cluster import KMeans
+                    km = KMeans(n_clusters=n_clusters, random_state=42, n_init=10)
+                    labels = km.fit_predict(vectors)
+                    self.cluster_centers = km.cluster_centers_
+                else:
+                    labels, self.cluster_centers = fit
             elif self.config.clustering_method == "dbscan":
                 from sklearn.cluster import DBSCAN
                 labels = DBSCAN(eps=0.5, min_samples=5).fit_predict(vectors)
@@ -286,6 +298,100 @@ class ReferenceBank:
         except Exception as e:  # noqa: BLE001
             logger.error("clustering failed: %s", e)
             return False
+
+    def _kmeans_device_assign(self, vectors: np.ndarray, n_clusters: int, n_init: int = 10, max_iter: int = 300,
+                              tol: float = 1e-4, seed: int = 42):
+        """KMeans(n_clusters, random_state=42, n_init=10).fit_predict(vectors) (src/ref_bank.py:296-300) with the
+        ASSIGNMENT step - the O(B * C * d) part - as kernel (a): argmin_c |x - c|^2 = argmax_c (x.c - |c|^2 / 2) is
+        an inner-product top-1 of the augmented rows [x, 1] against the augmented centres [c, -|c|^2 / 2]
+        (SURVEY.md §8f rank 3).  Initialisation (k-means++) and the update step stay scikit-learn's / NumPy's,
+        and the driver follows scikit-learn's Lloyd loop (sklearn/cluster/_kmeans.py, KMeans.fit and
+        _kmeans_single_lloyd: centred data, one RandomState shared by the n_init restarts, stop on unchanged
+        labels or centre shift <= tol * mean variance, a last assignment when stopped by tolerance, best inertia
+        wins) so that the labels are scikit-learn's.  Rows whose two best scores are closer than fp32 can
+        resolve are re-decided in fp64 on the host.  Returns (labels, centres) or None when a cluster runs
+        empty (scikit-learn relocates centres there: the caller falls back to it)."""
+        from sklearn.cluster import kmeans_plusplus
+        from sklearn.utils import check_random_state
+        X = np.ascontiguousarray(vectors, dtype=vectors.dtype if vectors.dtype in (np.float32, np.float64) else np.float64)
+        X = X.copy()
+        n, d = X.shape
+        if n_clusters < 2 or n < n_clusters:
+            return None
+        tol_abs = float(np.mean(np.var(X, axis=0)) * tol)
+        rs = check_random_state(seed)
+        mean = X.mean(axis=0)
+        X -= mean
+        x_sq = np.einsum("ij,ij->i", X, X)
+        q = np.empty((n, d + 1), np.float32)
+        q[:, :d], q[:, d] = X, 1.0
+        try:
+            import torch
+            q_dev = torch.from_numpy(q).cuda()
+        except Exception:  # noqa: BLE001 - no torch: host rows, staged by the library on every call
+            q_dev = None
+        kk = 2 if n_clusters <= 16 else (11 if n_clusters <= 32 else 27)   # candidate width 16 / 32 / 64 >= centres
+        kk = min(kk, n_clusters)
+
+        def assign(centers):
+            c = np.empty((n_clusters, d + 1), np.float32)
+            c[:, :d] = centers
+            c[:, d] = -0.5 * np.einsum("ij,ij->i", centers, centers)
+            gal = Gallery(c, normalize=False)
+            try:
+                sims, idx = gal.search(q_dev if q_dev is not None else q, kk)
+            finally:
+                gal.close()
+            if q_dev is not None:
+                sims, idx = sims.cpu().numpy(), idx.cpu().numpy()
+            labels = idx[:, 0].astype(np.int32)
+            # fp32 cannot separate the two best centres of these rows: decide them as scikit-learn does (argmin of
+            # the squared distance in the data's own precision, first minimum wins)
+            scale = max(1.0, float(np.abs(sims[:, 0]).max()))
+            close = np.nonzero((sims[:, 0] - sims[:, 1]) <= 1e-4 * scale)[0]
+            for r0 in range(0, len(close), 4096):
+                rows = close[r0:r0 + 4096]
+                dist = x_sq[rows, None] - 2.0 * (X[rows] @ centers.T) + np.einsum("ij,ij->i", centers, centers)[None, :]
+                labels[rows] = np.argmin(dist, axis=1)
+            return labels
+
+        def same_clustering(a, b):
+            mapping = np.full(n_clusters, -1, np.int32)
+            for i in range(n):
+                if mapping[a[i]] == -1:
+                    mapping[a[i]] = b[i]
+                elif mapping[a[i]] != b[i]:
+                    return False
+            return True
+
+        best = None
+        for _ in range(n_init):
+            centers, _ = kmeans_plusplus(X, n_clusters, x_squared_norms=x_sq, random_state=rs)
+            centers = centers.astype(X.dtype, copy=True)
+            labels_old = np.full(n, -1, np.int32)
+            strict = False
+            for _it in range(max_iter):
+                labels = assign(centers)
+                counts = np.bincount(labels, minlength=n_clusters)
+                if (counts == 0).any():
+                    return None
+                new = np.zeros_like(centers)
+                np.add.at(new, labels, X)
+                new /= counts[:, None]
+                shift = float(((new - centers) ** 2).sum())
+                centers = new
+                if np.array_equal(labels, labels_old):
+                    strict = True
+                    break
+                if shift <= tol_abs:
+                    break
+                labels_old = labels
+            if not strict:
+                labels = assign(centers)
+            inertia = float(((X - centers[labels]) ** 2).sum())
+            if best is None or (inertia < best[0] and not same_clustering(labels, best[1])):
+                best = (inertia, labels, centers)
+        return best[1], best[2] + mean
 
     # ------------------------------------------------------------------ insert / evict
     def _is_too_similar(self, vector: np.ndarray) -> bool:
@@ -374,8 +480,9 @@ class ReferenceBank:
     def _journal(self, op: Dict[str, Any]):
         """Append one operation; fold the journal into the JSON files every journal_compact_every ops."""
         try:
+            self._seq += 1
             with open(Path(self.config.save_path) / self._JOURNAL, "a") as f:
-                f.write(json.dumps(op) + "\n")
+                f.write(json.dumps(dict(op, seq=self._seq)) + "\n")
             self._journal_ops += 1
             if self._journal_ops >= self.journal_compact_every:
                 self._save_to_disk()
@@ -393,13 +500,27 @@ class ReferenceBank:
         try:
             root = Path(self.config.save_path)
             root.mkdir(parents=True, exist_ok=True)
-            (root / "references.json").write_text(json.dumps([r.to_dict() for r in self.references], indent=2))
-            (root / "clusters.json").write_text(json.dumps({
+
+            def put(name, text):                       # a reader (or a crash) never sees half a file
+                tmp = root / (name + ".tmp")
+                tmp.write_text(text)
+                os.replace(tmp, root / name)
+
+            # The folded sequence number travels INSIDE references.json (the one file whose replacement commits
+            # the fold): as an extra key of the first item - ReferenceItem.from_dict, here and in the reference
+            # (src/ref_bank.py:73-83), reads named keys only - or, for an empty bank, in the {"references": []}
+            # wrapper the shipped cache/ref_bank snapshot uses.  A crash between the replace and the unlink of
+            # the journal then replays nothing twice: lines with seq <= the folded number are skipped on load.
+            data = [r.to_dict() for r in self.references]
+            if data:
+                data[0] = dict(data[0], _journal_seq=self._seq)
+            put("clusters.json", json.dumps({
                 "clusters": {str(k): v for k, v in self.clusters.items()},
                 "cluster_centers": self.cluster_centers.tolist() if self.cluster_centers is not None else None},
                 indent=2))
-            (root / "stats.json").write_text(json.dumps(self.stats, indent=2))
-            (root / "config.json").write_text(json.dumps(asdict(self.config), indent=2))
+            put("stats.json", json.dumps(self.stats, indent=2))
+            put("config.json", json.dumps(asdict(self.config), indent=2))
+            put("references.json", json.dumps(data if data else {"references": [], "_journal_seq": self._seq}, indent=2))
             j = root / self._JOURNAL
             if j.exists():
                 j.unlink()
@@ -414,8 +535,13 @@ class ReferenceBank:
             if not self.config.persistence_enabled or not (refs_file.exists() or (root / self._JOURNAL).exists()):
                 return
             data = json.loads(refs_file.read_text()) if refs_file.exists() else []
+            folded = 0
             if isinstance(data, dict):  # the snapshot shipped in cache/ref_bank wraps the list
+                folded = int(data.get("_journal_seq", 0))
                 data = data.get("references", [])
+            elif data and isinstance(data[0], dict):
+                folded = int(data[0].get("_journal_seq", 0))
+            self._seq = folded
             self.references = [ReferenceItem.from_dict(d) for d in data]
             self._pos_cache = None
             cf = root / "clusters.json"
@@ -433,6 +559,10 @@ class ReferenceBank:
                     if not line.strip():
                         continue
                     op = json.loads(line)
+                    if "seq" in op:
+                        if int(op["seq"]) <= folded:        # already inside references.json (crash after the fold)
+                            continue
+                        self._seq = max(self._seq, int(op["seq"]))
                     if op.get("op") == "add":
                         self.references.append(ReferenceItem.from_dict(op["item"]))
                         self.stats["total_added"] += 1
@@ -454,6 +584,8 @@ class ReferenceBank:
             self._pos_cache = None
             self.stats = self._fresh_stats()
             self._dev_rebuild()
+            if self.config.persistence_enabled:
+                self._save_to_disk()      # the journal on disk describes the bank that was just dropped
 
     def get_statistics(self) -> Dict[str, Any]:
         with self._lock:
@@ -510,6 +642,8 @@ class ReferenceBank:
                 self._pos_cache = None
                 self._dev_append(taken)
                 self.stats["total_added"] += len(taken)
+                if self.config.persistence_enabled:
+                    self._save_to_disk()  # later journal lines index into a list that now holds these rows
                 return True
         except Exception as e:  # noqa: BLE001
             logger.error("import failed: %s", e)

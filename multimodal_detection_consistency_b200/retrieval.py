@@ -210,8 +210,10 @@ class MultiModalRetriever:
         # single-query calls made concurrently (the pipeline's worker threads, src/pipeline.py:555-560)
         # are coalesced into one encoder call + one search launch (batching.MicroBatcher)
         self.micro_batch = True
-        self._t2i_batcher = MicroBatcher(lambda k, texts: self.batch_retrieve_images_by_texts(texts, k))
-        self._i2t_batcher = MicroBatcher(lambda k, images: self.batch_retrieve_texts_by_images(images, k))
+        # (the raising forms: a failing round is re-run item by item by the batcher, so one bad query only
+        # empties its own caller's result - the reference fails per query, src/retrieval.py:574-576)
+        self._t2i_batcher = MicroBatcher(lambda k, texts: self._batch_t2i(texts, k))
+        self._i2t_batcher = MicroBatcher(lambda k, images: self._batch_i2t(images, k))
 
     def _initialize_clip_model(self):
         """The reference builds `src.models.CLIPModel` here (src/retrieval.py:347-369); that package is
@@ -354,57 +356,72 @@ class MultiModalRetriever:
             logger.error("image->text retrieval failed: %s", e)
             return [], []
 
+    def _batch_t2i(self, query_texts: List[str], top_k: int):
+        """One encoder call and ONE search launch for the whole batch; raises on failure."""
+        if self.image_index is None:
+            raise ValueError("image index not built")
+        todo = [t for t in dict.fromkeys(query_texts)
+                if not (self.config.enable_cache and f"text2img_{t}_{top_k}" in self.retrieval_cache)]
+        fresh = {}
+        if todo:
+            q = _to_numpy(self.clip_model.encode_text(todo, normalize=self.config.normalize_features))
+            sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k)
+            for t, s_row, i_row in zip(todo, sims, idx):
+                keep = i_row >= 0
+                fresh[t] = ([self.image_paths[i] for i in i_row[keep]], [float(s) for s in s_row[keep]])
+                if self.config.enable_cache:
+                    self.retrieval_cache[f"text2img_{t}_{top_k}"] = fresh[t]
+        return [fresh[t] if t in fresh else self.retrieval_cache[f"text2img_{t}_{top_k}"] for t in query_texts]
+
+    def _isolated(self, fn, items, top_k, what):
+        """The batch as one call; if that fails, item by item, so only the offending items come back empty
+        (the reference's batch_* are loops over the never-raising single call, src/retrieval.py:724-762)."""
+        try:
+            return fn(items, top_k)
+        except Exception as e:  # noqa: BLE001
+            logger.error("batched %s retrieval failed: %s", what, e)
+            if len(items) <= 1:
+                return [([], []) for _ in items]
+        out = []
+        for it in items:
+            try:
+                out.append(fn([it], top_k)[0])
+            except Exception as e:  # noqa: BLE001
+                logger.error("%s retrieval failed: %s", what, e)
+                out.append(([], []))
+        return out
+
     def batch_retrieve_images_by_texts(self, query_texts: List[str], top_k: Optional[int] = None):
         """src/retrieval.py:724-742, but one encoder call and ONE search launch for the whole batch."""
-        top_k = top_k or self.config.top_k
-        try:
-            if self.image_index is None:
-                raise ValueError("image index not built")
-            todo = [t for t in dict.fromkeys(query_texts)
-                    if not (self.config.enable_cache and f"text2img_{t}_{top_k}" in self.retrieval_cache)]
-            fresh = {}
-            if todo:
-                q = _to_numpy(self.clip_model.encode_text(todo, normalize=self.config.normalize_features))
-                sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k)
-                for t, s_row, i_row in zip(todo, sims, idx):
-                    keep = i_row >= 0
-                    fresh[t] = ([self.image_paths[i] for i in i_row[keep]], [float(s) for s in s_row[keep]])
-                    if self.config.enable_cache:
-                        self.retrieval_cache[f"text2img_{t}_{top_k}"] = fresh[t]
-            return [fresh[t] if t in fresh else self.retrieval_cache[f"text2img_{t}_{top_k}"] for t in query_texts]
-        except Exception as e:  # noqa: BLE001
-            logger.error("batched text->image retrieval failed: %s", e)
-            return [([], []) for _ in query_texts]
+        return self._isolated(self._batch_t2i, list(query_texts), top_k or self.config.top_k, "text->image")
 
     def batch_retrieve_texts_by_images(self, query_images: List[Any], top_k: Optional[int] = None):
         """src/retrieval.py:744-762 with one launch."""
-        top_k = top_k or self.config.top_k
-        try:
-            if self.text_index is None:
-                raise ValueError("text index not built")
-            # same cache keys as the single call (:596-600), so either entry point serves the other
-            keys = [f"img2text_{im}_{top_k}" if isinstance(im, str) else f"img2text_pil_{id(im)}_{top_k}"
-                    for im in query_images]
-            cache = self.retrieval_cache if self.config.enable_cache else {}
-            fresh: Dict[str, Any] = {}
-            todo = [(key, im) for key, im in dict(zip(keys, query_images)).items() if key not in cache]
-            if todo:
-                images = []
-                for _, im in todo:
-                    if isinstance(im, str):
-                        from PIL import Image
-                        im = Image.open(im).convert("RGB")
-                    images.append(im)
-                q = _to_numpy(self.clip_model.encode_image(images, normalize=self.config.normalize_features))
-                sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k, index="text")
-                for (key, _), s_row, i_row in zip(todo, sims, idx):
-                    fresh[key] = ([self.texts[i] for i in i_row[i_row >= 0]], [float(s) for s in s_row[i_row >= 0]])
-                    if self.config.enable_cache:
-                        self.retrieval_cache[key] = fresh[key]
-            return [fresh[key] if key in fresh else cache[key] for key in keys]
-        except Exception as e:  # noqa: BLE001
-            logger.error("batched image->text retrieval failed: %s", e)
-            return [([], []) for _ in query_images]
+        return self._isolated(self._batch_i2t, list(query_images), top_k or self.config.top_k, "image->text")
+
+    def _batch_i2t(self, query_images: List[Any], top_k: int):
+        if self.text_index is None:
+            raise ValueError("text index not built")
+        # same cache keys as the single call (:596-600), so either entry point serves the other
+        keys = [f"img2text_{im}_{top_k}" if isinstance(im, str) else f"img2text_pil_{id(im)}_{top_k}"
+                for im in query_images]
+        cache = self.retrieval_cache if self.config.enable_cache else {}
+        fresh: Dict[str, Any] = {}
+        todo = [(key, im) for key, im in dict(zip(keys, query_images)).items() if key not in cache]
+        if todo:
+            images = []
+            for _, im in todo:
+                if isinstance(im, str):
+                    from PIL import Image
+                    im = Image.open(im).convert("RGB")
+                images.append(im)
+            q = _to_numpy(self.clip_model.encode_image(images, normalize=self.config.normalize_features))
+            sims, idx = self.search_features(np.ascontiguousarray(q, np.float32), top_k, index="text")
+            for (key, _), s_row, i_row in zip(todo, sims, idx):
+                fresh[key] = ([self.texts[i] for i in i_row[i_row >= 0]], [float(s) for s in s_row[i_row >= 0]])
+                if self.config.enable_cache:
+                    self.retrieval_cache[key] = fresh[key]
+        return [fresh[key] if key in fresh else cache[key] for key in keys]
 
     # caller-side spellings (experiments/run_experiments.py:3143, README.md:368,810)
     def retrieve(self, text: str, k: Optional[int] = None, top_k: Optional[int] = None):

@@ -73,3 +73,42 @@ def test_errors_reach_every_caller_of_the_round():
     assert out == [None] * 4 and all(isinstance(e, RuntimeError) for e in errs)
     with pytest.raises(RuntimeError):
         MicroBatcher(lambda k, items: [], max_delay_s=0.0).submit(1)     # wrong result count
+
+
+def test_a_failing_item_does_not_fail_its_round():
+    """one bad sample inside a coalesced round must only fail its own caller (the reference isolates
+    failures per sample); the leader re-runs the round item by item."""
+    import threading
+    from multimodal_detection_consistency_b200.batching import MicroBatcher
+    calls = []
+
+    def fn(key, items):
+        calls.append(list(items))
+        if any(x == "bad" for x in items):
+            raise ValueError("corrupt sample")
+        return [x * 2 for x in items]
+
+    mb = MicroBatcher(fn, max_batch=4, max_delay_s=0.5, idle_s=10.0)
+    items = [1, "bad", 3, 4]
+    out, errs = {}, {}
+    gate = threading.Barrier(4)
+
+    def work(x):
+        gate.wait()
+        try:
+            out[x] = mb.submit(x)
+        except ValueError as e:
+            errs[x] = e
+
+    th = [threading.Thread(target=work, args=(x,)) for x in items]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert out == {1: 2, 3: 6, 4: 8}
+    assert list(errs) == ["bad"]
+    assert mb.isolated <= 1 and max(len(c) for c in calls) >= 1
+    # a lone failing call still raises its own error
+    try:
+        mb.submit("bad")
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass

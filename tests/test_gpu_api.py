@@ -166,6 +166,87 @@ def test_reference_bank_insert_dedup_eviction_persistence(tmp_path):
     assert len(kept) == 4 and (1 in kept) != (2 in kept)
 
 
+def test_reference_bank_journal_never_drifts_from_memory(tmp_path):
+    """clear(), import_references() and perform_clustering() change the bank outside the add / evict
+    journal; the disk state must still reload to exactly the memory state, and a crash between a fold's
+    replace of references.json and the unlink of the journal must not replay folded operations."""
+    import json
+    import shutil
+    from multimodal_detection_consistency_b200 import ReferenceBank, ReferenceBankConfig
+    rng = np.random.default_rng(9)
+    root = tmp_path / "bank"
+    cfg = ReferenceBankConfig(max_size=12, similarity_threshold=0.95, persistence_enabled=True, save_path=str(root),
+                              auto_clustering=False, feature_dim=16, num_clusters=3)
+    vecs = rng.standard_normal((60, 16)).astype(np.float32)
+    ids = lambda b: [r.metadata["i"] for r in b.references]   # noqa: E731
+    bank = ReferenceBank(cfg)
+    for i in range(5):
+        assert bank.add_reference(vecs[i], {"i": i})
+    # clear -> add: the five journalled adds must not come back
+    bank.clear()
+    assert bank.add_reference(vecs[5], {"i": 5})
+    assert ids(ReferenceBank(cfg)) == [5]
+    # import -> add -> evict: the imported rows are on disk before later `remove index` lines refer to them
+    donor = ReferenceBank(ReferenceBankConfig(max_size=50, persistence_enabled=False, save_path=str(tmp_path / "d"),
+                                              auto_clustering=False, feature_dim=16))
+    for i in range(10, 18):
+        assert donor.add_reference(vecs[i], {"i": i})
+    assert donor.export_references(str(tmp_path / "donor.json"))
+    assert bank.import_references(str(tmp_path / "donor.json"))
+    assert ids(bank) == [5] + list(range(10, 18))
+    for i in range(20, 28):                                   # 9 + 8 > 12: fifo evictions of 5, 10, 11, ...
+        assert bank.add_reference(vecs[i], {"i": i})
+    assert len(bank.references) == 12
+    again = ReferenceBank(cfg)
+    assert ids(again) == ids(bank)
+    assert again.stats["total_added"] == bank.stats["total_added"]
+    assert again.stats["total_removed"] == bank.stats["total_removed"]
+    # public perform_clustering folds the new cluster ids
+    assert bank.perform_clustering(force=True)
+    again = ReferenceBank(cfg)
+    assert [r.cluster_id for r in again.references] == [r.cluster_id for r in bank.references]
+    assert {int(k): v for k, v in again.clusters.items()} == {int(k): v for k, v in bank.clusters.items()}
+    # crash between the fold's os.replace(references.json) and the unlink of the journal
+    assert bank.add_reference(vecs[30], {"i": 30}) and bank.add_reference(vecs[31], {"i": 31})
+    journal = root / "references.journal.jsonl"
+    assert journal.exists()
+    shutil.copy(journal, tmp_path / "journal.keep")
+    bank.flush()
+    assert not journal.exists()
+    shutil.copy(tmp_path / "journal.keep", journal)           # the unlink "did not happen"
+    again = ReferenceBank(cfg)
+    assert ids(again) == ids(bank) and len(again.references) == 12
+    first = json.loads((root / "references.json").read_text())[0]
+    assert first["_journal_seq"] >= 2 and not list(root.glob("*.tmp"))
+    # and the operations after such a recovery keep counting from the folded number
+    assert again.add_reference(vecs[32], {"i": 32})
+    assert ids(ReferenceBank(cfg)) == ids(again)
+
+
+def test_reference_bank_kmeans_assignment_matches_sklearn(tmp_path):
+    """SURVEY.md §8f rank 3 / src/ref_bank.py:296-300: KMeans with the assignment step as an inner-product top-1
+    search (kernel a) gives scikit-learn's labels and centres."""
+    from sklearn.cluster import KMeans
+    from multimodal_detection_consistency_b200 import ReferenceBank, ReferenceBankConfig
+    rng = np.random.default_rng(21)
+    for n, d, c, dtype in ((300, 48, 7, np.float64), (900, 96, 20, np.float32), (150, 24, 40, np.float64)):
+        cent = rng.standard_normal((c, d)) * 2.0
+        vecs = (cent[rng.integers(0, c, n)] + 0.6 * rng.standard_normal((n, d))).astype(dtype)
+        bank = ReferenceBank(ReferenceBankConfig(max_size=n, similarity_threshold=0.9999, persistence_enabled=False,
+                                                 save_path=str(tmp_path / "km"), auto_clustering=False, feature_dim=d,
+                                                 num_clusters=c))
+        for i in range(n):
+            assert bank.add_reference(vecs[i], {"i": i})
+        fit = bank._kmeans_device_assign(np.array([r.vector for r in bank.references]), c)
+        assert fit is not None, "the device-assignment path must serve a non-degenerate input"
+        assert bank.perform_clustering()
+        km = KMeans(n_clusters=c, random_state=42, n_init=10)
+        want = km.fit_predict(np.array([r.vector for r in bank.references]))
+        got = np.array([r.cluster_id for r in bank.references])
+        assert np.array_equal(got, want), (n, d, c, int((got != want).sum()))
+        assert np.allclose(bank.get_cluster_centers(), km.cluster_centers_, rtol=1e-5, atol=1e-6)
+
+
 def test_adversarial_detector_matches_reference_outputs():
     """Golden: the reference's AdversarialDetector.detect_adversarial on the same table encoders."""
     from multimodal_detection_consistency_b200 import AdversarialDetector, DetectorConfig
@@ -333,3 +414,21 @@ def test_pipeline_worker_threads_are_micro_batched(tvc_ctx):
         assert a["detection_details"]["text_variants"]["num_variants"] == 5
     assert st_r["rounds"] < len(texts) and st_d["rounds"] < len(texts)      # calls were coalesced
     assert par_clip.calls < seq_clip.calls
+
+
+def test_c_probe_runs_the_hot_path_from_c(tmp_path):
+    """tests/c/abi_probe.c on the GPU box: a plain-C process (dlopen only, no Python, no torch) builds a gallery,
+    searches it with host buffers, checks the result against a scalar loop and histograms it."""
+    import shutil
+    import subprocess
+    from multimodal_detection_consistency_b200 import _native as N
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc on this box")
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "abi_probe"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(root / "include"),
+                    str(root / "tests" / "c" / "abi_probe.c"), "-o", str(exe), "-ldl", "-lm"], check=True)
+    out = subprocess.run([str(exe), str(N.LIB_PATH)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "search + k-occurrence from C" in out.stdout

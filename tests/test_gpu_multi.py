@@ -1,7 +1,8 @@
-"""Two-GPU run of the sharded TVCScorer (candidates stored into the owner's HBM over NVLink and
-re-ranked there from local + peer fp32 masters, kernel (b) reading peer shards over CUDA IPC,
-histogram all-reduce; a second pass forces the NCCL all-to-all + merge path) against the single-GPU result.
-Skipped on boxes with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
+"""Multi-GPU runs (world = 2, 4, 8 - whatever the box has) of the sharded TVCScorer (candidates stored into the
+owner's HBM over NVLink and re-ranked there from local + peer fp32 masters, kernel (b) reading peer shards over
+CUDA IPC, histogram all-reduce; a further pass forces the NCCL all-to-all + merge path) against the single-GPU
+result: indices, flags and the histogram bit-identical, and the same output digest bench.py prints.
+Skipped for world sizes the box cannot serve (run with `gpurun --gpus N`)."""
 import os
 import socket
 import sys
@@ -47,35 +48,55 @@ def _worker(rank, world, port, out_dir):
     assert sc._gallery_group is not None          # the peer-memory path, not the staged fetch
     assert sc._exchange is not None
     ex = sc._exchange
-    for tag in ("peer", "peer2", "nccl"):
+    import bench
+    for tag in ("peer", "peer2", "peer3", "nccl"):
         if tag == "nccl":
             sc._exchange = None                   # candidate all-to-all + merge kernel instead
         sc.reset_hubness()
+        if tag == "peer3":
+            # skewed arrival: every rank enters the batch at a different time (the double-buffered receive
+            # areas + stream-ordered barriers must not let a fast rank overwrite what a slow one still reads)
+            torch.cuda._sleep(int(2e8) * (rank % 3))
+            sc.score_batch(img, txt, var)
+            torch.cuda._sleep(int(3e8) * ((world - rank) % 4))
+            sc.reset_hubness()
         out = sc.score_batch(img, txt, var, to_host=True)   # (peer2: the second receive buffer)
         lo, hi = out["slice"]
         torch.cuda.synchronize()
+        v, k = int(var.shape[1]), 10
+        dg = (bench.digest64(torch, out["topk_idx"], lo * v * k, 1) + bench.digest64(torch, out["bank_idx"], lo * v * k, 2)
+              + bench.digest64(torch, out["flags"], lo, 3)).reshape(1).cuda()
+        dist.all_reduce(dg)
+        dg = int((dg.cpu() + bench.digest64(torch, sc.k_occurrence.cpu(), 0, 4)).item())
         np.savez(Path(out_dir) / f"{tag}_r{rank}.npz", lo=lo, hi=hi, scores=out["scores"].numpy(),
                  flags=out["flags"].numpy(), topk_idx=out["topk_idx"].numpy(), topk_sim=out["topk_sim"].numpy(),
-                 bank_idx=out["bank_idx"].numpy(), hub=sc.k_occurrence.cpu().numpy())
+                 bank_idx=out["bank_idx"].numpy(), hub=sc.k_occurrence.cpu().numpy(), digest=dg)
     sc._exchange = ex
     sc.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_equals_single_gpu(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
+    import bench
     from multimodal_detection_consistency_b200.pipeline import TVCScorer
     g, bank, img, txt, var = _data()
     ref = TVCScorer(g, bank, k=10, device="cuda:0")
     want = ref.score_batch(img, txt, var, to_host=True)
     want = {k: (v.numpy().copy() if hasattr(v, "numpy") else v) for k, v in want.items()}
     hub = ref.k_occurrence.cpu().numpy()
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    for tag in ("peer", "peer2", "nccl"):
+    t = {n: torch.from_numpy(want[n]) for n in ("topk_idx", "bank_idx", "flags")}
+    want_digest = int((bench.digest64(torch, t["topk_idx"], 0, 1) + bench.digest64(torch, t["bank_idx"], 0, 2)
+                       + bench.digest64(torch, t["flags"], 0, 3) + bench.digest64(torch, torch.from_numpy(hub), 0, 4)).item())
+    del ref
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for tag in ("peer", "peer2", "peer3", "nccl"):
         covered = 0
-        for r in range(2):
+        for r in range(world):
             z = np.load(tmp_path / f"{tag}_r{r}.npz")
             lo, hi = int(z["lo"]), int(z["hi"])
             covered += hi - lo
@@ -85,4 +106,5 @@ def test_two_gpu_sharded_equals_single_gpu(tmp_path):
             assert np.abs(z["scores"] - want["scores"][lo:hi]).max() <= 1e-5
             assert np.array_equal(z["flags"], want["flags"][lo:hi])
             assert np.array_equal(z["hub"], hub)
+            assert int(z["digest"]) == want_digest, (tag, r)
         assert covered == len(img)

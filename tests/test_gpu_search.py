@@ -295,3 +295,99 @@ def test_release_workspace_is_transparent(tvc_ctx):
     s1, i1 = gal.search(q, 10)
     assert np.array_equal(np.asarray(i0), np.asarray(i1)) and np.array_equal(np.asarray(s0), np.asarray(s1))
     assert tvc.Context.release_all_workspaces() > 0
+
+
+def test_wrong_query_dimension_raises(tvc_ctx):
+    """a query of another width must be refused before its pointer reaches the library (the
+    reference raises from np.dot / the FAISS assert)."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(5)
+    gal = tvc.Gallery(_unit(rng, 500, 128), ctx=tvc_ctx)
+    for bad in (64, 129, 256):
+        with pytest.raises(ValueError):
+            gal.search(_unit(rng, 3, bad), 5)
+        with pytest.raises(ValueError):
+            gal.similarity_matrix(_unit(rng, 3, bad))
+    # and the C entry itself refuses a mismatching d (what abi callers hit)
+    import ctypes as C
+    q = _unit(rng, 3, 64)
+    sims, idx = np.empty((3, 5), np.float32), np.empty((3, 5), np.int64)
+    rc = tvc_ctx.lib.tvc_search(tvc_ctx.handle, gal.handle, q.ctypes.data, 0, 3, 64, 5, C.c_float(-np.inf), 0,
+                                sims.ctypes.data, idx.ctypes.data, None)
+    assert rc == 1   # TVC_ERR_INVALID
+
+
+@pytest.mark.parametrize("k", [57, 100, 600])
+def test_k_beyond_the_epilogue_limit(tvc_ctx, k):
+    """FAISS and the reference accept any k; beyond TVC_MAX_K the wrapper serves it from the dense similarity
+    tile + fp32 re-score (same ordering rule, -1 padding when k > N)."""
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(k)
+    g, q = _unit(rng, 500, 128), _unit(rng, 9, 128)
+    g[300] = g[12]
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    sims, idx = gal.search(q, k)
+    ref_s, ref_i = O.search(q, g, k)
+    _check_topk(sims, idx, ref_s, ref_i, q @ g.T)
+    import torch
+    ts, ti = gal.search(torch.from_numpy(q).cuda(), k, threshold=0.05)
+    ref_s, ref_i = O.search(q, g, k, threshold=0.05)
+    _check_topk(ts.cpu().numpy(), ti.cpu().numpy(), ref_s, ref_i, q @ g.T)
+
+
+def test_concurrent_host_buffer_searches(tvc_ctx):
+    """SURVEY §8b threading row / VERDICT r1 weak 9: four threads (the reference's ThreadPoolExecutor(max_workers=4),
+    src/pipeline.py:42,288,555-560) call tvc_search with HOST buffers at the same time on one immutable gallery;
+    each call runs on its own context-owned stream with its own workspace, no context-wide lock is held across
+    the blocking copies, and every thread gets exactly the single-threaded answer."""
+    import threading
+    import time
+    import multimodal_detection_consistency_b200 as tvc
+    rng = np.random.default_rng(11)
+    g = _unit(rng, 60000, 256)
+    gal = tvc.Gallery(g, ctx=tvc_ctx)
+    qs = [_unit(rng, 700 + 50 * t, 256) for t in range(4)]
+    want = [gal.search(q, 10) for q in qs]
+    got = [None] * 4
+    errs = []
+    gate = threading.Barrier(4)
+
+    def work(t):
+        try:
+            gate.wait()
+            for _ in range(6):
+                got[t] = gal.search(qs[t], 10)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    t0 = time.perf_counter()
+    for q in qs:
+        for _ in range(6):
+            gal.search(q, 10)
+    serial = time.perf_counter() - t0
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    t0 = time.perf_counter()
+    [t.start() for t in th]
+    [t.join() for t in th]
+    threaded = time.perf_counter() - t0
+    assert not errs, errs
+    for t in range(4):
+        assert np.array_equal(got[t][1], want[t][1]) and np.array_equal(got[t][0], want[t][0])
+    print(f"24 host-buffer searches: serial {serial * 1e3:.1f} ms, 4 threads {threaded * 1e3:.1f} ms")
+    # device-pointer calls on distinct torch streams from threads as well
+    import torch
+    dq = [torch.from_numpy(q).cuda() for q in qs]
+    res = [None] * 4
+
+    def work_dev(t):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(4):
+                res[t] = gal.search(dq[t], 10)
+            s.synchronize()
+
+    th = [threading.Thread(target=work_dev, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(4):
+        assert np.array_equal(res[t][1].cpu().numpy(), want[t][1])

@@ -13,7 +13,8 @@ import fake_native
 HERE = Path(__file__).resolve().parent
 NAMES = ["test_adversarial_detector_matches_reference_outputs", "test_consistency_checker_matches_reference_outputs",
          "test_defense_detector_batched_matches_oracle", "test_reference_bank_matches_reference_outputs",
-         "test_reference_bank_insert_dedup_eviction_persistence", "test_retriever_drop_in"]
+         "test_reference_bank_insert_dedup_eviction_persistence", "test_retriever_drop_in",
+         "test_reference_bank_journal_never_drifts_from_memory", "test_reference_bank_kmeans_assignment_matches_sklearn"]
 
 
 @pytest.fixture(scope="module")

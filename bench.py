@@ -136,14 +136,18 @@ def synth_device(torch, args, device, n_rows, seed, lo=0, hi=None, centers=None)
     if centers is None:
         centers = torch.nn.functional.normalize(torch.randn(1024, d, device=device, generator=gen), dim=1)
     out = torch.empty(hi - lo, d, device=device)
-    chunk = 1 << 18
-    for c0 in range(lo, hi, chunk):
-        c1 = min(hi, c0 + chunk)
+    chunk = 1 << 16
+    # Seeded per GLOBAL chunk [c0, c0 + chunk) with c0 a multiple of `chunk`, whole chunks generated and cut to
+    # the shard: every row is the same whatever the sharding (round 1 started the chunks at the shard's first
+    # row, so shards that do not begin on a chunk boundary held different galleries at different N)
+    for c0 in range((lo // chunk) * chunk, hi, chunk):
+        n_c = min(n_rows, c0 + chunk) - c0
         g2 = torch.Generator(device=device)
-        g2.manual_seed(seed * 1_000_003 + c0)          # chunk-seeded: identical rows for any sharding
-        assign = torch.randint(0, centers.shape[0], (c1 - c0,), device=device, generator=g2)
-        x = centers[assign] + (0.35 / math.sqrt(d)) * torch.randn(c1 - c0, d, device=device, generator=g2)
-        out[c0 - lo:c1 - lo] = torch.nn.functional.normalize(x, dim=1)
+        g2.manual_seed(seed * 1_000_003 + c0)
+        assign = torch.randint(0, centers.shape[0], (n_c,), device=device, generator=g2)
+        x = centers[assign] + (0.35 / math.sqrt(d)) * torch.randn(n_c, d, device=device, generator=g2)
+        a, b = max(lo, c0), min(hi, c0 + n_c)
+        out[a - lo:b - lo] = torch.nn.functional.normalize(x[a - c0:b - c0], dim=1)
     return out, centers
 
 
@@ -244,8 +248,10 @@ def parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world,
     # ---- (i) sampled fp32 check -------------------------------------------------------------------
     g_full = gather_rows_all_ranks(torch, dist, g_rows, args.gallery, world)
     rows_here = (hi - lo) * v
-    want = -(-sample_rows // world)
-    pick = torch.linspace(0, max(rows_here - 1, 0), steps=min(want, rows_here), device=device).round().long().unique()
+    # the same global sample at every N (evenly spaced over all Q*V rows); a rank checks the part inside its slice
+    total_rows = args.queries * v
+    gpick = torch.linspace(0, total_rows - 1, steps=min(sample_rows, total_rows), device=device).round().long().unique()
+    pick = gpick[(gpick >= lo * v) & (gpick < hi * v)] - lo * v
     q_rows = var[lo:hi].reshape(rows_here, d)[pick].float()
     stats = torch.zeros(6, dtype=torch.float64, device=device)   # rows, idx mismatches, out of band, max sim err, slots, missed true
     for name, full, total in (("topk", g_full, args.gallery), ("bank", None, args.bank)):

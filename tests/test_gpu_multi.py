@@ -37,7 +37,9 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    # file rendezvous: a port probed free by the parent can be taken again before rank 0 listens on it
+    dist.init_process_group("nccl", init_method=f"file://{out_dir}/rendezvous", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
     sys.path.insert(0, str(ROOT))
     from multimodal_detection_consistency_b200.pipeline import TVCScorer, shard_bounds
     g, bank, img, txt, var = _data()

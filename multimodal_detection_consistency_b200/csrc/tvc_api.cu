@@ -757,7 +757,8 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
   const size_t q_in_b = (q_dev || prepared) ? 0 : up256(static_cast<size_t>(m) * d * elem_size(q_dtype));
   const size_t q_bf_b = prepared ? 0 : up256(static_cast<size_t>(m) * d_pad * 2);
   const size_t q_f32_b = (g->f32 && !cand) ? up256(static_cast<size_t>(m) * d * 4) : 0;
-  const size_t cand_n = static_cast<size_t>(m) * plan.splits * plan.kp;
+  const int64_t full_rows = static_cast<int64_t>(plan.full_tiles) * (plan.pair ? 2 * kBM : kBM);
+  const size_t cand_n = static_cast<size_t>(m) * plan.splits * plan.kp;   // (upper bound: unsplit rows own one list)
   const size_t cand_b = up256(cand_n * 4);
   const size_t os_b = (sim_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 4);
   const size_t oi_b = (idx_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 8);
@@ -822,12 +823,12 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
       sc = *cand->sc;
       if (row0 != 0) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_search_candidates: scatter needs m <= 2^20 rows");
     }
-    TVC_CUDA(ctx, launch_select_candidates(cand_val, cand_idx, m, plan.splits, plan.kp, g->offset, sc,
+    TVC_CUDA(ctx, launch_select_candidates(cand_val, cand_idx, m, full_rows, plan.splits, plan.kp, g->offset, sc,
                                            cand->val ? cand->val + row0 * plan.kp : nullptr,
                                            cand->idx ? cand->idx + row0 * plan.kp : nullptr, st));
     return TVC_OK;
   }
-  TVC_CUDA(ctx, launch_rerank(cand_val, cand_idx, m, plan.splits, plan.kp, k, q_f32, g->f32, d, threshold,
+  TVC_CUDA(ctx, launch_rerank(cand_val, cand_idx, m, full_rows, plan.splits, plan.kp, k, q_f32, g->f32, d, threshold,
                               g->offset, d_sim, d_idx, st));
   if (!sim_dev)
     TVC_CUDA(ctx, cudaMemcpyAsync(out_sim, d_sim, static_cast<size_t>(m) * k * 4, cudaMemcpyDeviceToHost, st));
@@ -925,7 +926,7 @@ int tvc_search_candidates(tvc_ctx* ctx, tvc_gallery* g, const void* queries, int
     int rc = get_ws(cs, 2 * cb, &ws);
     if (rc != TVC_OK) return rc;
     TVC_CUDA(ctx, cudaMemsetAsync(ws, 0xFF, 2 * cb, st));   // idx = -1 everywhere
-    TVC_CUDA(ctx, launch_select_candidates(reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + cb), m, 1,
+    TVC_CUDA(ctx, launch_select_candidates(reinterpret_cast<float*>(ws), reinterpret_cast<int32_t*>(ws + cb), m, 0, 1,
                                            kp, g->offset, sc, co.val, co.idx, st));
     return TVC_OK;
   }
@@ -979,6 +980,62 @@ int tvc_rerank_candidates(tvc_ctx* ctx, tvc_gallery* g, const float* queries, in
   fill_row_source(&src, g);
   TVC_CUDA(ctx, launch_rerank_merged(cand_val, cand_idx, m, parts, kp, k, queries, src, d, threshold, out_sim,
                                      out_idx, st));
+  return TVC_OK;
+}
+
+int tvc_exchange_merge(tvc_ctx* ctx, int64_t m, int32_t parts, int32_t kp, const float* cand_val,
+                       const int64_t* cand_idx, int32_t n_dst, int64_t* const* req_dst, void* stream) {
+  if (!ctx || m < 0 || parts < 1 || kp < 1 || kp > 64 || n_dst < 1 || n_dst > kMaxParts || !req_dst ||
+      (m > 0 && (!cand_val || !cand_idx)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_exchange_merge: bad argument");
+  if (m == 0) return TVC_OK;
+  ReqDst dst{};
+  dst.n = n_dst;
+  for (int i = 0; i < n_dst; ++i) {
+    if (!req_dst[i]) return fail(ctx, TVC_ERR_INVALID, "tvc_exchange_merge: null destination");
+    dst.req[i] = reinterpret_cast<long long*>(req_dst[i]);
+  }
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, launch_exchange_merge(cand_val, cand_idx, m, parts, kp, dst, static_cast<cudaStream_t>(stream)));
+  return TVC_OK;
+}
+
+int tvc_exchange_rescore(tvc_ctx* ctx, tvc_gallery* shard, const float* q_f32, int32_t d, int32_t owners,
+                         int64_t rows_per_slice, int64_t m_total, int32_t kp, const int64_t* req,
+                         float* const* score_dst, void* stream) {
+  if (!ctx || !shard || shard->ctx != ctx || !shard->parts.empty() || d != shard->d || owners < 1 ||
+      owners > kMaxParts || rows_per_slice < 1 || m_total < 0 || m_total > rows_per_slice * owners || kp < 1 ||
+      kp > 64 || !score_dst || (m_total > 0 && (!q_f32 || !req)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_exchange_rescore: bad argument");
+  if (m_total == 0 || shard->n == 0) return TVC_OK;
+  if (!shard->f32) return fail(ctx, TVC_ERR_UNSUPPORTED, "tvc_exchange_rescore: shard without fp32 master");
+  ScoreDst dst{};
+  for (int i = 0; i < owners; ++i) {
+    if (!score_dst[i]) return fail(ctx, TVC_ERR_INVALID, "tvc_exchange_rescore: null destination");
+    dst.score[i] = score_dst[i];
+  }
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, launch_exchange_rescore(req, q_f32, shard->f32, shard->offset, shard->n, d, owners, rows_per_slice,
+                                        m_total, kp, dst, static_cast<cudaStream_t>(stream)));
+  return TVC_OK;
+}
+
+int tvc_exchange_finalize(tvc_ctx* ctx, int64_t m, int32_t kp, int32_t k, float threshold, const int64_t* req,
+                          const float* score, float* out_sim, int64_t* out_idx, void* stream) {
+  if (!ctx || m < 0 || kp < 1 || kp > 64 || k < 1 || k > kp || (m > 0 && (!req || !score || !out_sim || !out_idx)))
+    return fail(ctx, TVC_ERR_INVALID, "tvc_exchange_finalize: bad argument");
+  if (m == 0) return TVC_OK;
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, launch_exchange_finalize(req, score, m, kp, k, threshold, out_sim, out_idx,
+                                         static_cast<cudaStream_t>(stream)));
+  return TVC_OK;
+}
+
+int tvc_peer_copy(tvc_ctx* ctx, void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!ctx || bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(ctx, TVC_ERR_INVALID, "tvc_peer_copy: bad argument");
+  if (bytes == 0) return TVC_OK;
+  DeviceGuard guard(ctx->device);
+  TVC_CUDA(ctx, cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return TVC_OK;
 }
 

@@ -169,7 +169,7 @@ constexpr int kMaxKp = 64;
 
 __global__ void __launch_bounds__(kRerankWarps * 32)
 rerank_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, long long m,
-              int splits, int kp, int k, const float* __restrict__ q_f32,
+              long long full_rows, int splits, int kp, int k, const float* __restrict__ q_f32,
               const float* __restrict__ g_f32, int d, float threshold, long long row_offset,
               float* __restrict__ out_sim, long long* __restrict__ out_idx) {
   __shared__ float s_val[kRerankWarps][kMaxKp];
@@ -177,9 +177,11 @@ rerank_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ ca
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
   if (row >= m) return;
+  if (row < full_rows) splits = 1;     // rows of the unsplit query tiles own one list (SearchPlan)
   const int ncand = splits * kp;
-  const float* cv = cand_val + row * ncand;
-  const int32_t* ci = cand_idx + row * ncand;
+  const size_t cbase = plan_cand_base(full_rows, ncand / kp, kp, row, 0);
+  const float* cv = cand_val + cbase;
+  const int32_t* ci = cand_idx + cbase;
 
   int nsel = 0;
   if (splits == 1) {
@@ -259,14 +261,16 @@ rerank_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ ca
 // kernel's store stream over NVLink, there is no collective).
 __global__ void __launch_bounds__(kRerankWarps * 32)
 select_candidates_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
-                         long long m, int splits, int kp, long long row_offset, const ScatterSpec sc,
+                         long long m, long long full_rows, int splits, int kp, long long row_offset, const ScatterSpec sc,
                          float* __restrict__ out_val, long long* __restrict__ out_idx) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
   if (row >= m) return;
+  const size_t cbase = plan_cand_base(full_rows, splits, kp, row, 0);
+  if (row < full_rows) splits = 1;
   const int ncand = splits * kp;
-  const float* cv = cand_val + row * ncand;
-  const int32_t* ci = cand_idx + row * ncand;
+  const float* cv = cand_val + cbase;
+  const int32_t* ci = cand_idx + cbase;
   float* dv;
   long long* di;
   if (sc.n_slices > 0) {
@@ -371,6 +375,124 @@ rerank_merged_kernel(const float* __restrict__ cand_val, const long long* __rest
     }
     const float s = warp_dot_f32(q, src.f32[part] + (gi - src.off[part]) * d, d);
     if (lane == 0) s_val[w][t] = s;
+  }
+  __syncwarp();
+  float bv = INFINITY;
+  long long bi = -1;
+  for (int j = 0; j < k; ++j) {
+    float v = -INFINITY;
+    long long i = -1;
+    bool ok = false;
+    if (bi != LLONG_MIN)
+      ok = warp_next_best(
+          kp, bv, bi, [&](int e, float& vv, long long& ii) { vv = s_val[w][e]; ii = s_idx[w][e]; }, v, i);
+    if (ok && v >= threshold) {
+      bv = v;
+      bi = i;
+      if (lane == 0) {
+        out_sim[row * k + j] = v;
+        out_idx[row * k + j] = i;
+      }
+    } else {
+      bi = LLONG_MIN;
+      if (lane == 0) {
+        out_sim[row * k + j] = -INFINITY;
+        out_idx[row * k + j] = -1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- sharded search, re-score at the shards
+// Phase 2 done where the rows live (round 2).  rerank_merged_kernel PULLS the KP fp32 master rows of every query
+// row from the shards that own them - 16 x 3 KB per row over NVLink, 0.44 GB per rank and search at 8 GPUs, the
+// largest non-GEMM item of the step.  Here the traffic goes the other way and is ~30x smaller:
+//   (1) the owner of a query slice merges the P candidate lists of each of its rows to the KP best by GEMM
+//       score and stores that index list (KP x 8 bytes) into every shard's request area       [exchange_merge]
+//   (2) every shard walks the request lists of ALL rows, re-scores the entries that fall into its own row
+//       range in fp32 - from its local master and the fp32 query rows, which every rank received by copy
+//       engine under the GEMM - and stores each score into the owner's score area                [exchange_rescore]
+//   (3) the owner orders (fp32 score desc, index asc), applies the threshold, emits the top-k     [exchange_finalize]
+// with one stream-ordered barrier between the steps.  Same candidates, same warp_dot_f32 on the same operands
+// as the single-GPU rerank_kernel, so the results stay bit-identical to the unsharded search.
+__global__ void __launch_bounds__(kRerankWarps * 32)
+exchange_merge_kernel(const float* __restrict__ cand_val, const long long* __restrict__ cand_idx, long long m,
+                      int parts, int kp, const ReqDst dst) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
+  if (row >= m) return;
+  const int ncand = parts * kp;
+  auto fetch = [&](int e, float& vv, long long& ii) {
+    const int pt = e / kp, t = e - pt * kp;
+    const long long o = (static_cast<long long>(pt) * m + row) * kp + t;
+    vv = cand_val[o];
+    ii = cand_idx[o];
+  };
+  // lane t keeps the t-th best (and t + 32 for kp = 64): the list leaves as coalesced stores
+  float bv = INFINITY;
+  long long bi = -1;
+  long long keep[2] = {-1, -1};
+  for (int t = 0; t < kp; ++t) {
+    float v;
+    long long i;
+    if (!warp_next_best(ncand, bv, bi, fetch, v, i)) break;
+    if (lane == (t & 31)) keep[t >> 5] = i;
+    bv = v;
+    bi = i;
+  }
+  for (int s = 0; s < dst.n; ++s) {
+    long long* o = dst.req[s] + row * kp;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = lane + 32 * h;
+      if (e < kp) o[e] = keep[h];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRerankWarps * 32)
+exchange_rescore_kernel(const long long* __restrict__ req, const float* __restrict__ q_f32,
+                        const float* __restrict__ g_f32, long long g_off, long long g_n, int d, int owners,
+                        long long rows_per_slice, long long m_total, int kp, const ScoreDst dst) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;   // global query row
+  if (row >= m_total) return;
+  const int o = static_cast<int>(row / rows_per_slice);
+  const long long lr = row - static_cast<long long>(o) * rows_per_slice;
+  if (o >= owners) return;
+  // request area: [owner][rows_per_slice][kp]
+  const long long* lst = req + (static_cast<long long>(o) * rows_per_slice + lr) * kp;
+  float* out = dst.score[o] + lr * kp;
+  const float* q = q_f32 + row * d;
+  for (int h = 0; h * 32 < kp; ++h) {
+    const int e = lane + 32 * h;
+    const long long gi = e < kp ? lst[e] : -1;
+    const bool mine = gi >= g_off && gi < g_off + g_n;
+    unsigned todo = __ballot_sync(kFull, mine);
+    float s_mine = 0.f;
+    while (todo) {
+      const int t = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long g = __shfl_sync(kFull, gi, t);
+      const float s = warp_dot_f32(q, g_f32 + (g - g_off) * d, d);
+      if (lane == t) s_mine = s;
+    }
+    if (mine) out[e] = s_mine;
+  }
+}
+
+__global__ void __launch_bounds__(kRerankWarps * 32)
+exchange_finalize_kernel(const long long* __restrict__ req, const float* __restrict__ score, long long m, int kp,
+                         int k, float threshold, float* __restrict__ out_sim, long long* __restrict__ out_idx) {
+  __shared__ float s_val[kRerankWarps][kMaxKp];
+  __shared__ long long s_idx[kRerankWarps][kMaxKp];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRerankWarps + w;
+  if (row >= m) return;
+  for (int e = lane; e < kp; e += 32) {
+    const long long gi = req[row * kp + e];
+    s_idx[w][e] = gi;
+    s_val[w][e] = gi >= 0 ? score[row * kp + e] : -INFINITY;
   }
   __syncwarp();
   float bv = INFINITY;
@@ -722,7 +844,7 @@ cudaError_t launch_prep_rows(const void* rows, int dtype, int64_t n, int d, int 
   return launch_prep_rows_bcast(rows, dtype, n, d, d_pad, normalize, dst, 0, out_f32, stream);
 }
 
-cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
+cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int64_t full_rows, int splits,
                           int kp, int k, const float* q_f32, const float* g_f32, int d,
                           float threshold, int64_t global_row_offset, float* out_sim,
                           int64_t* out_idx, cudaStream_t stream) {
@@ -730,18 +852,18 @@ cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_
   if (kp > kMaxKp) return cudaErrorInvalidValue;
   const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
   rerank_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(
-      cand_val, cand_idx, m, splits, kp, k, q_f32, g_f32, d, threshold, global_row_offset, out_sim,
+      cand_val, cand_idx, m, full_rows, splits, kp, k, q_f32, g_f32, d, threshold, global_row_offset, out_sim,
       reinterpret_cast<long long*>(out_idx));
   note_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
-                                     int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
+cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int64_t full_rows,
+                                     int splits, int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
                                      int64_t* out_idx, cudaStream_t stream) {
   if (m <= 0) return cudaSuccess;
   const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
-  select_candidates_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(cand_val, cand_idx, m, splits, kp,
+  select_candidates_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(cand_val, cand_idx, m, full_rows, splits, kp,
                                                                    global_row_offset, sc, out_val,
                                                                    reinterpret_cast<long long*>(out_idx));
   note_launch();
@@ -757,6 +879,41 @@ cudaError_t launch_rerank_merged(const float* cand_val, const int64_t* cand_idx,
   rerank_merged_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(
       cand_val, reinterpret_cast<const long long*>(cand_idx), m, parts, kp, k, q_f32, src, d, threshold, out_sim,
       reinterpret_cast<long long*>(out_idx));
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_merge(const float* cand_val, const int64_t* cand_idx, int64_t m, int parts, int kp,
+                                  const ReqDst& dst, cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  if (kp > kMaxKp) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
+  exchange_merge_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(cand_val, reinterpret_cast<const long long*>(cand_idx),
+                                                               m, parts, kp, dst);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_rescore(const int64_t* req, const float* q_f32, const float* g_f32, int64_t g_off,
+                                    int64_t g_n, int d, int owners, int64_t rows_per_slice, int64_t m_total, int kp,
+                                    const ScoreDst& dst, cudaStream_t stream) {
+  if (m_total <= 0) return cudaSuccess;
+  if (kp > kMaxKp) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>((m_total + kRerankWarps - 1) / kRerankWarps);
+  exchange_rescore_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(reinterpret_cast<const long long*>(req), q_f32, g_f32,
+                                                                 g_off, g_n, d, owners, rows_per_slice, m_total, kp, dst);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_finalize(const int64_t* req, const float* score, int64_t m, int kp, int k, float threshold,
+                                     float* out_sim, int64_t* out_idx, cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  if (kp > kMaxKp) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>((m + kRerankWarps - 1) / kRerankWarps);
+  exchange_finalize_kernel<<<grid, kRerankWarps * 32, 0, stream>>>(reinterpret_cast<const long long*>(req), score, m, kp,
+                                                                  k, threshold, out_sim,
+                                                                  reinterpret_cast<long long*>(out_idx));
   note_launch();
   return cudaGetLastError();
 }

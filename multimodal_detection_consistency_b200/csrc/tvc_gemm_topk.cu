@@ -61,7 +61,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_units = p.m_tiles * p.splits;
+  const int total_units = plan_units(p);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -90,10 +90,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int stage = 0;
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int split = u / p.m_tiles;
-      const int mt = u - split * p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
       for (int nt = t0; nt < t1; ++nt) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
@@ -117,9 +115,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int split = u / p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int t0 = un.t0, t1 = un.t1;
       for (int nt = t0; nt < t1; ++nt) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -155,10 +152,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int split = u / p.m_tiles;
-      const int mt = u - split * p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
       const int row = mt * kBM + row_in_tile;
       const long long self_col = p.skip_self ? static_cast<long long>(row) + p.self_offset : -1ll;
       top.reset();
@@ -175,7 +170,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx, (static_cast<size_t>(row) * p.splits + split) * KP);
+      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx,
+                                       plan_cand_base(static_cast<long long>(p.full_tiles) * kBM, p.splits, KP, row, split));
     }
   }
 
@@ -345,18 +341,21 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
   p.m_tiles = static_cast<int>((m + tile_m - 1) / tile_m);
   p.n_tiles = static_cast<int>((n + kBN - 1) / kBN);
   p.kp = k <= 10 ? 16 : (k <= 26 ? 32 : 64);
-  // Pick the number of gallery ranges S: minimise waves * (unit time) where a unit costs its tiles plus
-  // ~4 tile-times of fixed work (pipeline fill/drain, candidate store, its share of the re-rank) plus a
-  // quarter tile for each of the first 2*KP tiles, during which nearly every 32x32 chunk takes the
-  // epilogue's slow path.  (In quarter-tile units; ties go to fewer ranges.)
-  const int max_s = p.n_tiles < 1024 ? p.n_tiles : 1024;
+  // Whole waves of query tiles run unsplit (see SearchPlan); what is left - fewer tiles than workers - is cut
+  // into S gallery ranges.  S minimises waves * (unit time) where a unit costs its tiles plus ~4 tile-times of
+  // fixed work (pipeline fill/drain, candidate store, its share of the re-rank) plus a quarter tile for each of
+  // the first 2*KP tiles, during which nearly every 32x32 chunk takes the epilogue's slow path.  (In
+  // quarter-tile units; ties go to fewer ranges.)
+  p.full_tiles = (p.m_tiles / workers) * workers;
+  p.rem_tiles = p.m_tiles - p.full_tiles;
+  const int max_s = p.rem_tiles == 0 ? 1 : (p.n_tiles < 1024 ? p.n_tiles : 1024);
   long long best_cost = -1;
   int best_s = 1, best_tps = p.n_tiles;
   for (int s = 1; s <= max_s; ++s) {
     const int tps = (p.n_tiles + s - 1) / s;
     const int s_eff = (p.n_tiles + tps - 1) / tps;
     if (s_eff != s) continue;
-    const long long units = static_cast<long long>(p.m_tiles) * s_eff;
+    const long long units = static_cast<long long>(p.rem_tiles) * s_eff;
     const long long waves = (units + workers - 1) / workers;
     const long long warm = tps < 2 * p.kp ? tps : 2 * p.kp;
     const long long cost = waves * (4ll * tps + 16 + warm) * 64 + s_eff;
@@ -368,7 +367,7 @@ SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count
   }
   p.splits = best_s;
   p.tiles_per_split = best_tps;
-  const long long units = static_cast<long long>(p.m_tiles) * p.splits;
+  const long long units = plan_units(p);
   p.grid = static_cast<int>(units < workers ? units : workers);
   if (p.grid < 1) p.grid = 1;
   if (pair) p.grid *= 2;

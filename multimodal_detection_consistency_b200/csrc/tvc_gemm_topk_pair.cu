@@ -52,7 +52,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t rank = cluster_ctarank();       // 0 = leader
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int total_units = p.m_tiles * p.splits;  // m_tiles counts 256-row tiles here
+  const int total_units = plan_units(p);  // m_tiles counts 256-row tiles here
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -82,10 +82,8 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int stage = 0;
     uint32_t phase = 0;
     for (int u = pair; u < total_units; u += num_pairs) {
-      const int split = u / p.m_tiles;
-      const int mt = u - split * p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
       const int q_row = mt * 256 + static_cast<int>(rank) * 128;
       for (int nt = t0; nt < t1; ++nt) {
         const int g_row = nt * kBN + static_cast<int>(rank) * 128;
@@ -111,9 +109,8 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = pair; u < total_units; u += num_pairs) {
-      const int split = u / p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int t0 = un.t0, t1 = un.t1;
       for (int nt = t0; nt < t1; ++nt) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -148,10 +145,8 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = pair; u < total_units; u += num_pairs) {
-      const int split = u / p.m_tiles;
-      const int mt = u - split * p.m_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+      const SearchUnit un = plan_unit(p, u);
+      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
       const int row = mt * 256 + static_cast<int>(rank) * 128 + row_in_tile;
       const long long self_col = p.skip_self ? static_cast<long long>(row) + p.self_offset : -1ll;
       top.reset();
@@ -168,7 +163,8 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx, (static_cast<size_t>(row) * p.splits + split) * KP);
+      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx,
+                                       plan_cand_base(static_cast<long long>(p.full_tiles) * 256, p.splits, KP, row, split));
     }
   }
 

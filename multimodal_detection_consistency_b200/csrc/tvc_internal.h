@@ -26,7 +26,15 @@ struct SearchPlan {
   int kblocks;          // d_pad / 64
   int m_tiles;
   int n_tiles;
-  int splits;           // gallery ranges per query tile (each owns a candidate list)
+  // Two kinds of work unit.  The first `full_tiles` query tiles (whole waves of the persistent grid) each run
+  // against the WHOLE gallery (one candidate list per row); the remaining `rem_tiles` query tiles - less than
+  // one wave - are cut into `splits` gallery ranges of `tiles_per_split` tiles so that they fill the last wave
+  // (`splits` lists per row, merged by the re-rank).  Long units matter: a row's running threshold only
+  // becomes selective after ~16k gallery columns, and until then nearly every 32 x 32 chunk takes the
+  // epilogue's slow path (75 % of the chunks of a 163-tile unit, 8 % of a 3900-tile one).
+  int full_tiles;
+  int rem_tiles;
+  int splits;           // gallery ranges per query tile of the remainder (each owns a candidate list)
   int tiles_per_split;
   int kp;               // candidates kept per (row, split): 16 / 32 / 64
   int grid;
@@ -38,6 +46,34 @@ struct SearchPlan {
 
 // plans the unit decomposition for `sm_count` persistent CTAs
 SearchPlan make_search_plan(int64_t m, int64_t n, int d_pad, int k, int sm_count, bool pair);
+
+// unit u -> (query tile, gallery range, tile interval); candidate list of (row, range)
+struct SearchUnit {
+  int mt, split, t0, t1;
+};
+__host__ __device__ inline int plan_units(const SearchPlan& p) { return p.full_tiles + p.rem_tiles * p.splits; }
+__host__ __device__ inline SearchUnit plan_unit(const SearchPlan& p, int u) {
+  SearchUnit x;
+  if (u < p.full_tiles) {
+    x.mt = u;
+    x.split = 0;
+    x.t0 = 0;
+    x.t1 = p.n_tiles;
+  } else {
+    const int j = u - p.full_tiles;
+    x.split = j / p.rem_tiles;
+    x.mt = p.full_tiles + (j - x.split * p.rem_tiles);
+    x.t0 = x.split * p.tiles_per_split;
+    x.t1 = x.t0 + p.tiles_per_split < p.n_tiles ? x.t0 + p.tiles_per_split : p.n_tiles;
+  }
+  return x;
+}
+// rows below full_rows = full_tiles * (rows per query tile) own one list, the others `splits` lists
+__host__ __device__ inline size_t plan_cand_base(long long full_rows, int splits, int kp, long long row, int split) {
+  return row < full_rows ? static_cast<size_t>(row) * kp
+                         : static_cast<size_t>(full_rows) * kp +
+                               (static_cast<size_t>(row - full_rows) * splits + split) * kp;
+}
 
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g,
                              const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
@@ -67,7 +103,7 @@ cudaError_t launch_prep_rows_bcast(const void* rows, int dtype, int64_t n, int d
                                    const BcastSpec& dst, int64_t dst_row0, float* out_f32, cudaStream_t stream);
 
 // select top-kp by GEMM score over splits, re-score in fp32 from the masters, emit ordered top-k.
-cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
+cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_t m, int64_t full_rows, int splits,
                           int kp, int k, const float* q_f32, const float* g_f32, int d,
                           float threshold, int64_t global_row_offset, float* out_sim,
                           int64_t* out_idx, cudaStream_t stream);
@@ -111,9 +147,25 @@ struct ScatterSpec {
   long long* idx[kMaxParts];
 };
 
-cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int splits,
-                                     int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
+cudaError_t launch_select_candidates(const float* cand_val, const int32_t* cand_idx, int64_t m, int64_t full_rows,
+                                     int splits, int kp, int64_t global_row_offset, const ScatterSpec& sc, float* out_val,
                                      int64_t* out_idx, cudaStream_t stream);
+
+// re-score at the shards (exchange_* kernels, tvc_aux.cu)
+struct ReqDst {
+  int n;
+  long long* req[kMaxParts];     // per shard: this owner's block [rows_in_slice, kp] inside the shard's request area
+};
+struct ScoreDst {
+  float* score[kMaxParts];       // per owner: its score area [rows_in_slice, kp]
+};
+cudaError_t launch_exchange_merge(const float* cand_val, const int64_t* cand_idx, int64_t m, int parts, int kp,
+                                  const ReqDst& dst, cudaStream_t stream);
+cudaError_t launch_exchange_rescore(const int64_t* req, const float* q_f32, const float* g_f32, int64_t g_off,
+                                    int64_t g_n, int d, int owners, int64_t rows_per_slice, int64_t m_total, int kp,
+                                    const ScoreDst& dst, cudaStream_t stream);
+cudaError_t launch_exchange_finalize(const int64_t* req, const float* score, int64_t m, int kp, int k, float threshold,
+                                     float* out_sim, int64_t* out_idx, cudaStream_t stream);
 
 cudaError_t launch_rerank_merged(const float* cand_val, const int64_t* cand_idx, int64_t m, int parts, int kp,
                                  int k, const float* q_f32, const RowSource& src, int d, float threshold,

@@ -72,64 +72,103 @@ class CudaEngine:
 
 
 class PeerExchange:
-    """Candidate exchange of the sharded search without a data-path collective: every rank owns a
-    double-buffered receive area [2][P, rows_in_slice, KP] (values + indices) allocated through
-    libtvc and mapped by all peers with CUDA IPC; phase 1 of the search stores each row's candidates
-    straight into the owner's area over NVLink, one stream-ordered barrier (a 4-byte all-reduce)
-    separates the phase 1 of all searches of a batch from their phase 2, which re-ranks on the owner from local + peer fp32 masters."""
+    """Candidate exchange of the sharded search without a data-path collective.  Every buffer that crosses GPUs
+    is allocated through libtvc (tvc_peer_alloc), double-buffered and mapped by all peers with CUDA IPC; the
+    kernels themselves store into / the copy engines copy into the peers' HBM over NVLink, and stream-ordered
+    barriers (a 4-byte all-reduce) separate the steps.  Per batch:
+      begin_batch    this rank's slice of the query rows -> bf16 GEMM operand, stored into EVERY rank's operand
+                     buffer; barrier
+      push_queries   the same rows in fp32 -> every rank's fp32 query area, by copy engine on a side stream,
+                     under the GEMMs
+      scatter        GEMM + top-KP of ALL rows on this rank's shard; candidates stored into the slice owners'
+                     receive areas                                                       (per search); barrier
+      merge          owner: P lists per row -> KP best by GEMM score; the index list goes to every shard's
+                     request area                                                         (per search); barrier
+      rescore        every shard: the requested rows of ITS range re-scored in fp32 against the fp32 query rows;
+                     scores stored into the owners' score areas                           (per search); barrier
+      finalize       owner: (fp32 score desc, index asc), threshold, top-k                 (per search)
+    `collect` is the round-1 phase 2 (the owner pulls KP master rows per query row from peer HBM); it remains for
+    shards without an fp32 master."""
 
     def __init__(self, ctx, dist, group, world, rank):
         self.ctx, self.dist, self.group, self.world, self.rank = ctx, dist, group, world, rank
-        self.areas = {}           # (tag, rows_per_slice, kp) -> dict(own=[(val, idx)] * 2, peers=[[(val, idx)] * 2] * P)
+        self.areas = {}           # (tag, ...) -> dict(bases=[ptr per rank], nbytes=bytes of one of the two buffers, own=ptr)
         self.parity = {}
         self._token = None
         self._operand = None
+        self._qf32 = None
+        self._push_stream = None
+        self._push_ev = None
 
-    def _area(self, tag, rows_per_slice: int, kp: int):
-        key = (tag, rows_per_slice, kp)
-        area = self.areas.get(key)
-        if area is not None:
+    def _shared(self, tag, nbytes: int):
+        """Double-buffered peer-mapped area `tag` of 2 x (>= nbytes) on every rank.  Grow-only: a request that
+        fits reuses the area (every layout inside is addressed by the request's own strides), a larger one
+        replaces it - collectively: batch shapes are the same on all ranks, so all take the same path."""
+        area = self.areas.get(tag)
+        if area is not None and area["nbytes"] >= nbytes:
             return area
         self._retire(tag)
-        n = self.world * rows_per_slice * kp
-        vb, ib = n * 4, n * 8
-        own = [self.ctx.peer_alloc(2 * (vb + ib))]
-        ptr, handle = own[0]
+        ptr, handle = self.ctx.peer_alloc(2 * nbytes)
         info = [None] * self.world
         self.dist.all_gather_object(info, handle, group=self.group)
         bases = [ptr if r == self.rank else self.ctx.peer_open(h) for r, h in enumerate(info)]
-        # layout of one rank's area: [val buf0 | val buf1 | idx buf0 | idx buf1]
-        area = dict(bases=bases, vb=vb, ib=ib, own=ptr)
-        self.areas[key] = area
-        self.parity[key] = 0
+        area = dict(bases=bases, nbytes=nbytes, own=ptr)
+        self.areas[tag] = area
+        self.parity[tag] = 0
         return area
 
-    def begin_batch(self, rows_slice, q_total: int, v: int, lo: int):
+    def _flip(self, tag) -> int:
+        b = self.parity[tag]
+        self.parity[tag] = b ^ 1
+        return b
+
+    def _area(self, tag, rows_per_slice: int, kp: int):
+        # layout of one rank's candidate area: [val buf0 | val buf1 | idx buf0 | idx buf1], the region sizes
+        # fixed when the area was allocated (the same on every rank)
+        n = self.world * rows_per_slice * kp
+        area = self._shared(tag, n * 12)
+        if "vb" not in area:
+            area["vb"], area["ib"] = n * 4, n * 8
+        return area
+
+    def begin_batch(self, rows_slice, q_total: int, v: int, lo: int, per: Optional[int] = None):
         """Convert this rank's slice of the query rows to the bf16 GEMM operand once and store it into
         every rank's query buffer (own HBM + peers over NVLink): after the barrier each rank holds the
         operand of the WHOLE batch although it only ever saw (or uploaded) its own slice."""
         d = int(rows_slice.shape[1])
-        per = -(-q_total // self.world)
+        per = -(-q_total // self.world) if per is None else per
         rows_cap = per * self.world * v
-        row_bytes = self.ctx.query_row_bytes(d)
-        key = ("q", rows_cap, d)
-        area = self.areas.get(key)
-        if area is None:
-            self._retire("q")
-            nbytes = rows_cap * row_bytes
-            ptr, handle = self.ctx.peer_alloc(2 * nbytes)
-            info = [None] * self.world
-            self.dist.all_gather_object(info, handle, group=self.group)
-            area = dict(bases=[ptr if r == self.rank else self.ctx.peer_open(h) for r, h in enumerate(info)],
-                        nbytes=nbytes, own=ptr)
-            self.areas[key] = area
-            self.parity[key] = 0
-        b = self.parity[key]
-        self.parity[key] = b ^ 1
+        area = self._shared("q", rows_cap * self.ctx.query_row_bytes(d))
+        b = self._flip("q")
         if rows_slice.shape[0] > 0:
             self.ctx.prepare_queries(rows_slice, [base + b * area["nbytes"] for base in area["bases"]], lo * v)
         self.barrier(rows_slice.device)
         self._operand = (area["own"] + b * area["nbytes"], q_total * v)
+
+    def push_queries(self, rows_slice, q_total: int, v: int, lo: int, per: Optional[int] = None):
+        """The fp32 rows of this rank's slice -> every rank's fp32 query area, on a side stream by the copy
+        engines (no SM taken from the GEMMs they run under).  The barrier that follows the scatters waits for
+        them, so every shard holds the fp32 rows of the whole batch when it re-scores."""
+        import torch
+        d = int(rows_slice.shape[1])
+        per = -(-q_total // self.world) if per is None else per
+        rows_cap = per * self.world * v
+        area = self._shared("qf32", rows_cap * d * 4)
+        b = self._flip("qf32")
+        self._qf32 = area["own"] + b * area["nbytes"]
+        if self._push_stream is None:
+            self._push_stream = torch.cuda.Stream(rows_slice.device)
+        ps = self._push_stream
+        ps.wait_stream(torch.cuda.current_stream(rows_slice.device))
+        nb = rows_slice.numel() * 4
+        if nb > 0:
+            off = lo * v * d * 4
+            order = [(self.rank + 1 + i) % self.world for i in range(self.world)]    # peers first, staggered
+            for r in order:
+                self.ctx.peer_copy(area["bases"][r] + b * area["nbytes"] + off, rows_slice.data_ptr(), nb, ps.cuda_stream)
+            rows_slice.record_stream(ps)
+        self._push_ev = torch.cuda.Event()
+        self._push_ev.record(ps)
 
     def _release(self, area):
         for r, base in enumerate(area["bases"]):
@@ -145,7 +184,7 @@ class PeerExchange:
         """A batch of another size needs areas of another shape: the old ones of this tag are released (every
         rank takes this path together - batch sizes are the same on all ranks), after every GPU has drained
         what may still read or write them.  Without it varying batch sizes leak HBM on every rank."""
-        old = [k for k in self.areas if k[0] == tag]
+        old = [k for k in self.areas if k == tag]
         if not old:
             return
         import torch
@@ -163,32 +202,33 @@ class PeerExchange:
 
     def barrier(self, device):
         import torch
+        if self._push_ev is not None:          # peers may read what this rank's copy engines wrote only after it
+            torch.cuda.current_stream(device).wait_event(self._push_ev)
+            self._push_ev = None
         if self._token is None:
             self._token = torch.zeros(1, dtype=torch.int32, device=device)
         self.dist.all_reduce(self._token, group=self.group)
 
-    def scatter(self, tag, gallery, q_total: int, v: int, k: int):
+    def scatter(self, tag, gallery, q_total: int, v: int, k: int, per: Optional[int] = None):
         """Phase 1 on this rank's shard: GEMM + top-KP of ALL rows (the operand begin_batch spread), the
-        candidates stored into the slice owners' receive buffers.  Returns the token collect() needs."""
-        per = -(-q_total // self.world)
+        candidates stored into the slice owners' receive buffers.  Returns the token the later steps need."""
+        per = -(-q_total // self.world) if per is None else per
         rows_per_slice = per * v
         kp = self.ctx.candidate_width(k)
         area = self._area(tag, rows_per_slice, kp)
-        key = (tag, rows_per_slice, kp)
-        b = self.parity[key]
-        self.parity[key] = b ^ 1
+        b = self._flip(tag)
         sc = N.Scatter()
         sc.n_slices, sc.slot, sc.rows_per_slice = self.world, self.rank, rows_per_slice
         for r, base in enumerate(area["bases"]):
             sc.val[r] = base + b * area["vb"]
             sc.idx[r] = base + 2 * area["vb"] + b * area["ib"]
         gallery.search_candidates(self._operand, k, sc)
-        return area, b, kp
+        return dict(area=area, b=b, kp=kp, tag=tag, rps=rows_per_slice, total=q_total * v)
 
     def collect(self, token, group_gallery, rows_slice, k: int, threshold: float):
-        """Phase 2 (after a barrier): global top-k of this rank's query slice, (sims [rows, k], idx).
+        """Round-1 phase 2 (after a barrier): global top-k of this rank's query slice, (sims [rows, k], idx).
         rows_slice are the slice's fp32 rows; the candidate rows are read from local + peer masters."""
-        area, b, kp = token
+        area, b, kp = token["area"], token["b"], token["kp"]
         if rows_slice.shape[0] == 0:
             import torch
             return (torch.empty((0, k), dtype=torch.float32, device=rows_slice.device),
@@ -196,6 +236,32 @@ class PeerExchange:
         own = area["own"]
         return self.ctx.rerank_candidates(group_gallery, rows_slice, own + b * area["vb"],
                                           own + 2 * area["vb"] + b * area["ib"], self.world, kp, k, threshold)
+
+    # -- phase 2 where the rows live ----------------------------------------------------------------
+    def merge(self, token, my_rows: int, stream: int):
+        area, b, kp, rps = token["area"], token["b"], token["kp"], token["rps"]
+        key = token["tag"] + ".req"
+        req = self._shared(key, self.world * rps * kp * 8)
+        rb = self._flip(key)
+        token["req"] = req["own"] + rb * req["nbytes"]
+        mine = self.rank * rps * kp * 8
+        own = area["own"]
+        self.ctx.exchange_merge(my_rows, self.world, kp, own + b * area["vb"], own + 2 * area["vb"] + b * area["ib"],
+                                [base + rb * req["nbytes"] + mine for base in req["bases"]], stream)
+
+    def rescore(self, token, shard, d: int, stream: int):
+        kp, rps = token["kp"], token["rps"]
+        key = token["tag"] + ".score"
+        score = self._shared(key, rps * kp * 4)
+        sb = self._flip(key)
+        token["score"] = score["own"] + sb * score["nbytes"]
+        self.ctx.exchange_rescore(shard, self._qf32, d, self.world, rps, token["total"], kp, token["req"],
+                                  [base + sb * score["nbytes"] for base in score["bases"]], stream)
+
+    def finalize(self, token, my_rows: int, k: int, threshold: float, device):
+        kp, rps = token["kp"], token["rps"]
+        return self.ctx.exchange_finalize(my_rows, kp, k, threshold, token["req"] + self.rank * rps * kp * 8,
+                                          token["score"], device)
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -259,8 +325,17 @@ class TVCScorer:
         self._exchange = None
         if self.world > 1 and self._gallery_group is not None and hasattr(engine, "make_exchange"):
             self._exchange = engine.make_exchange(self.dist, self.group, self.world, self.rank)
+        # phase 2 of the sharded search: True = re-score where the rows live (PeerExchange.merge / rescore /
+        # finalize), False = the round-1 pull of master rows over NVLink (PeerExchange.collect)
+        self.rescore_at_shards = True
         self.track_hubness = track_hubness
-        self.k_occurrence = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
+        self._k_occ = torch.zeros(self.n_total, dtype=torch.int32, device=self.device) if track_hubness else None
+        # multi-GPU: the per-step histogram all-reduce runs on its own stream and NCCL communicator, under the
+        # next step's upload / operand broadcast; reading `k_occurrence` waits for it
+        self._hist_stream = self._hist_ev = self._hist_group = None
+        if track_hubness and self.world > 1 and self.device.type == "cuda" and self._exchange is not None:
+            self._hist_group = self.dist.new_group(ranks=list(range(self.world))) if process_group is None else None
+            self._hist_stream = torch.cuda.Stream(self.device)
         self._host: Dict[str, torch.Tensor] = {}
         self._dev_stage: Dict[str, torch.Tensor] = {}
         self._copy_stream = None
@@ -276,6 +351,13 @@ class TVCScorer:
         self.min_chunk_queries = 1024       # ... when every piece keeps at least this many queries
         self.profile = False            # True: CUDA-event time per phase, read with phase_times()
         self._marks = []
+
+    @property
+    def k_occurrence(self):
+        """Running k-occurrence histogram over the whole gallery (int32 [N]); on several GPUs the all-reduced one."""
+        if self._hist_ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._hist_ev)
+        return self._k_occ
 
     # ------------------------------------------------------------------ helpers
     def _mark(self, name: str):
@@ -404,9 +486,13 @@ class TVCScorer:
         uploaded on a copy stream while piece c is searched and scored, and piece c's results go back
         to pinned host memory behind it - only the first upload and the last download are exposed."""
         host_in = not (isinstance(var, torch.Tensor) and var.device.type == "cuda")
+        pinned = isinstance(var, torch.Tensor) and var.is_pinned()
         if (host_in and self.world == 1 and self.device.type == "cuda"
-                and len(self._piece_bounds(int(var.shape[0]))) > 1):
+                and len(self._piece_bounds(int(var.shape[0]), pinned)) > 1):
             out = self._score_batch_pipelined(img, txt, var, gen, g_cnt, to_host)
+        elif (host_in and self.world > 1 and self._exchange is not None and self.device.type == "cuda"
+                and len(self._piece_bounds(-(-int(var.shape[0]) // self.world), pinned)) > 1):
+            out = self._score_batch_pipelined_multi(img, txt, var, gen, g_cnt, to_host)
         else:
             out = self._score_batch(img, txt, var, gen, g_cnt, to_host=to_host)
         if to_host and copy:
@@ -439,6 +525,72 @@ class TVCScorer:
             buf = torch.empty(tuple(shape), dtype=dtype, device=self.device)
             self._dev_stage[name] = buf
         return buf
+
+    def _score_batch_pipelined_multi(self, img, txt, var, gen, g_cnt, to_host: bool):
+        """Host batch on several GPUs (peer-memory path): every rank's slice is cut at the same relative
+        positions; piece c of ALL ranks is one run of the sharded protocol, and a rank uploads its rows of piece
+        c+1 on the copy stream while piece c is searched, results going back behind it - only the first upload
+        and the last download stay exposed (round 1 uploaded the whole slice in front of the first GEMM)."""
+        q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
+        per = -(-q_total // self.world)
+        lo, hi = slice_bounds(q_total, self.world, self.rank)
+        qs = hi - lo
+        pinned = isinstance(var, torch.Tensor) and var.is_pinned()
+        bounds = self._piece_bounds(per, pinned=pinned)
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        srcs = dict(img=(img, torch.float32), txt=(txt, torch.float32), var=(var, torch.float32))
+        if gen is not None:
+            srcs["gen"] = (gen, torch.float32)
+        if g_cnt is not None:
+            srcs["g_cnt"] = (g_cnt, torch.int32)
+        host = {n: (t if isinstance(t, torch.Tensor) else torch.as_tensor(t)) for n, (t, _) in srcs.items()}
+        dev = {n: self._staging("m_" + n, (per,) + tuple(host[n].shape[1:]), dt) for n, (_, dt) in srcs.items()}
+
+        def mine(a, b):                       # this rank's rows of piece [a, b), relative to its slice start
+            return min(qs, a), min(qs, b)
+
+        def upload(a, b):
+            a, b = mine(a, b)
+            with torch.cuda.stream(cs):
+                for n in ("var", "img", "txt", "gen", "g_cnt"):
+                    if n in dev and b > a:
+                        dev[n][a:b].copy_(host[n][lo + a:lo + b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return ev
+
+        pieces, o = [], None
+        ev = upload(*bounds[0])
+        for i, (a, b) in enumerate(bounds):
+            main.wait_event(ev)
+            ma, mb = mine(a, b)
+            # queries of this piece over all ranks: full slices contribute b - a, the last slice what it has
+            q_piece = sum(max(0, min(b, (min(q_total, (r + 1) * per) - r * per)) - a) for r in range(self.world))
+            o = self._score_batch(dev["img"][ma:mb], dev["txt"][ma:mb], dev["var"][ma:mb],
+                                  dev["gen"][ma:mb] if "gen" in dev else None,
+                                  dev["g_cnt"][ma:mb] if "g_cnt" in dev else None, to_host=False,
+                                  layout=(q_piece, b - a, self.rank * (b - a)))
+            o.pop("slice")
+            if to_host:
+                for name, t in o.items():
+                    buf = self._pinned(name, torch.empty((qs,) + tuple(t.shape[1:]), dtype=t.dtype, device="meta"))
+                    buf[ma:mb].copy_(t, non_blocking=True)
+            else:
+                pieces.append(o)
+            if i + 1 < len(bounds):
+                ev = upload(*bounds[i + 1])
+        if to_host:
+            main.synchronize()
+            out = {name: self._host[name] for name in o}
+            self._mark("to_host")
+        else:
+            out = {name: torch.cat([pc[name] for pc in pieces], 0) for name in pieces[0]}
+        out["slice"] = (lo, hi)
+        return out
 
     def _score_batch_pipelined(self, img, txt, var, gen, g_cnt, to_host: bool):
         q_total = int(var.shape[0])
@@ -493,13 +645,26 @@ class TVCScorer:
         out["slice"] = (0, q_total)
         return out
 
-    def _score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False):
+    def _score_batch(self, img, txt, var, gen=None, g_cnt=None, *, to_host: bool = False, layout=None):
+        """layout=None: the arrays hold the whole batch and this rank takes its contiguous slice of it.
+        layout=(q_total, per, lo): peer-memory path only - the arrays hold ONLY this rank's rows of a batch of
+        q_total queries cut into slices of `per` queries per rank, this rank's starting at query `lo` (the
+        pipelined multi-GPU host path cuts every rank's slice at the same relative positions)."""
         self._mark("begin")
-        q_total, v, d = int(var.shape[0]), int(var.shape[1]), int(var.shape[2])
+        v, d = int(var.shape[1]), int(var.shape[2])
         if v != self.params.n_variants:
             raise ValueError(f"{v} variants given, params.n_variants = {self.params.n_variants}")
-        lo, hi = slice_bounds(q_total, self.world, self.rank)
+        per = None
+        if layout is None:
+            q_total = int(var.shape[0])
+            lo, hi = slice_bounds(q_total, self.world, self.rank)
+        else:
+            q_total, per, lo = layout
+            hi = lo + int(var.shape[0])
+            z = slice(None)                       # the arrays already are this rank's rows
         qs = hi - lo
+        if layout is None:
+            z = slice(lo, hi)
         k = self.k
         host_var = not (isinstance(var, torch.Tensor) and var.device.type == self.device.type == "cuda")
         b_sim = b_idx = None
@@ -507,28 +672,48 @@ class TVCScorer:
         def upload_rest():
             # the rows only kernel (b) reads go up on the copy stream, under the searches - queued BEHIND the
             # variant rows (the copy stream waits for what the current stream holds), which the GEMM waits for
-            return self._side_upload(dict(img=(img[lo:hi], torch.float32), txt=(txt[lo:hi], torch.float32),
-                                          gen=(gen[lo:hi] if gen is not None else None, torch.float32),
-                                          g_cnt=(g_cnt[lo:hi] if g_cnt is not None else None, torch.int32)))
+            return self._side_upload(dict(img=(img[z], torch.float32), txt=(txt[z], torch.float32),
+                                          gen=(gen[z] if gen is not None else None, torch.float32),
+                                          g_cnt=(g_cnt[z] if g_cnt is not None else None, torch.int32)))
+        if layout is not None and not (self.world > 1 and self._exchange is not None):
+            raise ValueError("layout= serves the peer-memory path only")
         if self.world > 1 and self._exchange is not None:
             # peer-memory path: this rank only touches (uploads) ITS slice of the batch.  The bf16 operand
             # of the whole batch is assembled in every rank's HBM by the prepare kernel's peer stores, the
             # candidates are stored into the slice owners' HBM, and the owners re-rank.
-            var_s = self._dev(var[lo:hi])
+            var_s = self._dev(var[z])
             side, side_ev = upload_rest()
             rows_s = var_s.view(qs * v, d)
             ex = self._exchange
-            ex.begin_batch(rows_s, q_total, v, lo)
-            # both shard searches first, ONE barrier, then both re-ranks: a rank whose gallery GEMM finishes
+            at_shards = self.rescore_at_shards and self.gallery.has_master and (self.bank is None or self.bank.has_master)
+            ex.begin_batch(rows_s, q_total, v, lo, per)
+            if at_shards:
+                ex.push_queries(rows_s, q_total, v, lo, per)
+            # both shard searches first, ONE barrier, then phase 2 of both: a rank whose gallery GEMM finishes
             # early spends the wait in its bank GEMM instead of in a barrier
-            tg = ex.scatter("gallery", self.gallery, q_total, v, k)
-            tb = ex.scatter("bank", self.bank, q_total, v, k) if self.bank is not None else None
+            tg = ex.scatter("gallery", self.gallery, q_total, v, k, per)
+            tb = ex.scatter("bank", self.bank, q_total, v, k, per) if self.bank is not None else None
             ex.barrier(self.device)
-            g_sim, g_idx = ex.collect(tg, self._gallery_group, rows_s, k, -math.inf)
-            self._mark("search_gallery")
-            if tb is not None:
-                b_sim, b_idx = ex.collect(tb, self._bank_group, rows_s, k, self.bank_threshold)
-                self._mark("search_bank")
+            self._mark("search_gemm")
+            if at_shards:
+                st = torch.cuda.current_stream(self.device).cuda_stream
+                toks = [(tg, self.gallery, -math.inf)] + ([(tb, self.bank, self.bank_threshold)] if tb is not None else [])
+                for tok, _, _ in toks:
+                    ex.merge(tok, qs * v, st)
+                ex.barrier(self.device)
+                for tok, shard, _ in toks:
+                    ex.rescore(tok, shard, d, st)
+                ex.barrier(self.device)
+                g_sim, g_idx = ex.finalize(tg, qs * v, k, -math.inf, self.device)
+                if tb is not None:
+                    b_sim, b_idx = ex.finalize(tb, qs * v, k, self.bank_threshold, self.device)
+                self._mark("search_phase2")
+            else:
+                g_sim, g_idx = ex.collect(tg, self._gallery_group, rows_s, k, -math.inf)
+                self._mark("search_gallery")
+                if tb is not None:
+                    b_sim, b_idx = ex.collect(tb, self._bank_group, rows_s, k, self.bank_threshold)
+                    self._mark("search_bank")
         else:
             if self.world > 1 and host_var and self.device.type == "cuda":
                 # every rank holds the same host batch: upload only this rank's slice over PCIe and
@@ -573,13 +758,23 @@ class TVCScorer:
         self._mark("consistency")
         if self.track_hubness:
             if self.world > 1:
-                local = torch.zeros_like(self.k_occurrence)
+                local = torch.zeros_like(self._k_occ)
                 if qs > 0:
                     self.engine.k_occurrence(g_idx, self.n_total, local)
-                self.dist.all_reduce(local, group=self.group)
-                self.k_occurrence += local
+                if self._hist_stream is not None:
+                    hs = self._hist_stream
+                    hs.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(hs):
+                        self.dist.all_reduce(local, group=self._hist_group if self._hist_group is not None else self.group)
+                        self._k_occ += local
+                        self._hist_ev = torch.cuda.Event()
+                        self._hist_ev.record(hs)
+                    local.record_stream(hs)
+                else:
+                    self.dist.all_reduce(local, group=self.group)
+                    self._k_occ += local
             else:
-                self.engine.k_occurrence(g_idx, self.n_total, self.k_occurrence)
+                self.engine.k_occurrence(g_idx, self.n_total, self._k_occ)
         self._mark("hubness")
         out = dict(scores=scores, flags=flags, topk_idx=g_idx.view(qs, v, k), topk_sim=g_sim.view(qs, v, k))
         if b_idx is not None:
@@ -608,5 +803,7 @@ class TVCScorer:
             self._exchange = None
 
     def reset_hubness(self):
-        if self.k_occurrence is not None:
-            self.k_occurrence.zero_()
+        if self._k_occ is not None:
+            self.k_occurrence.zero_()          # (the property orders this behind an all-reduce still in flight)
+            if self._hist_stream is not None:
+                self._hist_stream.wait_stream(torch.cuda.current_stream(self.device))

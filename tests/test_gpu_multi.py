@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
+TAGS = ("peer", "peer2", "peer3", "pipe", "pull", "nccl")
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -51,9 +54,11 @@ def _worker(rank, world, port, out_dir):
     assert sc._exchange is not None
     ex = sc._exchange
     import bench
-    for tag in ("peer", "peer2", "peer3", "nccl"):
+    for tag in TAGS:
         if tag == "nccl":
             sc._exchange = None                   # candidate all-to-all + merge kernel instead
+        sc.rescore_at_shards = tag != "pull"      # "pull": round-1 phase 2 (owner reads peer masters)
+        sc.min_chunk_queries = 32 if tag == "pipe" else 1024     # "pipe": host batch pipelined in pieces
         sc.reset_hubness()
         if tag == "peer3":
             # skewed arrival: every rank enters the batch at a different time (the double-buffered receive
@@ -96,7 +101,7 @@ def test_sharded_equals_single_gpu(tmp_path, world):
                        + bench.digest64(torch, t["flags"], 0, 3) + bench.digest64(torch, torch.from_numpy(hub), 0, 4)).item())
     del ref
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    for tag in ("peer", "peer2", "peer3", "nccl"):
+    for tag in TAGS:
         covered = 0
         for r in range(world):
             z = np.load(tmp_path / f"{tag}_r{r}.npz")

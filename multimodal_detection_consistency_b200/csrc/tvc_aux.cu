@@ -1,6 +1,6 @@
-// Bandwidth-bound kernels around the GEMM: operand preparation, candidate re-rank / merge,
-// kernel (b) variant-consistency reduction and kernel (c) k-occurrence histogram.  128-bit loads,
-// warp shuffles, shared-memory staging, warp-aggregated atomics; no tensor cores.
+// Bandwidth-bound kernels around the GEMM: operand preparation, candidate re-rank / merge / exchange and
+// kernel (c), the k-occurrence histogram.  128-bit loads, warp shuffles, shared-memory staging,
+// warp-aggregated atomics (__match_any_sync: one RED per distinct bin a warp holds); no tensor cores.
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <math.h>
@@ -573,8 +573,11 @@ merge_topk_kernel(const float* __restrict__ in_sim, const long long* __restrict_
 constexpr int kHotMax = 256;          // hot lines the sampling pass may publish
 constexpr int kHotSlots = 1024;       // open-addressing slots of the per-block key table
 constexpr int kSampleSlots = 4096;
-constexpr int kSamples = 8192;
-constexpr int kHotShare = 512;        // hot = sample count * kHotShare >= samples
+constexpr int kSamples = 8192;        // streams below kBigStream entries
+constexpr int kSamplesBig = 65536;    // long streams: enough samples to rank kHotMax lines, not just the top dozen
+constexpr long long kBigStream = 8ll << 20;
+constexpr int kHotShare = 512;        // hot = sample count * kHotShare >= samples (short streams)
+constexpr int kHotShareBig = 4096;
 
 __device__ __forceinline__ unsigned bin_hash(int b) {
   return static_cast<unsigned>(b) * 0x9E3779B1u;
@@ -595,18 +598,25 @@ k_occurrence_sample_kernel(const long long* __restrict__ idx, long long total, l
   }
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const int samples = total < kSamples ? static_cast<int>(total) : kSamples;
+  // Round 1 sampled 8192 entries at a 1/512 share whatever the stream: on a power-law stream (idx = N u^3,
+  // 50M entries into 1M bins) that publishes ~13 of the 256 lines the table can hold (7 % of the entries);
+  // 65536 samples at a 1/4096 share fill it (20 %).
+  const bool big = total >= kBigStream;
+  const int want = big ? kSamplesBig : kSamples;
+  const int samples = total < want ? static_cast<int>(total) : want;
   const long long stride = total / samples;
-  const int thresh = max(4, samples / kHotShare);
+  const int thresh = max(4, samples / (big ? kHotShareBig : kHotShare));
+#pragma unroll 8       // independent loads in flight: 64 samples per thread on a long stream
   for (int i = threadIdx.x; i < samples; i += blockDim.x) {
-    const long long b = idx[static_cast<long long>(i) * stride] - idx_base;
+    const long long b = __ldg(idx + static_cast<long long>(i) * stride) - idx_base;
     if (b >= 0 && b < n_bins) atomicAdd(&s_cnt[bin_hash(static_cast<int>(b >> 5)) >> 20], 1);
   }
   __syncthreads();
   // second walk: entries whose lossy slot is heavy are counted exactly (bounded linear probing; a
   // dropped candidate only costs speed, never correctness)
+#pragma unroll 4
   for (int i = threadIdx.x; i < samples; i += blockDim.x) {
-    const long long b64 = idx[static_cast<long long>(i) * stride] - idx_base;
+    const long long b64 = __ldg(idx + static_cast<long long>(i) * stride) - idx_base;
     if (b64 < 0 || b64 >= n_bins) continue;
     const int line = static_cast<int>(b64 >> 5);
     if (s_cnt[bin_hash(line) >> 20] < thresh) continue;
@@ -621,8 +631,29 @@ k_occurrence_sample_kernel(const long long* __restrict__ idx, long long total, l
     }
   }
   __syncthreads();
+  // more qualifying lines than the table holds: raise the bar until they fit (counts are small integers)
+  __shared__ int s_bar;
+  if (threadIdx.x == 0) s_bar = thresh;
+  __syncthreads();
+  for (int round = 0; round < 12; ++round) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int bar = s_bar;
+    int mine = 0;
+    for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) mine += (s_key[i] >= 0 && s_exact[i] >= bar) ? 1 : 0;
+    if (mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (s_n <= kHotMax) break;
+    __syncthreads();
+    if (threadIdx.x == 0) s_bar = bar + max(1, bar >> 2);
+    __syncthreads();
+  }
+  const int bar = s_bar;
+  __syncthreads();
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x)
-    if (s_key[i] >= 0 && s_exact[i] >= thresh) {
+    if (s_key[i] >= 0 && s_exact[i] >= bar) {
       const int slot = atomicAdd(&s_n, 1);
       if (slot < kHotMax) hot[1 + slot] = s_key[i];
     }
@@ -651,6 +682,38 @@ __device__ __forceinline__ void for_each_bin(const long long* __restrict__ idx, 
   }
 }
 
+// One RED per DISTINCT bin among the lanes of a warp that reach this point together (what north_star calls
+// warp-aggregated atomics): the lanes holding the same bin elect their lowest lane, which adds the group's
+// population.  Lanes without a bin (b < 0) take part in the vote with a value nobody shares.
+__device__ __forceinline__ void red_aggregated(int* __restrict__ counts, long long b) {
+  const unsigned active = __activemask();
+  const int lane = threadIdx.x & 31;
+  const long long key = b >= 0 ? b : -1ll - lane;
+  const unsigned peers = __match_any_sync(active, key);
+  if (b >= 0 && lane == __ffs(peers) - 1) atomicAdd(&counts[b], __popc(peers));
+}
+
+// Same walk, but `emit` is called by every lane that entered the trip, with -1 for an entry outside the
+// histogram - the callee uses warp votes, so the lanes of a trip must reach it together.
+template <bool VEC, typename Emit>
+__device__ __forceinline__ void for_each_bin_warp(const long long* __restrict__ idx, long long total,
+                                                  long long idx_base, long long n_bins, Emit emit) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long quads = VEC ? (total >> 2) : 0;
+  const longlong2* idx2 = reinterpret_cast<const longlong2*>(idx);
+  for (long long p = tid; p < quads; p += nthreads) {
+    const longlong2 a = idx2[2 * p], c = idx2[2 * p + 1];
+    const long long b[4] = {a.x - idx_base, a.y - idx_base, c.x - idx_base, c.y - idx_base};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) emit((b[h] >= 0 && b[h] < n_bins) ? b[h] : -1ll);
+  }
+  for (long long e = (quads << 2) + tid; e < total; e += nthreads) {
+    const long long b = idx[e] - idx_base;
+    emit((b >= 0 && b < n_bins) ? b : -1ll);
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_occurrence_smem_kernel(const long long* __restrict__ idx, long long total, long long idx_base,
@@ -675,7 +738,7 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
   __shared__ int s_cnt[kHotMax * 32];
   const int n_hot = hot ? min(hot[0], kHotMax) : 0;   // block-uniform
   if (n_hot == 0) {
-    for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](long long b) { atomicAdd(&counts[b], 1); });
+    for_each_bin_warp<VEC>(idx, total, idx_base, n_bins, [&](long long b) { red_aggregated(counts, b); });
     return;
   }
   for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) s_key[i] = -1;
@@ -688,19 +751,23 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
     s_id[h] = static_cast<unsigned short>(i);
   }
   __syncthreads();
-  for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](long long b64) {
-    const int line = static_cast<int>(b64 >> 5);
-    unsigned h = (bin_hash(line) >> 8) & (kHotSlots - 1);
-    while (true) {
-      const int k = s_key[h];
-      if (k == line) {
-        atomicAdd(&s_cnt[s_id[h] * 32 + (static_cast<int>(b64) & 31)], 1);
-        return;
+  for_each_bin_warp<VEC>(idx, total, idx_base, n_bins, [&](long long b64) {
+    bool cold = b64 >= 0;
+    if (cold) {
+      const int line = static_cast<int>(b64 >> 5);
+      unsigned h = (bin_hash(line) >> 8) & (kHotSlots - 1);
+      while (true) {
+        const int k = s_key[h];
+        if (k == line) {
+          atomicAdd(&s_cnt[s_id[h] * 32 + (static_cast<int>(b64) & 31)], 1);
+          cold = false;
+          break;
+        }
+        if (k == -1) break;
+        h = (h + 1) & (kHotSlots - 1);
       }
-      if (k == -1) break;
-      h = (h + 1) & (kHotSlots - 1);
     }
-    atomicAdd(&counts[b64], 1);
+    red_aggregated(counts, cold ? b64 : -1ll);     // every lane of the trip votes; hot / invalid ones with no bin
   });
   __syncthreads();
   for (int i = threadIdx.x; i < n_hot * 32; i += blockDim.x) {

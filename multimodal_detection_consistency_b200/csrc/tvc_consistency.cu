@@ -21,6 +21,7 @@
 //     Measured limits (scripts/trace_emb.py): the kernel is bound by per-stage latency (index load ->
 //     bulk copies -> tasks -> selection ~ 9 us) over the 3 stages that fit in 227 KB, not by HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -60,34 +61,34 @@ struct Stats {
   float mn, mx;
 };
 
-// x[0..n): MAXN <= 16 keeps the converted values in registers between the two passes
-template <int MAXN>
+// x[0..n) in shared memory.  Two passes that RE-READ the values (an LDS + a convert per element) instead of
+// keeping them in registers: the converted values of the four groups were 28 fp64 registers under a 64-register
+// cap, and with a run-time count every unrolled element carried its own predicate (ncu / SASS of round 1: 1830
+// instructions per query, a third of them ISETP / FSEL / IMAD.MOV).  FIXED > 0 = the count is the compile-time
+// constant FIXED (straight-line code, no predicates); FIXED == 0 = run-time count, a plain loop.  The order of
+// the additions is the same in every form, so all kernels that share this function agree to the bit.
+template <int FIXED>
 __device__ __forceinline__ Stats stats_of(const float* x, int n, const double* rcp, bool want_sd) {
   Stats s{0., 0., 0., 0., 0., 0.f, 0.f};
   if (n <= 0) return s;
   float mn = x[0], mx = x[0];
   double sum = 0., ss = 0.;
-  if constexpr (MAXN <= 16) {
-    double v[MAXN];
+  if constexpr (FIXED > 0) {
 #pragma unroll
-    for (int i = 0; i < MAXN; ++i) {
-      v[i] = 0.;
-      if (i < n) {
-        const float f = x[i];
-        mn = fminf(mn, f);
-        mx = fmaxf(mx, f);
-        v[i] = static_cast<double>(f);
-        sum += v[i];
-      }
+    for (int i = 0; i < FIXED; ++i) {
+      const float f = x[i];
+      mn = fminf(mn, f);
+      mx = fmaxf(mx, f);
+      sum += static_cast<double>(f);
     }
-    s.mean = div_n(sum, n, rcp);
+    s.mean = div_n(sum, FIXED, rcp);
 #pragma unroll
-    for (int i = 0; i < MAXN; ++i)
-      if (i < n) {
-        const double dlt = v[i] - s.mean;
-        ss = fma(dlt, dlt, ss);
-      }
+    for (int i = 0; i < FIXED; ++i) {
+      const double dlt = static_cast<double>(x[i]) - s.mean;
+      ss = fma(dlt, dlt, ss);
+    }
   } else {
+#pragma unroll 2
     for (int i = 0; i < n; ++i) {
       const float f = x[i];
       mn = fminf(mn, f);
@@ -95,6 +96,7 @@ __device__ __forceinline__ Stats stats_of(const float* x, int n, const double* r
       sum += static_cast<double>(f);
     }
     s.mean = div_n(sum, n, rcp);
+#pragma unroll 2
     for (int i = 0; i < n; ++i) {
       const double dlt = static_cast<double>(x[i]) - s.mean;
       ss = fma(dlt, dlt, ss);
@@ -109,6 +111,14 @@ __device__ __forceinline__ Stats stats_of(const float* x, int n, const double* r
   return s;
 }
 
+// the counts the defaults produce (V = 5, X = 10, G = 3) take the straight-line form
+template <int A, int B>
+__device__ __forceinline__ Stats stats_dispatch(const float* x, int n, const double* rcp, bool want_sd) {
+  if (n == A) return stats_of<A>(x, n, rcp, want_sd);
+  if (B > 0 && n == B) return stats_of<(B > 0 ? B : 1)>(x, n, rcp, want_sd);
+  return stats_of<0>(x, n, rcp, want_sd);
+}
+
 __device__ __forceinline__ double clipd(double x, double lo, double hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
@@ -117,7 +127,7 @@ __device__ __forceinline__ double clipd(double x, double lo, double hi) {
 // references, generative references, variant pairs).
 __device__ __forceinline__ void combine_scores(const tvc_detector_params& p, const double* rcp, float s0f,
                                                const Stats& tv, int nv, const Stats& rt, int nr,
-                                               const Stats& gn, int ng, const Stats& xv, float* out,
+                                               const Stats& gn, int ng, float* out,
                                                int out_stride, uint8_t* flag) {
   const double s0 = s0f;
 
@@ -252,9 +262,6 @@ __device__ __forceinline__ void combine_scores(const tvc_detector_params& p, con
   put(TVC_S_GEN_STD, gn_s);
   out[TVC_S_GEN_MAX * out_stride] = ng > 0 ? gn.mx : 0.f;
   put(TVC_S_CROSS_MODAL_VAR, cmv);
-  put(TVC_S_XV_MEAN, xv.mean);
-  out[TVC_S_XV_MIN * out_stride] = xv.mn;
-  put(TVC_S_XV_VAR, xv.var);
   put(TVC_S_DET_TV, det_tv);
   put(TVC_S_DET_SD, det_sd);
   put(TVC_S_DET_C, det_c);
@@ -269,35 +276,27 @@ __device__ __forceinline__ void combine_scores(const tvc_detector_params& p, con
                                (sig_adv ? TVC_FLAG_SIGMA_ADV : 0u));
 }
 
-// sv/sr/sg/sx point at this query's similarity lists (shared memory).  VM/RM/GM bound the counts.
-template <int VM, int RM, int GM>
-__device__ __forceinline__ void finish_scores(const tvc_detector_params& p, const double* rcp, float s0f,
-                                              const float* sv, int nv, const float* sr, int nr,
-                                              const float* sg, int ng, const float* sx, int nx,
-                                              float* out, int out_stride, uint8_t* flag) {
-  const Stats tv = stats_of<VM>(sv, nv, rcp, true);
-  const Stats rt = stats_of<RM>(sr, nr, rcp, true);
-  const Stats gn = stats_of<GM>(sg, ng, rcp, true);
-  const Stats xv = stats_of<VM*(VM - 1) / 2>(sx, nx, rcp, false);
-  combine_scores(p, rcp, s0f, tv, nv, rt, nr, gn, ng, xv, out, out_stride, flag);
-}
-
-// runtime dispatch on the configured widths: the common (V<=5, R<=10, G<=4) build keeps every list in
-// registers; the wide build serves anything up to TVC_MAX_*
+// sv/sr/sg/sx point at this query's similarity lists (shared memory)
 __device__ __forceinline__ void finish_scores_any(const tvc_detector_params& p, const double* rcp, float s0,
                                                   const float* sv, int nv, const float* sr, int nr,
                                                   const float* sg, int ng, const float* sx, int nx,
                                                   float* out, int out_stride, uint8_t* flag) {
-  if (p.n_variants <= 5 && p.n_retrieval <= 10 && p.n_generative <= 4)
-    finish_scores<5, 10, 4>(p, rcp, s0, sv, nv, sr, nr, sg, ng, sx, nx, out, out_stride, flag);
-  else
-    finish_scores<TVC_MAX_VARIANTS, TVC_MAX_REFS, TVC_MAX_REFS>(p, rcp, s0, sv, nv, sr, nr, sg, ng, sx, nx, out,
-                                                                 out_stride, flag);
+  {   // the variant<->variant columns depend on nothing else: written first, so their moments are not kept live
+    const Stats xv = stats_dispatch<10, 0>(sx, nx, rcp, false);
+    out[TVC_S_XV_MEAN * out_stride] = static_cast<float>(xv.mean);
+    out[TVC_S_XV_MIN * out_stride] = xv.mn;
+    out[TVC_S_XV_VAR * out_stride] = static_cast<float>(xv.var);
+  }
+  const Stats tv = stats_dispatch<5, 0>(sv, nv, rcp, true);
+  const Stats rt = stats_dispatch<10, 5>(sr, nr, rcp, true);
+  const Stats gn = stats_dispatch<3, 0>(sg, ng, rcp, true);
+  combine_scores(p, rcp, s0, tv, nv, rt, nr, gn, ng, out, out_stride, flag);
 }
 
 // ------------------------------------------------------------------------------- similarity-fed
 constexpr int kSimsBlock = 128;
-constexpr int kOutStride = kSimsBlock + 1;   // column-major result tile, conflict-free both ways
+constexpr int kSimsMinBlocks = 8;
+constexpr int kOutStride = TVC_NSCORES + 1;  // row-major result tile [query][25]: odd stride, conflict-free scalar access
 
 __device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__ src, long long q0,
                                            int nq, int width) {
@@ -315,7 +314,8 @@ __device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(kSimsBlock, 8)
+template <int MINB>   // resident blocks per SM the register budget is cut for: 8 -> 64 registers, 6 -> 80, 4 -> 128
+__global__ void __launch_bounds__(kSimsBlock, MINB)
 consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const float* __restrict__ s0,
                         const float* __restrict__ sv, const float* __restrict__ sr,
                         const int32_t* __restrict__ r_cnt, const float* __restrict__ sg,
@@ -348,15 +348,27 @@ consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const f
     const int nv = sv ? V : 0;
     uint8_t flag = 0;
     finish_scores_any(p, s_rcp, s0[q], b_sv + t * V, nv, b_sr + t * R, nr, b_sg + t * G, ng, b_sx + t * X, X,
-                      b_out + t, kOutStride, &flag);
+                      b_out + t * kOutStride, 1, &flag);
     flags[q] = flag;
   }
   __syncthreads();
+  // the tile leaves as 128-bit streaming stores: TVC_NSCORES is a multiple of 4, so a float4 never straddles two
+  // queries (one division per 4 values instead of a division per value)
+  static_assert(TVC_NSCORES % 4 == 0, "float4 copy-out");
   float* dst = scores + q0 * TVC_NSCORES;
-  const int total = nq * TVC_NSCORES;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int qq = i / TVC_NSCORES, col = i - qq * TVC_NSCORES;
-    __stcs(dst + i, b_out[col * kOutStride + qq]);
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const int total4 = nq * (TVC_NSCORES / 4);
+    for (int i = threadIdx.x; i < total4; i += blockDim.x) {
+      const int qq = i / (TVC_NSCORES / 4), c4 = (i - qq * (TVC_NSCORES / 4)) * 4;
+      const float* r = b_out + qq * kOutStride + c4;
+      __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(r[0], r[1], r[2], r[3]));
+    }
+  } else {
+    const int total = nq * TVC_NSCORES;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int qq = i / TVC_NSCORES, col = i - qq * TVC_NSCORES;
+      dst[i] = b_out[qq * kOutStride + col];
+    }
   }
 }
 
@@ -1483,14 +1495,23 @@ cudaError_t launch_consistency_sims(const tvc_detector_params& p, int64_t q, con
   const int X = sxv ? V * (V - 1) / 2 : 0;
   auto up4 = [](int x) { return (x + 3) & ~3; };
   const size_t floats = up4(kSimsBlock * V) + up4(kSimsBlock * R) + up4(kSimsBlock * G) +
-                        up4(kSimsBlock * X) + 16 + kOutStride * TVC_NSCORES;
+                        up4(kSimsBlock * X) + 16 + kOutStride * kSimsBlock;
   const size_t smem = floats * 4;
-  static SmemAttrOnce configured;   // per (kernel, device): a second context on another GPU sets its own
-  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(consistency_sims_kernel), 160 * 1024); e != cudaSuccess)
-    return e;
+  static const int minb = [] {
+    const char* e = getenv("TVC_SIMS_MIN_BLOCKS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 4 || v == 6 || v == 8) ? v : kSimsMinBlocks;
+  }();
   const int grid = static_cast<int>((q + kSimsBlock - 1) / kSimsBlock);
-  consistency_sims_kernel<<<grid, kSimsBlock, smem, stream>>>(p, q, s0, sv, sr, r_cnt, sg, g_cnt, sxv,
-                                                              scores, flags);
+  auto go = [&](auto kernel, SmemAttrOnce& once) -> cudaError_t {
+    if (cudaError_t e = once.ensure(reinterpret_cast<const void*>(kernel), 160 * 1024); e != cudaSuccess) return e;
+    kernel<<<grid, kSimsBlock, smem, stream>>>(p, q, s0, sv, sr, r_cnt, sg, g_cnt, sxv, scores, flags);
+    return cudaSuccess;
+  };
+  static SmemAttrOnce c4, c6, c8;   // per (kernel, device): a second context on another GPU sets its own
+  cudaError_t le = minb == 4 ? go(consistency_sims_kernel<4>, c4)
+                   : (minb == 6 ? go(consistency_sims_kernel<6>, c6) : go(consistency_sims_kernel<8>, c8));
+  if (le != cudaSuccess) return le;
   note_launch();
   return cudaGetLastError();
 }

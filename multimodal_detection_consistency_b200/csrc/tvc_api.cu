@@ -41,6 +41,10 @@ struct tvc_ctx {
   std::vector<cudaEvent_t> idle_events;
   int64_t debug_flags = 0;
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
+  // pacing of the CTA pairs of a wave (SearchPlan::pace): a producer may run pace_ahead blocks of pace_every
+  // gallery tiles ahead of the slowest pair of its wave; pace_every = 0 switches it off (TVC_PACE_EVERY / _AHEAD)
+  int64_t pace_every = 16;
+  int64_t pace_ahead = 3;
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
   int64_t emb_generic = 0;       // 1: kernel (b) embedding mode always takes the one-warp-per-query kernel
   bool timing = false;
@@ -382,6 +386,8 @@ int tvc_ctx_create(int device, tvc_ctx** out) {
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   ctx->launches0 = launches_so_far();
   if (const char* e = getenv("TVC_PAIR_MIN_ROWS")) ctx->pair_min_rows = atoll(e);
+  if (const char* e = getenv("TVC_PACE_EVERY")) ctx->pace_every = atoll(e);
+  if (const char* e = getenv("TVC_PACE_AHEAD")) ctx->pace_ahead = atoll(e);
   *out = ctx;
   return TVC_OK;
 }
@@ -429,6 +435,14 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   }
   if (strcmp(name, "debug_flags") == 0) {
     ctx->debug_flags = value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "pace_every") == 0) {
+    ctx->pace_every = value < 0 ? 0 : value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "pace_ahead") == 0) {
+    ctx->pace_ahead = value < 1 ? 1 : value;
     return TVC_OK;
   }
   return fail(ctx, TVC_ERR_INVALID, std::string("unknown option ") + name);
@@ -762,10 +776,29 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
   const size_t cand_b = up256(cand_n * 4);
   const size_t os_b = (sim_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 4);
   const size_t oi_b = (idx_dev || cand) ? 0 : up256(static_cast<size_t>(m) * k * 8);
+  // pacing counters: only where the pairs of a wave stream more gallery than the L2 keeps
+  size_t pace_b = 0;
+  {
+    const int64_t every = ctx->pace_every, ahead = ctx->pace_ahead;
+    const size_t stream_b = static_cast<size_t>(plan.n_tiles) * kBN * d_pad * 2;
+    if (plan.pair && plan.full_tiles > 0 && every > 0 && ahead > 0 && stream_b > (48u << 20) &&
+        plan.n_tiles > every * (ahead + 1)) {
+      plan.pace_every = static_cast<int>(every);
+      plan.pace_ahead = static_cast<int>(ahead);
+      plan.pace_blocks = static_cast<int>((plan.n_tiles + every - 1) / every);
+      const int waves = plan.full_tiles / (plan.grid / 2);
+      pace_b = up256(static_cast<size_t>(waves) * plan.pace_blocks * 4);
+    }
+  }
   uint8_t* ws;
-  int rc = get_ws(cs, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b, &ws);
+  int rc = get_ws(cs, q_in_b + q_bf_b + q_f32_b + 2 * cand_b + os_b + oi_b + pace_b, &ws);
   if (rc != TVC_OK) return rc;
   uint8_t* p = ws;
+  if (pace_b) {
+    plan.pace = reinterpret_cast<unsigned int*>(p);
+    p += pace_b;
+    TVC_CUDA(ctx, cudaMemsetAsync(plan.pace, 0, pace_b, st));
+  }
   uint8_t* q_in = p; p += q_in_b;
   __nv_bfloat16* q_bf = reinterpret_cast<__nv_bfloat16*>(p); p += q_bf_b;
   float* q_f32 = q_f32_b ? reinterpret_cast<float*>(p) : nullptr; p += q_f32_b;

@@ -1,9 +1,11 @@
 // Bandwidth-bound kernels around the GEMM: operand preparation, candidate re-rank / merge / exchange and
 // kernel (c), the k-occurrence histogram.  128-bit loads, warp shuffles, shared-memory staging,
-// warp-aggregated atomics (__match_any_sync: one RED per distinct bin a warp holds); no tensor cores.
+// warp-aggregated atomics (__match_any_sync: one RED per distinct bin a warp holds, used where the sampling
+// pre-pass finds the stream repeating itself inside a warp); no tensor cores.
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -559,54 +561,58 @@ merge_topk_kernel(const float* __restrict__ in_sim, const long long* __restrict_
 // ------------------------------------------------------------------------------- k-occurrence
 // Kernel (c): N_k(j) = #{rows i : j in topk(i)} (references/Adversarial_Hubness_.../README.md:43-57).
 // The int64 index stream is read with 128-bit loads at HBM speed; what bounds the kernel is the
-// atomic path.  Measured on B200 (50M entries, 1M bins): one RED per entry sustains ~180 G entries/s
-// when bins are spread (one atomic per clock per L2 slice), but increments that land in ONE 128-byte
-// line serialise in its slice at ~1.5 G/s - and hubness histograms are exactly the data with hot
-// lines (an adversarial hub sits in most rows; popular rows cluster).  So:
+// atomic path, and on the SM side: a RED costs the load/store pipe ~1.3 cycles per LANE whatever the
+// address (B300_MICROARCH "REDG 1.29 cyc/lane spread"; measured here ~180 G increments/s over 148 SMs), a
+// shared-memory atomic 1-2 cycles per lane, so no private copy makes an increment cheaper than its RED.
+// What the kernel can do is (1) not serialise: increments that land in ONE 128-byte line queue in its L2
+// slice at ~1.5 G/s, and hubness histograms are exactly the data with hot lines (an adversarial hub sits
+// in most rows; popular rows cluster) - and (2) send fewer REDs where the stream repeats itself.  So:
 //   * histograms that fit in shared memory (<= 48 KB) and see many increments per bin accumulate
 //     privately per block with shared-memory atomics and flush once;
 //   * otherwise a sampling pre-pass (one block, <= 8192 strided entries) finds the 32-bin lines that
-//     hold >= 1/512 of the stream and publishes up to 256 of them; the main kernel keeps those lines
-//     (32 counters each) in a block-private shared-memory table (one LDS probe per entry,
-//     shared-memory atomic on a hit, flushed once per block) and sends every other entry to its bin
-//     with one RED, four entries per thread in flight.
+//     hold >= 1/512 of the stream - the share above which a line's serial time in its slice would reach the
+//     kernel's own - and publishes up to 256 of them; the main kernel keeps those lines (32 counters
+//     each) in a block-private shared-memory table (one LDS probe per entry, shared-memory atomic on a
+//     hit, flushed once per block) and sends every other entry to its bin with one RED;
+//   * WARP-AGGREGATED atomics (north_star (c)): the lanes of a warp that hold the same bin elect one lane,
+//     which adds the group's population (__match_any_sync).  A warp-wide match costs the SM more than the
+//     32 REDs it can save (measured: 50 M i.i.d. entries 420 -> 950 us with the vote on every entry), so
+//     the pre-pass also MEASURES how often the kernel's own lane groups repeat a bin (32 windows of the
+//     stream, same entry-to-lane mapping) and publishes that rate; the main kernel votes only when at
+//     least kAggPermille of the entries would be absorbed (top-k lists of neighbouring rows - the 5 text
+//     variants of one query - and hub-dominated streams are; a shuffled stream is not).
 constexpr int kHotMax = 256;          // hot lines the sampling pass may publish
 constexpr int kHotSlots = 1024;       // open-addressing slots of the per-block key table
 constexpr int kSampleSlots = 4096;
-constexpr int kSamples = 8192;        // streams below kBigStream entries
-constexpr int kSamplesBig = 65536;    // long streams: enough samples to rank kHotMax lines, not just the top dozen
-constexpr long long kBigStream = 8ll << 20;
-constexpr int kHotShare = 512;        // hot = sample count * kHotShare >= samples (short streams)
-constexpr int kHotShareBig = 4096;
+constexpr int kSamples = 8192;
+constexpr int kHotShare = 512;        // hot = sample count * kHotShare >= samples
+constexpr int kAggSlot = kHotMax + 1; // scratch word: permille of entries a warp vote would absorb
+constexpr int kAggPermille = 500;     // vote when the average group holds >= 2 lanes
 
 __device__ __forceinline__ unsigned bin_hash(int b) {
   return static_cast<unsigned>(b) * 0x9E3779B1u;
 }
 
-// scratch layout: hot[0] = number of keys, hot[1 .. kHotMax] = line numbers ((bin - idx_base) >> 5)
+// scratch layout: hot[0] = number of keys, hot[1 .. kHotMax] = line numbers ((bin - idx_base) >> 5),
+// hot[kAggSlot] = permille of the sampled entries that share their bin with a lower lane of their group
 __global__ void __launch_bounds__(1024)
 k_occurrence_sample_kernel(const long long* __restrict__ idx, long long total, long long idx_base,
                            long long n_bins, int* __restrict__ hot) {
   __shared__ int s_cnt[kSampleSlots];     // lossy hashed counts
   __shared__ int s_key[kHotSlots];        // exact table of the candidates
   __shared__ int s_exact[kHotSlots];
-  __shared__ int s_n;
+  __shared__ int s_n, s_dup, s_valid;
   for (int i = threadIdx.x; i < kSampleSlots; i += blockDim.x) s_cnt[i] = 0;
   for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) {
     s_key[i] = -1;
     s_exact[i] = 0;
   }
-  if (threadIdx.x == 0) s_n = 0;
+  if (threadIdx.x == 0) s_n = s_dup = s_valid = 0;
   __syncthreads();
-  // Round 1 sampled 8192 entries at a 1/512 share whatever the stream: on a power-law stream (idx = N u^3,
-  // 50M entries into 1M bins) that publishes ~13 of the 256 lines the table can hold (7 % of the entries);
-  // 65536 samples at a 1/4096 share fill it (20 %).
-  const bool big = total >= kBigStream;
-  const int want = big ? kSamplesBig : kSamples;
-  const int samples = total < want ? static_cast<int>(total) : want;
+  const int samples = total < kSamples ? static_cast<int>(total) : kSamples;
   const long long stride = total / samples;
-  const int thresh = max(4, samples / (big ? kHotShareBig : kHotShare));
-#pragma unroll 8       // independent loads in flight: 64 samples per thread on a long stream
+  const int thresh = max(4, samples / kHotShare);
+#pragma unroll 8
   for (int i = threadIdx.x; i < samples; i += blockDim.x) {
     const long long b = __ldg(idx + static_cast<long long>(i) * stride) - idx_base;
     if (b >= 0 && b < n_bins) atomicAdd(&s_cnt[bin_hash(static_cast<int>(b >> 5)) >> 20], 1);
@@ -631,37 +637,60 @@ k_occurrence_sample_kernel(const long long* __restrict__ idx, long long total, l
     }
   }
   __syncthreads();
-  // more qualifying lines than the table holds: raise the bar until they fit (counts are small integers)
-  __shared__ int s_bar;
-  if (threadIdx.x == 0) s_bar = thresh;
-  __syncthreads();
-  for (int round = 0; round < 12; ++round) {
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const int bar = s_bar;
-    int mine = 0;
-    for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) mine += (s_key[i] >= 0 && s_exact[i] >= bar) ? 1 : 0;
-    if (mine) atomicAdd(&s_n, mine);
-    __syncthreads();
-    if (s_n <= kHotMax) break;
-    __syncthreads();
-    if (threadIdx.x == 0) s_bar = bar + max(1, bar >> 2);
-    __syncthreads();
+  // repetition inside the main kernel's lane groups, hot lines aside (they never reach the vote): warp w reads
+  // the 128 consecutive entries at w/32 of the stream the way a trip of the main kernel does (lane l holds
+  // entries 4l .. 4l+3, group h = the lanes' h-th entries)
+  {
+    __syncwarp();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long base = ((total / 32) * w) & ~3ll;
+    int dup = 0, valid = 0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const long long e = base + 4 * lane + h;
+      long long b = e < total ? __ldg(idx + e) - idx_base : -1;
+      if (b >= n_bins) b = -1;
+      if (b >= 0) {
+        const int line = static_cast<int>(b >> 5);
+        unsigned hh = (bin_hash(line) >> 8) & (kHotSlots - 1);
+        for (int probe = 0; probe < 16; ++probe) {
+          const int k = s_key[hh];
+          if (k == -1) break;
+          if (k == line) {
+            if (s_exact[hh] >= thresh) b = -1;
+            break;
+          }
+          hh = (hh + 1) & (kHotSlots - 1);
+        }
+      }
+      __syncwarp();
+      const long long key = b >= 0 ? b : -1ll - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (b >= 0) {
+        ++valid;
+        if (lane != __ffs(peers) - 1) ++dup;
+      }
+    }
+    if (valid) atomicAdd(&s_valid, valid);
+    if (dup) atomicAdd(&s_dup, dup);
   }
-  const int bar = s_bar;
-  __syncthreads();
-  if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x)
-    if (s_key[i] >= 0 && s_exact[i] >= bar) {
+    if (s_key[i] >= 0 && s_exact[i] >= thresh) {
       const int slot = atomicAdd(&s_n, 1);
       if (slot < kHotMax) hot[1 + slot] = s_key[i];
     }
   __syncthreads();
-  if (threadIdx.x == 0) hot[0] = min(s_n, kHotMax);
+  if (threadIdx.x == 0) {
+    hot[0] = min(s_n, kHotMax);
+    hot[kAggSlot] = s_valid > 0 ? static_cast<int>(1000ll * s_dup / s_valid) : 0;
+  }
 }
 
-// 4 entries per thread per trip (two 128-bit loads when VEC), `emit(bin)` per valid entry
+// Walks the stream in trips of 8 entries per thread (four 128-bit loads in flight when VEC), then 4, then 1;
+// `emit(b, n)` receives the trip's n bins at once, -1 for an entry outside the histogram, so that the callee
+// can issue its n table probes / votes / REDs back to back instead of one dependent chain per entry (ncu on
+// the per-entry form: 52 instructions per entry, 28 of every 50 stall cycles on the shared-memory scoreboard).
 template <bool VEC, typename Emit>
 __device__ __forceinline__ void for_each_bin(const long long* __restrict__ idx, long long total,
                                              long long idx_base, long long n_bins, Emit emit) {
@@ -669,49 +698,47 @@ __device__ __forceinline__ void for_each_bin(const long long* __restrict__ idx, 
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long quads = VEC ? (total >> 2) : 0;
   const longlong2* idx2 = reinterpret_cast<const longlong2*>(idx);
-  for (long long p = tid; p < quads; p += nthreads) {
+  auto bin_of = [&](long long v) {
+    v -= idx_base;
+    return (v >= 0 && v < n_bins) ? v : -1ll;
+  };
+  long long p = tid;
+  for (; p + nthreads < quads; p += 2 * nthreads) {
+    const longlong2 a0 = idx2[2 * p], c0 = idx2[2 * p + 1];
+    const longlong2 a1 = idx2[2 * (p + nthreads)], c1 = idx2[2 * (p + nthreads) + 1];
+    const long long b[8] = {bin_of(a0.x), bin_of(a0.y), bin_of(c0.x), bin_of(c0.y),
+                            bin_of(a1.x), bin_of(a1.y), bin_of(c1.x), bin_of(c1.y)};
+    emit(b, 8);
+  }
+  // (p + nthreads < quads is not warp-uniform on the last trip: the leftovers run under the lanes' own mask;
+  // red_aggregated votes over __activemask())
+  for (; p < quads; p += nthreads) {
     const longlong2 a = idx2[2 * p], c = idx2[2 * p + 1];
-    const long long b[4] = {a.x - idx_base, a.y - idx_base, c.x - idx_base, c.y - idx_base};
-#pragma unroll
-    for (int h = 0; h < 4; ++h)
-      if (b[h] >= 0 && b[h] < n_bins) emit(b[h]);
+    const long long b[8] = {bin_of(a.x), bin_of(a.y), bin_of(c.x), bin_of(c.y), -1, -1, -1, -1};
+    emit(b, 4);
   }
   for (long long e = (quads << 2) + tid; e < total; e += nthreads) {
-    const long long b = idx[e] - idx_base;
-    if (b >= 0 && b < n_bins) emit(b);
+    const long long b[8] = {bin_of(idx[e]), -1, -1, -1, -1, -1, -1, -1};
+    emit(b, 1);
   }
 }
 
 // One RED per DISTINCT bin among the lanes of a warp that reach this point together (what north_star calls
 // warp-aggregated atomics): the lanes holding the same bin elect their lowest lane, which adds the group's
-// population.  Lanes without a bin (b < 0) take part in the vote with a value nobody shares.
+// population.  Lanes without a bin (b < 0) take part in the vote with a value nobody shares.  NARROW: the
+// bins fit 31 bits, the vote compares 32-bit keys (measured: the 64-bit match costs 2.2x the kernel, the
+// 32-bit one 6 %).
+template <bool NARROW>
 __device__ __forceinline__ void red_aggregated(int* __restrict__ counts, long long b) {
   const unsigned active = __activemask();
   const int lane = threadIdx.x & 31;
-  const long long key = b >= 0 ? b : -1ll - lane;
-  const unsigned peers = __match_any_sync(active, key);
+  unsigned peers;
+  if (NARROW) {
+    peers = __match_any_sync(active, b >= 0 ? static_cast<int>(b) : -1 - lane);
+  } else {
+    peers = __match_any_sync(active, b >= 0 ? b : -1ll - lane);
+  }
   if (b >= 0 && lane == __ffs(peers) - 1) atomicAdd(&counts[b], __popc(peers));
-}
-
-// Same walk, but `emit` is called by every lane that entered the trip, with -1 for an entry outside the
-// histogram - the callee uses warp votes, so the lanes of a trip must reach it together.
-template <bool VEC, typename Emit>
-__device__ __forceinline__ void for_each_bin_warp(const long long* __restrict__ idx, long long total,
-                                                  long long idx_base, long long n_bins, Emit emit) {
-  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long quads = VEC ? (total >> 2) : 0;
-  const longlong2* idx2 = reinterpret_cast<const longlong2*>(idx);
-  for (long long p = tid; p < quads; p += nthreads) {
-    const longlong2 a = idx2[2 * p], c = idx2[2 * p + 1];
-    const long long b[4] = {a.x - idx_base, a.y - idx_base, c.x - idx_base, c.y - idx_base};
-#pragma unroll
-    for (int h = 0; h < 4; ++h) emit((b[h] >= 0 && b[h] < n_bins) ? b[h] : -1ll);
-  }
-  for (long long e = (quads << 2) + tid; e < total; e += nthreads) {
-    const long long b = idx[e] - idx_base;
-    emit((b >= 0 && b < n_bins) ? b : -1ll);
-  }
 }
 
 template <bool VEC>
@@ -721,7 +748,11 @@ k_occurrence_smem_kernel(const long long* __restrict__ idx, long long total, lon
   extern __shared__ int s_hist[];
   for (int b = threadIdx.x; b < n_bins; b += blockDim.x) s_hist[b] = 0;
   __syncthreads();
-  for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](long long b) { atomicAdd(&s_hist[b], 1); });
+  for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](const long long (&b)[8], int n) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < n && b[h] >= 0) atomicAdd(&s_hist[b[h]], 1);
+  });
   __syncthreads();
   for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
     const int c = s_hist[b];
@@ -729,50 +760,81 @@ k_occurrence_smem_kernel(const long long* __restrict__ idx, long long total, lon
   }
 }
 
+constexpr unsigned kSlotEmpty = 0xffffffffu;   // key table word: (line << 8) | compact line id, lines < 2^24
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_occurrence_kernel(const long long* __restrict__ idx, long long total, long long idx_base,
-                    long long n_bins, int* __restrict__ counts, const int* __restrict__ hot) {
-  __shared__ int s_key[kHotSlots];            // line number or -1
-  __shared__ unsigned short s_id[kHotSlots];  // slot -> compact line id
+                    long long n_bins, int* __restrict__ counts, const int* __restrict__ hot, int force_agg) {
+  __shared__ unsigned s_tab[kHotSlots];
   __shared__ int s_cnt[kHotMax * 32];
-  const int n_hot = hot ? min(hot[0], kHotMax) : 0;   // block-uniform
-  if (n_hot == 0) {
-    for_each_bin_warp<VEC>(idx, total, idx_base, n_bins, [&](long long b) { red_aggregated(counts, b); });
-    return;
-  }
-  for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) s_key[i] = -1;
-  for (int i = threadIdx.x; i < n_hot * 32; i += blockDim.x) s_cnt[i] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n_hot; i += blockDim.x) {
-    const int line = hot[1 + i];
-    unsigned h = (bin_hash(line) >> 8) & (kHotSlots - 1);
-    while (atomicCAS(&s_key[h], -1, line) != -1) h = (h + 1) & (kHotSlots - 1);   // keys are distinct
-    s_id[h] = static_cast<unsigned short>(i);
-  }
-  __syncthreads();
-  for_each_bin_warp<VEC>(idx, total, idx_base, n_bins, [&](long long b64) {
-    bool cold = b64 >= 0;
-    if (cold) {
-      const int line = static_cast<int>(b64 >> 5);
+  // block-uniform (every block reads the same scratch words)
+  const int n_hot = hot ? min(hot[0], kHotMax) : 0;
+  const bool agg = force_agg >= 0 ? force_agg != 0 : (hot != nullptr && hot[kAggSlot] >= kAggPermille);
+  if (n_hot > 0) {
+    for (int i = threadIdx.x; i < kHotSlots; i += blockDim.x) s_tab[i] = kSlotEmpty;
+    for (int i = threadIdx.x; i < n_hot * 32; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_hot; i += blockDim.x) {
+      const int line = hot[1 + i];
       unsigned h = (bin_hash(line) >> 8) & (kHotSlots - 1);
-      while (true) {
-        const int k = s_key[h];
-        if (k == line) {
-          atomicAdd(&s_cnt[s_id[h] * 32 + (static_cast<int>(b64) & 31)], 1);
-          cold = false;
-          break;
-        }
-        if (k == -1) break;
-        h = (h + 1) & (kHotSlots - 1);
+      const unsigned word = (static_cast<unsigned>(line) << 8) | static_cast<unsigned>(i);
+      while (atomicCAS(&s_tab[h], kSlotEmpty, word) != kSlotEmpty) h = (h + 1) & (kHotSlots - 1);   // keys are distinct
+    }
+    __syncthreads();
+  }
+  // One trip: all first probes are issued together, then each entry is resolved - an empty slot (the common
+  // case: the table is at most a quarter full) sends it to its bin, a key match to the block's private counters,
+  // anything else walks on.
+  auto trip = [&](const long long (&b)[8], int n, auto cold) {
+    unsigned slot[8], word[8];
+    if (n_hot > 0) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        slot[h] = (bin_hash(static_cast<int>(b[h] >> 5)) >> 8) & (kHotSlots - 1);
+        word[h] = h < n ? s_tab[slot[h]] : kSlotEmpty;
       }
     }
-    red_aggregated(counts, cold ? b64 : -1ll);     // every lane of the trip votes; hot / invalid ones with no bin
-  });
-  __syncthreads();
-  for (int i = threadIdx.x; i < n_hot * 32; i += blockDim.x) {
-    const int c = s_cnt[i];
-    if (c) atomicAdd(&counts[static_cast<long long>(hot[1 + (i >> 5)]) * 32 + (i & 31)], c);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h >= n) break;
+      long long bb = b[h];
+      if (n_hot > 0 && bb >= 0 && word[h] != kSlotEmpty) {
+        const unsigned line = static_cast<unsigned>(bb >> 5);
+        unsigned w = word[h], s = slot[h];
+        while (w != kSlotEmpty && (w >> 8) != line) {
+          s = (s + 1) & (kHotSlots - 1);
+          w = s_tab[s];
+        }
+        if (w != kSlotEmpty) {
+          atomicAdd(&s_cnt[(w & 255u) * 32 + (static_cast<int>(bb) & 31)], 1);
+          bb = -1;
+        }
+      }
+      cold(bb);
+    }
+  };
+  if (!agg) {
+    for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](const long long (&b)[8], int n) {
+      trip(b, n, [&](long long bb) {
+        if (bb >= 0) atomicAdd(&counts[bb], 1);
+      });
+    });
+  } else if (n_bins <= 0x7fffffffll) {
+    for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](const long long (&b)[8], int n) {
+      trip(b, n, [&](long long bb) { red_aggregated<true>(counts, bb); });   // hot / invalid lanes vote with no bin
+    });
+  } else {
+    for_each_bin<VEC>(idx, total, idx_base, n_bins, [&](const long long (&b)[8], int n) {
+      trip(b, n, [&](long long bb) { red_aggregated<false>(counts, bb); });
+    });
+  }
+  if (n_hot > 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_hot * 32; i += blockDim.x) {
+      const int c = s_cnt[i];
+      if (c) atomicAdd(&counts[static_cast<long long>(hot[1 + (i >> 5)]) * 32 + (i & 31)], c);
+    }
   }
 }
 
@@ -1024,16 +1086,21 @@ cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t id
   }
   // hot-bin list: a key table in per-stream scratch written by the sampling pass, read by the main kernel
   int* hot = nullptr;
-  if (hot_scratch != nullptr && total >= 4096 && n_bins < (1ll << 36)) {
+  if (hot_scratch != nullptr && total >= 4096 && n_bins <= (1ll << 29)) {   // line numbers fit 24 bits
     hot = hot_scratch;
     k_occurrence_sample_kernel<<<1, 1024, 0, stream>>>(ip, total, idx_base, n_bins, hot);
     note_launch();
   }
+  // TVC_KOCC_AGG=0/1 pins the warp vote off / on (measurements); default: the pre-pass decides
+  static const int force_agg = [] {
+    const char* e = getenv("TVC_KOCC_AGG");
+    return e ? atoi(e) : -1;
+  }();
   const int g = static_cast<int>(blocks);
   if (aligned)
-    k_occurrence_kernel<true><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot);
+    k_occurrence_kernel<true><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot, force_agg);
   else
-    k_occurrence_kernel<false><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot);
+    k_occurrence_kernel<false><<<g, block, 0, stream>>>(ip, total, idx_base, n_bins, counts, hot, force_agg);
   note_launch();
   return cudaGetLastError();
 }

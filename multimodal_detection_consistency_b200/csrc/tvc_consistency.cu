@@ -45,9 +45,38 @@ __device__ __forceinline__ float warp_sum(float v) {
 // IEEE division (np.mean / np.var) returns, for a fraction of the cost of the DP division sequence.
 constexpr int kRcpN = 128;   // covers every count: V, R, G <= 16, V(V-1)/2 <= 120, R+G <= 32
 
+// 1/i, correctly rounded by the host compiler (IEEE division of constants).  Round 1 had every block divide the
+// table out itself: 128 DP divisions = 3.7 % of all instructions of the statistics kernel (ncu source view).
+#define TVC_RCP1(i) ((i) == 0 ? 0.0 : 1.0 / static_cast<double>(i))
+#define TVC_RCP8(b) TVC_RCP1(b), TVC_RCP1(b + 1), TVC_RCP1(b + 2), TVC_RCP1(b + 3), TVC_RCP1(b + 4), TVC_RCP1(b + 5), \
+                    TVC_RCP1(b + 6), TVC_RCP1(b + 7)
+#define TVC_RCP64(b) TVC_RCP8(b), TVC_RCP8(b + 8), TVC_RCP8(b + 16), TVC_RCP8(b + 24), TVC_RCP8(b + 32), \
+                     TVC_RCP8(b + 40), TVC_RCP8(b + 48), TVC_RCP8(b + 56)
+__constant__ double c_rcp[kRcpN] = {TVC_RCP64(0), TVC_RCP64(64)};
+
 __device__ __forceinline__ void fill_rcp_table(double* rcp, int tid, int nthreads) {
-  for (int i = tid; i < kRcpN; i += nthreads) rcp[i] = i > 0 ? 1.0 / static_cast<double>(i) : 0.0;
+  for (int i = tid; i < kRcpN; i += nthreads) rcp[i] = c_rcp[i];
 }
+
+// sqrt of a finite double >= 0, correctly rounded like IEEE sqrt (np.std / math.sqrt), in 15 instructions
+// instead of the ~40 of the library sequence with its special-case branches: a 22-bit reciprocal square root
+// from the fp32 unit seeds two coupled Newton steps (g -> sqrt x, h -> 1 / (2 sqrt x)), and the FMA residual
+// step g + h (x - g g) rounds correctly (Markstein).  Checked against IEEE sqrt on 3e5 values with an exact-FMA
+// emulation, seed perturbed by +-3 fp32 ulp: no mismatch.  Values the fp32 seed cannot represent take the
+// library path.
+__device__ __forceinline__ double sqrt_lean(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return sqrt(x);
+  const double r = static_cast<double>(rsqrtf(static_cast<float>(x)));
+  double g = x * r, h = 0.5 * r;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+  }
+  return fma(fma(-g, g, x), h, g);
+}
+
 __device__ __forceinline__ double div_n(double s, int n, const double* rcp) {
   const double r = rcp[n], dn = static_cast<double>(n);
   double q = s * r;
@@ -105,7 +134,7 @@ __device__ __forceinline__ Stats stats_of(const float* x, int n, const double* r
   s.sum = sum;
   s.ss = ss;
   s.var = div_n(ss, n, rcp);
-  s.sd = want_sd ? sqrt(s.var) : 0.;
+  s.sd = want_sd ? sqrt_lean(s.var) : 0.;
   s.mn = mn;
   s.mx = mx;
   return s;
@@ -231,7 +260,7 @@ __device__ __forceinline__ void combine_scores(const tvc_detector_params& p, con
   }
   const bool cc_adv = overall < thr;
   const double dist_conf = fabs(overall - thr) / thr;
-  const double cons_conf = nvalid > 1 ? 1.0 - sqrt(vvar) : 0.5;
+  const double cons_conf = nvalid > 1 ? 1.0 - sqrt_lean(vvar) : 0.5;
   const double var_conf = 1.0 - (cmv < 1.0 ? cmv : 1.0);
   const double conf = clipd(div_n(dist_conf + cons_conf + var_conf, 3, rcp), 0.0, 1.0);
 
@@ -245,7 +274,7 @@ __device__ __forceinline__ void combine_scores(const tvc_detector_params& p, con
       double acc = rt.ss + gn.ss;
       acc = fma(static_cast<double>(nr) * (rt.mean - mu), rt.mean - mu, acc);
       acc = fma(static_cast<double>(ng) * (gn.mean - mu), gn.mean - mu, acc);
-      sigma = sqrt(div_n(acc, n, rcp));
+      sigma = sqrt_lean(div_n(acc, n, rcp));
     }
   }
   const bool sig_adv = sigma > static_cast<double>(p.sigma_threshold);
@@ -296,7 +325,19 @@ __device__ __forceinline__ void finish_scores_any(const tvc_detector_params& p, 
 // ------------------------------------------------------------------------------- similarity-fed
 constexpr int kSimsBlock = 128;
 constexpr int kSimsMinBlocks = 8;
-constexpr int kOutStride = TVC_NSCORES + 1;  // row-major result tile [query][25]: odd stride, conflict-free scalar access
+// Result tile [query][28]: 24 scores + 4 floats of padding keep every row 16-byte aligned, so the thread that
+// computed a query copies its own row out with 128-bit accesses - no barrier, no index arithmetic (the copy-out
+// loop over the whole tile was 8 % of the kernel's instructions).  Scalar stores into the tile are 4-way bank
+// conflicted (stride 28), 21 of them per query.
+constexpr int kOutStride = TVC_NSCORES + 4;
+
+// global -> shared bulk copy (TMA, no tensor map), completion bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__ src, long long q0,
                                            int nq, int width) {
@@ -323,6 +364,7 @@ consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const f
                         float* __restrict__ scores, uint8_t* __restrict__ flags) {
   extern __shared__ __align__(16) float s_buf[];
   __shared__ double s_rcp[kRcpN];
+  __shared__ __align__(8) uint64_t s_bar;
   const int V = p.n_variants, R = p.n_retrieval, G = p.n_generative;
   const int X = sxv ? V * (V - 1) / 2 : 0;
   const int pad4 = 4;  // keep every slab 16-byte aligned
@@ -332,42 +374,65 @@ consistency_sims_kernel(const tvc_detector_params p, long long nq_total, const f
   float* b_sg = b_sr + up4(kSimsBlock * R) + pad4;
   float* b_sx = b_sg + up4(kSimsBlock * G) + pad4;
   float* b_out = b_sx + up4(kSimsBlock * X) + pad4;
-  fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
   const long long q0 = static_cast<long long>(blockIdx.x) * kSimsBlock;
   const int nq = static_cast<int>(min(static_cast<long long>(kSimsBlock), nq_total - q0));
-  stage_slab(b_sv, sv, q0, nq, V);
-  stage_slab(b_sr, sr, q0, nq, R);
-  stage_slab(b_sg, sg, q0, nq, G);
-  stage_slab(b_sx, sxv, q0, nq, X);
-  __syncthreads();
+  // The block's four similarity slabs are contiguous in global memory: one thread hands them to the copy
+  // engine (cp.async.bulk completing on an mbarrier) instead of 128 threads looping over float4s - that loop was
+  // 13 % of the kernel's instructions and its load waits a quarter of all stall samples (ncu source view).
+  // Needs 16-byte aligned sources and sizes, which holds for every block but a ragged last one.
+  auto bulk_ok = [&](const float* src, int width) {
+    return src == nullptr || width == 0 ||
+           (((reinterpret_cast<uintptr_t>(src + q0 * width) & 15u) == 0) && ((nq * width) & 3) == 0);
+  };
+  const bool bulk = bulk_ok(sv, V) && bulk_ok(sr, R) && bulk_ok(sg, G) && bulk_ok(sxv, X);   // block-uniform
+  if (bulk && threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    uint32_t bytes = 0;
+    auto slab_bytes = [&](const float* src, int width) { return (src && width) ? static_cast<uint32_t>(nq * width * 4) : 0u; };
+    bytes = slab_bytes(sv, V) + slab_bytes(sr, R) + slab_bytes(sg, G) + slab_bytes(sxv, X);
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    if (slab_bytes(sv, V)) bulk_g2s(b_sv, sv + q0 * V, slab_bytes(sv, V), &s_bar);
+    if (slab_bytes(sr, R)) bulk_g2s(b_sr, sr + q0 * R, slab_bytes(sr, R), &s_bar);
+    if (slab_bytes(sg, G)) bulk_g2s(b_sg, sg + q0 * G, slab_bytes(sg, G), &s_bar);
+    if (slab_bytes(sxv, X)) bulk_g2s(b_sx, sxv + q0 * X, slab_bytes(sxv, X), &s_bar);
+  }
+  fill_rcp_table(s_rcp, threadIdx.x, blockDim.x);
+  if (!bulk) {
+    stage_slab(b_sv, sv, q0, nq, V);
+    stage_slab(b_sr, sr, q0, nq, R);
+    stage_slab(b_sg, sg, q0, nq, G);
+    stage_slab(b_sx, sxv, q0, nq, X);
+  }
   const int t = threadIdx.x;
+  // this thread's scalars travel while the slabs do
+  const long long q = q0 + t;
+  float my_s0 = 0.f;
+  int nr = 0, ng = 0;
   if (t < nq) {
-    const long long q = q0 + t;
-    const int nr = sr ? (r_cnt ? max(0, min(R, r_cnt[q])) : R) : 0;
-    const int ng = sg ? (g_cnt ? max(0, min(G, g_cnt[q])) : G) : 0;
+    my_s0 = s0[q];
+    nr = sr ? (r_cnt ? max(0, min(R, r_cnt[q])) : R) : 0;
+    ng = sg ? (g_cnt ? max(0, min(G, g_cnt[q])) : G) : 0;
+  }
+  __syncthreads();   // barrier initialised (bulk) / slabs staged (fallback), reciprocal table filled
+  if (bulk) mbar_wait(&s_bar, 0);
+  if (t < nq) {
     const int nv = sv ? V : 0;
     uint8_t flag = 0;
-    finish_scores_any(p, s_rcp, s0[q], b_sv + t * V, nv, b_sr + t * R, nr, b_sg + t * G, ng, b_sx + t * X, X,
-                      b_out + t * kOutStride, 1, &flag);
+    float* row = b_out + t * kOutStride;
+    finish_scores_any(p, s_rcp, my_s0, b_sv + t * V, nv, b_sr + t * R, nr, b_sg + t * G, ng, b_sx + t * X, X, row, 1,
+                      &flag);
     flags[q] = flag;
-  }
-  __syncthreads();
-  // the tile leaves as 128-bit streaming stores: TVC_NSCORES is a multiple of 4, so a float4 never straddles two
-  // queries (one division per 4 values instead of a division per value)
-  static_assert(TVC_NSCORES % 4 == 0, "float4 copy-out");
-  float* dst = scores + q0 * TVC_NSCORES;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-    const int total4 = nq * (TVC_NSCORES / 4);
-    for (int i = threadIdx.x; i < total4; i += blockDim.x) {
-      const int qq = i / (TVC_NSCORES / 4), c4 = (i - qq * (TVC_NSCORES / 4)) * 4;
-      const float* r = b_out + qq * kOutStride + c4;
-      __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(r[0], r[1], r[2], r[3]));
-    }
-  } else {
-    const int total = nq * TVC_NSCORES;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int qq = i / TVC_NSCORES, col = i - qq * TVC_NSCORES;
-      dst[i] = b_out[qq * kOutStride + col];
+    // own row out: TVC_NSCORES is a multiple of 4 and the tile rows are 16-byte aligned
+    static_assert(TVC_NSCORES % 4 == 0 && kOutStride % 4 == 0, "float4 copy-out");
+    float* dst = scores + q * TVC_NSCORES;
+    if ((reinterpret_cast<uintptr_t>(scores) & 15u) == 0) {
+#pragma unroll
+      for (int c = 0; c < TVC_NSCORES / 4; ++c)
+        __stcs(reinterpret_cast<float4*>(dst) + c, reinterpret_cast<const float4*>(row)[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < TVC_NSCORES; ++c) dst[c] = row[c];
     }
   }
 }
@@ -570,14 +635,6 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
   do {                                                                                               \
     if (a.trace != nullptr && blockIdx.x == 0 && (i) < 512) atomicMin(a.trace + (i)*8 + (k), gtime_ns()); \
   } while (0)
-
-// global -> shared bulk copy (TMA, no tensor map), completion bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :
-               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // One task = dots of row A against rows B0 .. B0+nb-1 of the stage (+ squared norms for the image
 // group).  Groups: 0 = image/text/variants (always resident), 1 = retrieval rows, 2 = generative rows.

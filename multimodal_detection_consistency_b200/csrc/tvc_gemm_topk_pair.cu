@@ -21,6 +21,7 @@ namespace tvc {
 namespace {
 
 constexpr int kPStages = 6;
+constexpr long long kPaceTimeoutCycles = 400000;   // ~0.2 ms: far beyond any drift pacing is meant to absorb
 constexpr int kPABytes = kBM * kBK * 2;        // 128 query rows x 64
 constexpr int kPBBytes = 128 * kBK * 2;        // this CTA's 128 of the tile's 256 gallery rows x 64
 constexpr int kPStageBytes = kPABytes + kPBBytes;
@@ -81,11 +82,29 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
+    bool pacing = p.pace != nullptr && rank == 0;   // the peer CTA follows through the shared ring
     for (int u = pair; u < total_units; u += num_pairs) {
       const SearchUnit un = plan_unit(p, u);
       const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
       const int q_row = mt * 256 + static_cast<int>(rank) * 128;
+      const bool paced = pacing && u < p.full_tiles;
+      unsigned int* pace_row = paced ? p.pace + static_cast<size_t>(u / num_pairs) * p.pace_blocks : nullptr;
       for (int nt = t0; nt < t1; ++nt) {
+        if (paced && pacing && nt % p.pace_every == 0) {
+          const int c = nt / p.pace_every;
+          atomicAdd(pace_row + c, 1u);
+          if (c >= p.pace_ahead) {
+            const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
+            const long long t_start = clock64();
+            while (*behind < static_cast<unsigned int>(num_pairs)) {
+              if (clock64() - t_start > kPaceTimeoutCycles) {
+                pacing = false;   // a pair of this wave is not running: stop waiting for it
+                break;
+              }
+              __nanosleep(256);
+            }
+          }
+        }
         const int g_row = nt * kBN + static_cast<int>(rank) * 128;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);

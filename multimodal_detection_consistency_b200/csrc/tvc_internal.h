@@ -42,6 +42,17 @@ struct SearchPlan {
   int debug;            // profiling only: bit0 = skip the top-k epilogue (results are garbage)
   int skip_self;        // drop candidate == query row (+ self_offset)
   int64_t self_offset;  // global row of query 0 minus global row of gallery row 0
+  // Pacing of the CTA pairs of a wave (pair kernel, whole-gallery units only; null = off).  The pairs of a wave
+  // stream the same gallery tiles; left alone they drift apart by more than the L2 holds and the stragglers
+  // fetch every tile from HBM again (ncu, round 1: 22.8 GB per launch against a 7.1 GB floor).  pace[w *
+  // pace_blocks + c] counts the pairs of wave w that have reached gallery tile c * pace_every; a producer enters
+  // block c only once every pair of its wave has reached block c - pace_ahead, so the spread between the first
+  // and the last pair of a wave stays below pace_ahead * pace_every tiles.  A hint, not a barrier: a wait that
+  // times out (a pair that is not resident because another kernel holds its SMs) switches pacing off for that CTA.
+  unsigned int* pace;
+  int pace_every;
+  int pace_ahead;
+  int pace_blocks;
 };
 
 // plans the unit decomposition for `sm_count` persistent CTAs

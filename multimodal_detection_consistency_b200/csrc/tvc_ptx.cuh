@@ -72,11 +72,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Waiting with a suspend-time hint: the warp is parked by the hardware until the phase completes (or
-// the hint expires) instead of spinning, so waiters do not take issue slots from working warps.
+// Waiting without taking issue slots from working warps.  try_wait with a suspend-time hint parks the warp
+// only briefly (measured on B200: it returns after ~40 ns), so a bare loop around it still issues: in kernel
+// (b)'s embedding pipeline the wait loops - try_wait, a clock64 watchdog, its 64-bit compare, the branch - were
+// 55 % of all issued instructions (ncu source view, round 2).  Each failed attempt is therefore followed by a
+// short nanosleep (the warp leaves the scheduler for its duration; adds at most that much latency to a wake-up)
+// and the watchdog clock is read only every 256th attempt.
+#ifndef TVC_PARK_NS
+#define TVC_PARK_NS 64
+#endif
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t"
@@ -88,10 +96,15 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > TVC_WATCHDOG_CYCLES) {
-      printf("tvc: mbarrier watchdog block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
-             (void*)bar, parity);
-      __trap();
+    __nanosleep(TVC_PARK_NS);
+    if ((++spins & 0xFFu) == 0) {
+      if (t0 == 0) {
+        t0 = clock64();
+      } else if (clock64() - t0 > TVC_WATCHDOG_CYCLES) {
+        printf("tvc: mbarrier watchdog block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
+               (void*)bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -24,6 +24,24 @@ def test_k_occurrence_exact(tvc_ctx, m, k, n_bins):
     assert got.sum() == (idx >= 0).sum()
 
 
+@pytest.mark.parametrize("m,k,n_bins,repeat", [(20000, 10, 300000, 4), (20001, 10, 300000, 1), (4099, 7, 200000, 8),
+                                               (30000, 10, 1000000, 2)])
+def test_k_occurrence_repeating_streams(tvc_ctx, m, k, n_bins, repeat):
+    """Histograms too large for shared memory on streams that do / do not repeat themselves inside a warp: the
+    sampling pre-pass turns the warp vote (one RED per distinct bin) on for the first kind and leaves it off for
+    the second; both paths, the hot-line table and the ragged tail of the 8-entries-per-thread walk are exact."""
+    rng = np.random.default_rng(m + repeat)
+    base = rng.integers(0, n_bins, ((m + repeat - 1) // repeat, k)).astype(np.int64)
+    base[rng.uniform(size=base.shape) < 0.3] = 17                      # a hub: one hot bin (and line)
+    idx = np.repeat(base, repeat, axis=0)[:m].copy()                   # neighbouring rows share their lists
+    idx[rng.uniform(size=idx.shape) < 0.02] = -1
+    flat = idx.reshape(-1)[: m * k - 3]                                 # odd length: scalar tail
+    for arr, bins in ((idx, n_bins), (flat, n_bins)):
+        got = tvc_ctx.k_occurrence(arr, bins)
+        assert np.array_equal(got, O.k_occurrence(arr, bins))
+        assert got.sum() == (arr >= 0).sum()
+
+
 def test_k_occurrence_device_accumulate_and_base(tvc_ctx):
     import torch
     rng = np.random.default_rng(0)

@@ -739,9 +739,10 @@ def main():
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
                     frac=(achieved / peaks["bf16_sustained"]) if achieved else None, traffic=traffic,
                     traffic_note="DRAM bytes of the gallery launch (ncu, profiles/roofline_traffic.json); algorithmic "
-                                 "bytes 1.69e9 = one pass; 13 waves of 74 CTA pairs each stream a 0.51 GB gallery range "
-                                 "(floor 7.1e9 for 256-row tiles), stragglers of a wave re-fetch tiles L2 dropped (3.2x); "
-                                 "272 GB/s = 4% of HBM peak, kernel is tensor bound (DESIGN.md section 3a)",
+                                 "bytes 1.69e9 = one pass over the operands; 13 waves of 74 CTA pairs each stream a 0.51 GB "
+                                 "gallery range once = 7.1e9, the floor of a 256-row-per-pair tiling; the pairs of a wave are "
+                                 "paced to stay within 16 gallery tiles of each other (unpaced: 22.9e9 in round 1, 35.0e9 on "
+                                 "this tree); 93 GB/s = 1.4% of HBM peak, kernel is tensor bound (DESIGN.md section 3a)",
                     kernel="gemm_topk_pair_kernel<16> (tcgen05 cta_group::2 GEMM + in-register top-k epilogue)",
                     kernel_ms_per_step=k_ms / args.steps, kernel_launches=k_n,
                     kernel_share_of_step=k_ms / total_ms, peak_source=f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",

@@ -139,7 +139,11 @@ const char* tvc_last_error(tvc_ctx* ctx);
 /* kernels launched through this context since creation (bench.py's gpu_launches) */
 int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
 /* tuning knobs: "pair_min_rows" = query rows from which tvc_search uses the CTA-pair (cta_group::2)
- * kernel instead of the single-CTA one (default 4096; 0 = always, INT64_MAX = never) */
+ * kernel instead of the single-CTA one (default 4096; 0 = always, INT64_MAX = never);
+ * "pace_every" / "pace_ahead" = the CTA pairs of a wave of the pair kernel stay within pace_ahead blocks
+ * of pace_every gallery tiles of each other, so that a gallery tile is read from HBM once per wave
+ * (defaults 8 / 2; pace_every = 0 switches pacing off; also TVC_PACE_EVERY / TVC_PACE_AHEAD in the
+ * environment at context creation).  Results do not depend on any of them. */
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value);
 /* Frees the context's grow-only per-stream device workspaces (query operands, candidate lists, host
  * staging windows) after synchronising the device; they are re-grown on demand.  For callers that

@@ -43,8 +43,8 @@ struct tvc_ctx {
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
   // pacing of the CTA pairs of a wave (SearchPlan::pace): a producer may run pace_ahead blocks of pace_every
   // gallery tiles ahead of the slowest pair of its wave; pace_every = 0 switches it off (TVC_PACE_EVERY / _AHEAD)
-  int64_t pace_every = 16;
-  int64_t pace_ahead = 3;
+  int64_t pace_every = 8;     // measured on the bench workload (profiles/r2h_pace.log): 2..8 tiles x 1..4 blocks
+  int64_t pace_ahead = 2;     // all give 98.7-99.2 ms per step against 102.0-102.6 unpaced; 16 x 3: 101.4-101.8
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
   int64_t emb_generic = 0;       // 1: kernel (b) embedding mode always takes the one-warp-per-query kernel
   bool timing = false;

@@ -14,6 +14,9 @@ TOL = 2e-3
 TIGHT = 5e-6
 
 
+MASKED = {"decisions": 0, "masked": 0}      # how much of the decision parity the exclusion zone hides (reported below)
+
+
 def _decisions_match(flags, ref_flags, ref_scores, params):
     p = dict(O.DEFAULT_PARAMS)
     p.update(params or {})
@@ -24,6 +27,12 @@ def _decisions_match(flags, ref_flags, ref_scores, params):
     ok_sig = np.abs(ref_scores[:, O.S_REF_SIGMA] - p["sigma_threshold"]) > 1e-5
     for bit, ok in [(O.FLAG_DET_ADV, ok_det), (O.FLAG_CC_ADV, ok_cc), (O.FLAG_SIGMA_ADV, ok_sig)]:
         assert np.array_equal((flags & bit)[ok], (ref_flags & bit)[ok])
+        MASKED["decisions"] += ok.size
+        MASKED["masked"] += int((~ok).sum())
+        # the zone is a few float ulps wide: on continuous synthetic scores it may hide a handful of decisions, never
+        # a visible share of a batch (a degenerate batch - every score ON a threshold - would make the test vacuous)
+        if ok.size >= 200:
+            assert (~ok).mean() <= 0.01, f"exclusion zone hides {(~ok).mean():.3%} of the decisions"
 
 
 @pytest.mark.parametrize("q,V,R,G", [(1, 5, 10, 3), (127, 5, 10, 3), (1000, 5, 10, 3), (513, 3, 4, 2), (300, 16, 16, 16)])
@@ -279,3 +288,12 @@ def test_emb_mode_repeatable_when_slow_finishers_hold_stages(tvc_ctx):
     for _ in range(6):
         s, f = run()
         assert torch.equal(s, want_s) and torch.equal(f, want_f)
+
+
+def test_zz_masked_fraction_report():
+    """Runs last in this module: the share of all compared decisions that fell inside the exclusion zone."""
+    if MASKED["decisions"] == 0:
+        pytest.skip("no decision comparison ran")
+    share = MASKED["masked"] / MASKED["decisions"]
+    print(f"decision parity: {MASKED['decisions']} decisions compared, {MASKED['masked']} inside the exclusion zone ({share:.4%})")
+    assert share <= 1e-3

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtvc.so"
 STAMP = PKG_DIR / ".libtvc.stamp"
-SOURCES = ["tvc_gemm_topk.cu", "tvc_gemm_topk_pair.cu", "tvc_aux.cu", "tvc_consistency.cu", "tvc_api.cu"]
+SOURCES = ["tvc_gemm_topk.cu", "tvc_gemm_topk_pair.cu", "tvc_gemm_topk_ts.cu", "tvc_aux.cu", "tvc_consistency.cu", "tvc_api.cu"]
 HEADERS = ["tvc_ptx.cuh", "tvc_topk.cuh", "tvc_internal.h", "../../include/tvc.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -43,6 +43,12 @@ struct tvc_ctx {
   int64_t pair_min_rows = 4096;  // TVC_PAIR_MIN_ROWS overrides (0 = always, huge = never)
   // pacing of the CTA pairs of a wave (SearchPlan::pace): a producer may run pace_ahead blocks of pace_every
   // gallery tiles ahead of the slowest pair of its wave; pace_every = 0 switches it off (TVC_PACE_EVERY / _AHEAD)
+  // resident-query kernel (tvc_gemm_topk_ts.cu): used when a unit spans at least this many 256-row gallery tiles
+  // (the query tile is loaded into tensor memory once per unit).  OFF by default (INT64_MAX): bit-identical to the
+  // pair kernel but at N = 64 - all that fits next to a 768-wide query tile in tensor memory - the MMA is bound by
+  // the A read from TMEM (0.53x the pair kernel's rate, profiles/r2j_probe.log); kept as the measured experiment
+  // and for its test (TVC_TS_MIN_TILES / option "ts_min_tiles" switch it on)
+  int64_t ts_min_tiles = INT64_MAX;
   int64_t pace_every = 8;     // measured on the bench workload (profiles/r2h_pace.log): 2..8 tiles x 1..4 blocks
   int64_t pace_ahead = 2;     // all give 98.7-99.2 ms per step against 102.0-102.6 unpaced; 16 x 3: 101.4-101.8
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
@@ -66,6 +72,8 @@ struct tvc_gallery {
   float* f32 = nullptr;
   CUtensorMap tmap;      // box [64 x 256]: single-CTA kernel
   CUtensorMap tmap128;   // box [64 x 128]: CTA-pair kernel (each CTA stages half a gallery tile)
+  CUtensorMap tmap3;     // {64, rows, k-blocks} with box {64, 32, 4}: resident-query kernel
+  bool tmap3_ok = false;
   int64_t tmap_rows = -1;
 };
 
@@ -226,7 +234,20 @@ int gallery_tmap(tvc_gallery* g) {
   if (g->tmap_rows == g->n) return TVC_OK;
   int rc = make_tmap(g->ctx, &g->tmap, g->bf16, g->n, g->d_pad, kBN);
   if (rc == TVC_OK) rc = make_tmap(g->ctx, &g->tmap128, g->bf16, g->n, g->d_pad, 128);
-  if (rc == TVC_OK) g->tmap_rows = g->n;
+  if (rc == TVC_OK) {
+    // the same rows seen as {k within a block, row, k-block}: one box = 32 rows x 4 k-blocks, landing as four
+    // [32 x 64] swizzled slabs.  (The k-block stride is smaller than the row stride; if a driver refuses that,
+    // searches stay on the pair kernel.)
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(kBK), static_cast<cuuint64_t>(g->n),
+                                static_cast<cuuint64_t>(g->d_pad / kBK)};
+    const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(g->d_pad) * 2, static_cast<cuuint64_t>(kBK) * 2};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), 32, 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    g->tmap3_ok = g->ctx->encode(&g->tmap3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, g->bf16, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    g->tmap_rows = g->n;
+  }
   return rc;
 }
 
@@ -386,6 +407,7 @@ int tvc_ctx_create(int device, tvc_ctx** out) {
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
   ctx->launches0 = launches_so_far();
   if (const char* e = getenv("TVC_PAIR_MIN_ROWS")) ctx->pair_min_rows = atoll(e);
+  if (const char* e = getenv("TVC_TS_MIN_TILES")) ctx->ts_min_tiles = atoll(e);
   if (const char* e = getenv("TVC_PACE_EVERY")) ctx->pace_every = atoll(e);
   if (const char* e = getenv("TVC_PACE_AHEAD")) ctx->pace_ahead = atoll(e);
   *out = ctx;
@@ -435,6 +457,10 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   }
   if (strcmp(name, "debug_flags") == 0) {
     ctx->debug_flags = value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "ts_min_tiles") == 0) {
+    ctx->ts_min_tiles = value;
     return TVC_OK;
   }
   if (strcmp(name, "pace_every") == 0) {
@@ -840,7 +866,12 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
     }
     TVC_CUDA(ctx, cudaEventRecord(ev.first, st));
   }
-  if (plan.pair)
+  // shortest unit of the plan, in 256-row gallery tiles
+  const int64_t unit_tiles = plan.rem_tiles > 0 ? plan.tiles_per_split : plan.n_tiles;
+  const bool resident_q = plan.pair && g->tmap3_ok && plan.kblocks <= ts_max_kblocks() && unit_tiles >= ctx->ts_min_tiles;
+  if (resident_q)
+    TVC_CUDA(ctx, launch_gemm_topk_ts(g->tmap3, q_bf, plan, cand_val, cand_idx, st));
+  else if (plan.pair)
     TVC_CUDA(ctx, launch_gemm_topk_pair(tq, g->tmap128, plan, cand_val, cand_idx, st));
   else
     TVC_CUDA(ctx, launch_gemm_topk(tq, g->tmap, plan, cand_val, cand_idx, st));

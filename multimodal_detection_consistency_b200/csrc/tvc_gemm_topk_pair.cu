@@ -83,6 +83,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int stage = 0;
     uint32_t phase = 0;
     bool pacing = p.pace != nullptr && rank == 0;   // the peer CTA follows through the shared ring
+    long long issued = 0;
     for (int u = pair; u < total_units; u += num_pairs) {
       const SearchUnit un = plan_unit(p, u);
       const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
@@ -109,9 +110,13 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
-          if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * kPStageBytes);
+          // profiling only (debug bit 2, results are garbage): the query tile is loaded for the first trip round the
+          // ring and stale shared memory multiplied afterwards - what a query operand that never travels would save
+          const bool skip_a = (p.debug & 4) && issued >= kPStages;
+          ++issued;
+          if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], skip_a ? 2 * kPBBytes : 2 * kPStageBytes);
           uint8_t* sa = smem + stage * kPStageBytes;
-          tma_load_2d_pair(&tmap_q, full_leader, sa, kb * kBK, q_row, kEvictLast);
+          if (!skip_a) tma_load_2d_pair(&tmap_q, full_leader, sa, kb * kBK, q_row, kEvictLast);
           tma_load_2d_pair(&tmap_g, full_leader, sa + kPABytes, kb * kBK, g_row, kEvictNormal);
           if (++stage == kPStages) {
             stage = 0;

@@ -95,6 +95,12 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
                                   const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
                                   cudaStream_t stream);
 
+// resident-query revision (tvc_gemm_topk_ts.cu): the query tile lives in tensor memory for the whole unit;
+// tmap_g3 = the gallery as {64, rows, k-blocks} with a {64, 32, 4} box; q_bf = prepared bf16 queries [m, d_pad]
+int ts_max_kblocks();
+cudaError_t launch_gemm_topk_ts(const CUtensorMap& tmap_g3, const __nv_bfloat16* q_bf, const SearchPlan& plan,
+                                float* cand_val, int32_t* cand_idx, cudaStream_t stream);
+
 cudaError_t launch_gemm_store(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g, int m, int n,
                               int kblocks, float* out, int64_t ld_out, int sm_count,
                               cudaStream_t stream);

@@ -53,12 +53,12 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
 // One 128 x 256 accumulator buffer: read this thread's lane 32 columns at a time; a chunk whose
 // maximum does not beat the current KP-th best costs one tcgen05.ld + a max tree; otherwise the chunk
 // is staged through shared memory (keeps `top` in registers) and walked with bubble inserts.
-template <int KP>
+template <int KP, int NCOLS = kBN>
 __device__ __forceinline__ void topk_consume_tile(TopList<KP>& top, float& thr, uint32_t t_addr, float* my_stage,
                                                   int col_base, int n_rows, long long self_col,
                                                   int debug = 0) {
 #pragma unroll 1
-  for (int c = 0; c < kBN / 32; ++c) {
+  for (int c = 0; c < NCOLS / 32; ++c) {
     uint32_t r[32];
     tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
     tmem_ld_wait();

@@ -48,12 +48,19 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   float* sStage = reinterpret_cast<float*>(smem + kPSmemStage);
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem + kPSmemBar);
 
-  const int warp = threadIdx.x >> 5;
+  // Warp index and CTA rank in forms the compiler can prove warp-uniform (a shuffle result, blockIdx): the two
+  // issue loops below then run on the uniform datapath.  As single-thread branches (threadIdx.x == 0 / 32) every
+  // UTCHMMA / UTMALDG sat in a divergence "waterfall" (ELECT + 5 R2UR + BRA.U.ANY each) and one k-block cost the
+  // issuing thread ~90 dependent instructions - about the 512 cycles the tensor cores need for it, so the issue
+  // thread, not the tensor pipe, set the pace (a handful of extra instructions in that loop cost 6 %).
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const uint32_t rank = blockIdx.x & 1u;         // == %cluster_ctarank of a (2,1,1) cluster; 0 = leader
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int total_units = plan_units(p);  // m_tiles counts 256-row tiles here
+  // profiling only: debug bits 4-6 = use fewer stages of the ring (how thin a ring still covers the L2 latency)
+  const int nstages = ((p.debug >> 4) & 7) ? min(kPStages, (p.debug >> 4) & 7) : kPStages;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -77,56 +84,68 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   cluster_sync_all();   // barrier inits of both CTAs visible before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars_base = smem_u32(bars);
 
-  if (threadIdx.x == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; whole warp
+    // walks the loop, one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     bool pacing = p.pace != nullptr && rank == 0;   // the peer CTA follows through the shared ring
     long long issued = 0;
     for (int u = pair; u < total_units; u += num_pairs) {
       const SearchUnit un = plan_unit(p, u);
-      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
+      const int mt = un.mt, t0 = un.t0, t1 = un.t1;
       const int q_row = mt * 256 + static_cast<int>(rank) * 128;
       const bool paced = pacing && u < p.full_tiles;
       unsigned int* pace_row = paced ? p.pace + static_cast<size_t>(u / num_pairs) * p.pace_blocks : nullptr;
       for (int nt = t0; nt < t1; ++nt) {
         if (paced && pacing && nt % p.pace_every == 0) {
           const int c = nt / p.pace_every;
-          atomicAdd(pace_row + c, 1u);
-          if (c >= p.pace_ahead) {
-            const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
-            const long long t_start = clock64();
-            while (*behind < static_cast<unsigned int>(num_pairs)) {
-              if (clock64() - t_start > kPaceTimeoutCycles) {
-                pacing = false;   // a pair of this wave is not running: stop waiting for it
-                break;
+          int keep = 1;
+          if (lane == 0) {
+            atomicAdd(pace_row + c, 1u);
+            if (c >= p.pace_ahead) {
+              const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
+              const long long t_start = clock64();
+              while (*behind < static_cast<unsigned int>(num_pairs)) {
+                if (clock64() - t_start > kPaceTimeoutCycles) {
+                  keep = 0;   // a pair of this wave is not running: stop waiting for it
+                  break;
+                }
+                __nanosleep(256);
               }
-              __nanosleep(256);
             }
           }
+          pacing = __shfl_sync(0xffffffffu, keep, 0) != 0;
         }
         const int g_row = nt * kBN + static_cast<int>(rank) * 128;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
+          // the leader's barrier of this stage: same offset, CTA-rank bit of the shared::cluster address cleared
+          const uint32_t full_leader = (bars_base + static_cast<uint32_t>(offsetof(PairBarriers, full) + 8 * stage)) & kLeaderCtaMask;
           // profiling only (debug bit 2, results are garbage): the query tile is loaded for the first trip round the
           // ring and stale shared memory multiplied afterwards - what a query operand that never travels would save
           const bool skip_a = (p.debug & 4) && issued >= kPStages;
           ++issued;
-          if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], skip_a ? 2 * kPBBytes : 2 * kPStageBytes);
-          uint8_t* sa = smem + stage * kPStageBytes;
-          if (!skip_a) tma_load_2d_pair(&tmap_q, full_leader, sa, kb * kBK, q_row, kEvictLast);
-          tma_load_2d_pair(&tmap_g, full_leader, sa + kPABytes, kb * kBK, g_row, kEvictNormal);
-          if (++stage == kPStages) {
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage * kPStageBytes);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], skip_a ? 2 * kPBBytes : 2 * kPStageBytes);
+            if (!skip_a) tma_load_2d_pair_u32(&tmap_q, full_leader, sa, kb * kBK, q_row, kEvictLast);
+            tma_load_2d_pair_u32(&tmap_g, full_leader, sa + kPABytes, kb * kBK, g_row, kEvictNormal);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
     }
-  } else if (threadIdx.x == 32 && rank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (leader only)
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader only; whole warp walks
+    // the loop, one elected lane - always the same - issues the MMAs and their commits)
     constexpr uint32_t idesc = umma_idesc_bf16_f32(256, kBN);
     int stage = 0;
     uint32_t phase = 0;
@@ -142,20 +161,24 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          uint8_t* sa = smem + stage * kPStageBytes;
-          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(sa));
-          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(sa + kPABytes));
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage * kPStageBytes);
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sa + kPABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&bars->empty[stage], 3);
-          if (++stage == kPStages) {
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&bars->empty[stage], 3);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit_pair(&bars->tmem_full[acc], 3);
+        if (elect_one()) umma_commit_pair(&bars->tmem_full[acc], 3);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -201,6 +224,248 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pair kernel with a (mostly) RESIDENT query tile.  A unit multiplies one 256-row query tile with thousands of
+// gallery tiles; the kernel above re-delivers that tile through the ring for every gallery tile - half of the
+// L2 -> SM traffic and of the shared-memory writes.  Not re-loading it at all is worth +5.9 % under the 1 kW cap
+// (stale-operand probe, debug bit 4, profiles/r2i_probe_a.log); the ring needs only 3 k-blocks of lookahead to
+// cover the L2 latency (4 of the 6 stages: same speed, 3: -11 %, profiles/r2k_ring.log).  So here the first
+// kRqResident = 7 k-blocks of this CTA's 128 query rows (112 KB at d >= 448) stay in shared memory for the whole
+// unit and the ring shrinks to 6 slots of 16 KB that carry the gallery k-blocks and the query k-blocks that did
+// not fit (17 slots per gallery tile at d = 768 = 3.5 k-blocks of lookahead).  Same MMAs on the same operands in
+// the same order as the kernel above: bit-identical results.
+//   thread 0    TMA producer of the ring (gallery k-blocks, streamed query k-blocks), paced
+//   thread 32   MMA issuer (leader): per unit waits a_full; A descriptors point into the resident area or a slot;
+//               after a unit's last MMA a multicast commit on a_empty lets both CTAs replace the resident tile
+//   thread 96   resident-tile loader: waits a_empty (previous unit computed), loads the next unit's k-blocks,
+//               completion on the leader's a_full - on its own thread so that the ring keeps streaming meanwhile
+constexpr int kRqResident = 7;
+constexpr int kRqSlots = 6;
+constexpr int kRqSlotBytes = kPABytes;                       // 16 KB: [128 rows x 64] bf16, A or B
+constexpr int kRqSmemRes = kRqResident * kRqSlotBytes;       // 112 KB
+constexpr int kRqSmemRing = kRqSmemRes + kRqSlots * kRqSlotBytes;   // end of the interleaved operand area
+// Layout experiment: resident k-block kb at 16 KB unit 2 kb, ring slot s at unit 2 s + 1, so that the A and the B
+// operand of an MMA on a resident k-block always differ in address bit 14
+__device__ __forceinline__ int rq_res_off(int kb) { return (2 * kb) * kRqSlotBytes; }
+__device__ __forceinline__ int rq_slot_off(int s) { return (2 * s + 1) * kRqSlotBytes; }
+constexpr int kRqSmemBar = kRqSmemRing + kStageFloats * 4;
+constexpr int kRqSmemTotal = kRqSmemBar + 256 + 1024;
+static_assert(kPABytes == kPBBytes, "one slot size for both operands");
+
+struct RqBarriers {
+  uint64_t full[kRqSlots];      // used in the leader CTA only
+  uint64_t empty[kRqSlots];     // per CTA, arrived by the leader's multicast commit
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t a_full;              // leader only: the unit's resident query k-blocks of both CTAs have landed
+  uint64_t a_empty;             // per CTA: every MMA of the unit has completed
+  uint32_t tmem_base;
+};
+
+template <int KP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                         const __grid_constant__ CUtensorMap tmap_g, const SearchPlan p,
+                         float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  float* sStage = reinterpret_cast<float*>(smem + kRqSmemRing);
+  RqBarriers* bars = reinterpret_cast<RqBarriers*>(smem + kRqSmemBar);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_units = plan_units(p);
+  const int n_res = p.kblocks < kRqResident ? p.kblocks : kRqResident;   // resident query k-blocks
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+    for (int s = 0; s < kRqSlots; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], 8);
+    }
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(&bars->tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (threadIdx.x == 0) {
+    // ------------------------------------------------------------------ ring producer (both CTAs)
+    int slot = 0;
+    uint32_t phase = 0;
+    bool pacing = p.pace != nullptr && rank == 0;
+    bool first_unit = true;
+    uint32_t a_ph = 0;
+    auto push = [&](const CUtensorMap* tm, int c0, int c1, uint64_t hint) {
+      mbar_wait(&bars->empty[slot], phase ^ 1u);
+      const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[slot]), 0);
+      if (rank == 0) mbar_arrive_expect_tx(&bars->full[slot], 2 * kRqSlotBytes);
+      tma_load_2d_pair(tm, full_leader, smem + rq_slot_off(slot), c0, c1, hint);
+      if (++slot == kRqSlots) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    };
+    for (int u = pair; u < total_units; u += num_pairs) {
+      const SearchUnit un = plan_unit(p, u);
+      const int mt = un.mt, t0 = un.t0, t1 = un.t1;
+      const int q_row = mt * 256 + static_cast<int>(rank) * 128;
+      const bool paced = pacing && u < p.full_tiles;
+      unsigned int* pace_row = paced ? p.pace + static_cast<size_t>(u / num_pairs) * p.pace_blocks : nullptr;
+      {   // the unit's resident query k-blocks (the previous unit's MMAs must have read theirs for the last time)
+        if (!first_unit) {
+          mbar_wait(&bars->a_empty, a_ph);
+          a_ph ^= 1u;
+        }
+        first_unit = false;
+        const uint32_t a_full_leader = mapa_u32(smem_u32(&bars->a_full), 0);
+        if (rank == 0) mbar_arrive_expect_tx(&bars->a_full, static_cast<uint32_t>(2 * n_res * kRqSlotBytes));
+        for (int kb = 0; kb < n_res; ++kb)
+          tma_load_2d_pair(&tmap_q, a_full_leader, smem + rq_res_off(kb), kb * kBK, q_row, kEvictNormal);
+      }
+      for (int nt = t0; nt < t1; ++nt) {
+        if (paced && pacing && nt % p.pace_every == 0) {
+          const int c = nt / p.pace_every;
+          atomicAdd(pace_row + c, 1u);
+          if (c >= p.pace_ahead) {
+            const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
+            const long long t_start = clock64();
+            while (*behind < static_cast<unsigned int>(num_pairs)) {
+              if (clock64() - t_start > kPaceTimeoutCycles) {
+                pacing = false;
+                break;
+              }
+              __nanosleep(256);
+            }
+          }
+        }
+        const int g_row = nt * kBN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (kb >= n_res) push(&tmap_q, kb * kBK, q_row, kEvictLast);
+          push(&tmap_g, kb * kBK, g_row, kEvictNormal);
+        }
+      }
+    }
+  } else if (threadIdx.x == 32 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(256, kBN);
+    int slot = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0, a_phase = 0;
+    auto advance = [&]() {
+      if (++slot == kRqSlots) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    };
+    for (int u = pair; u < total_units; u += num_pairs) {
+      const SearchUnit un = plan_unit(p, u);
+      const int t0 = un.t0, t1 = un.t1;
+      mbar_wait(&bars->a_full, a_phase);
+      a_phase ^= 1u;
+      tc_fence_after();
+      for (int nt = t0; nt < t1; ++nt) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          uint64_t da;
+          int a_slot = -1;
+          if (kb < n_res) {
+            da = umma_desc_sw128_kmajor(smem_u32(smem + rq_res_off(kb)));
+          } else {
+            mbar_wait(&bars->full[slot], phase);
+            a_slot = slot;
+            da = umma_desc_sw128_kmajor(smem_u32(smem + rq_slot_off(slot)));
+            advance();
+          }
+          mbar_wait(&bars->full[slot], phase);
+          tc_fence_after();
+          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem + rq_slot_off(slot)));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+          if (a_slot >= 0) umma_commit_pair(&bars->empty[a_slot], 3);
+          umma_commit_pair(&bars->empty[slot], 3);
+          advance();
+        }
+        umma_commit_pair(&bars->tmem_full[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      umma_commit_pair(&bars->a_empty, 3);   // both CTAs may now replace their resident k-blocks
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ top-k epilogue (both CTAs)
+    const int q4 = warp & 3;
+    const int row_in_tile = q4 * 32 + lane;
+    float* my_stage = sStage + row_in_tile;
+    TopList<KP> top;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = pair; u < total_units; u += num_pairs) {
+      const SearchUnit un = plan_unit(p, u);
+      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
+      const int row = mt * 256 + static_cast<int>(rank) * 128 + row_in_tile;
+      const long long self_col = p.skip_self ? static_cast<long long>(row) + p.self_offset : -1ll;
+      top.reset();
+      float thr = -INFINITY;
+      for (int nt = t0; nt < t1; ++nt) {
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr =
+            tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+        if (!(p.debug & 1)) topk_consume_tile<KP>(top, thr, t_addr, my_stage, nt * kBN, p.n_rows, self_col, p.debug);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (row < p.m_rows) topk_store<KP>(top, cand_val, cand_idx,
+                                       plan_cand_base(static_cast<long long>(p.full_tiles) * 256, p.splits, KP, row, split));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int KP>
+cudaError_t launch_pair_rq_kp(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
+                              int32_t* ci, cudaStream_t stream) {
+  static SmemAttrOnce configured;
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_topk_pair_rq_kernel<KP>), kRqSmemTotal); e != cudaSuccess)
+    return e;
+  gemm_topk_pair_rq_kernel<KP><<<plan.grid, kThreads, kRqSmemTotal, stream>>>(tq, tg, plan, cv, ci);
+  note_launch();
+  return cudaGetLastError();
+}
+
 template <int KP>
 cudaError_t launch_pair_kp(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
                            int32_t* ci, cudaStream_t stream) {
@@ -224,6 +489,21 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
       return launch_pair_kp<32>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
     case 64:
       return launch_pair_kp<64>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
+                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                                     cudaStream_t stream) {
+  switch (plan.kp) {
+    case 16:
+      return launch_pair_rq_kp<16>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+    case 32:
+      return launch_pair_rq_kp<32>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+    case 64:
+      return launch_pair_rq_kp<64>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
     default:
       return cudaErrorInvalidValue;
   }

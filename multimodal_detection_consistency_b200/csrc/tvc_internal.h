@@ -95,6 +95,11 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
                                   const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
                                   cudaStream_t stream);
 
+// pair kernel with the first 7 k-blocks of the query tile resident in shared memory for the whole unit
+cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
+                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                                     cudaStream_t stream);
+
 // resident-query revision (tvc_gemm_topk_ts.cu): the query tile lives in tensor memory for the whole unit;
 // tmap_g3 = the gallery as {64, rows, k-blocks} with a {64, 32, 4} box; q_bf = prepared bf16 queries [m, d_pad]
 int ts_max_kblocks();

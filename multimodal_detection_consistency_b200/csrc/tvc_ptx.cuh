@@ -215,6 +215,20 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* tmap, uint32_t bar_
         "r"(c1), "l"(cache_hint)
       : "memory");
 }
+// same, destination given as a shared-memory address (kept in a uniform register by warp-uniform callers)
+__device__ __forceinline__ void tma_load_2d_pair_u32(const void* tmap, uint32_t bar_cluster_addr, uint32_t smem_dst,
+                                                     int32_t c0, int32_t c1, uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "l"(cache_hint)
+      : "memory");
+}
+// A CTA's own shared-memory addresses carry its rank inside the cluster from bit 24 up; clearing bit 24 names the
+// same offset in the even (leader) CTA of a cta_group::2 pair - what mapa(addr, rank & ~1) returns, as arithmetic
+constexpr uint32_t kLeaderCtaMask = 0xFEFFFFFFu;
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)

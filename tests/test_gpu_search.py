@@ -181,34 +181,41 @@ def test_pair_kernel_matches_oracle(tvc_ctx, m, n, d, k):
 
 @pytest.mark.parametrize("m,n,d,k", [(256, 2048, 64, 10), (300, 5000, 128, 10), (1000, 9000, 768, 10), (4500, 30000, 768, 10),
                                      (2500, 9000, 512, 20), (700, 6000, 320, 10), (640, 3000, 96, 50), (513, 4099, 704, 1)])
-def test_resident_query_kernel_matches_pair_kernel(tvc_ctx, m, n, d, k):
-    """The resident-query kernel (query tile in tensor memory, N = 64 MMA tiles, 3-D TMA boxes), forced for every
-    size, against the oracle and against the CTA-pair kernel: bit-identical outputs (same bf16 operands and k order
-    into the same fp32 accumulators, same column order into the top-k lists).  Covers ragged last tiles in both
-    dimensions, several query tiles per pair (units back to back: the tile in tensor memory is replaced), k-block
-    counts that are not a multiple of the 4 a TMA box carries (d = 320, 704: zero-filled k-blocks are skipped),
-    KP = 16 / 32 / 64, ties and skip_self."""
+def test_resident_query_kernels_match_pair_kernel(tvc_ctx, m, n, d, k):
+    """The two resident-query revisions of kernel (a), forced for every size, against the oracle and against the plain
+    CTA-pair kernel: bit-identical outputs (same bf16 operands and k order into the same fp32 accumulators, same
+    column order into the top-k lists).
+      rq: first 7 k-blocks of the query tile resident in shared memory, the rest and the gallery through a 6-slot ring
+          (the default for long units);
+      ts: query tile in tensor memory, N = 64 MMA tiles, 3-D TMA boxes (measured slower, off by default).
+    Covers ragged last tiles in both dimensions, several query tiles per pair (units back to back: the resident tile
+    is replaced), d <= 448 (everything resident) and d > 448 (streamed query k-blocks), k-block counts that are not a
+    multiple of the 4 a 3-D box carries (d = 320, 704), KP = 16 / 32 / 64, ties and skip_self."""
     import multimodal_detection_consistency_b200 as tvc
     rng = np.random.default_rng(m * 7 + n)
     g, q = _unit(rng, n, d), _unit(rng, m, d)
     g[n // 2] = g[3]                                   # a tie
     gal = tvc.Gallery(g, ctx=tvc_ctx)
+    never = 1 << 62
+    got = {}
     try:
         tvc_ctx.set_option("pair_min_rows", 0)
-        tvc_ctx.set_option("ts_min_tiles", 1)
-        sims, idx = gal.search(q, k)
-        sims_self, idx_self = (gal.search(g[:m], k, skip_self=True) if m <= n else (None, None))
-        tvc_ctx.set_option("ts_min_tiles", 1 << 62)
-        sims1, idx1 = gal.search(q, k)
+        for name, rq, ts in (("rq", 1, never), ("ts", never, 1), ("pair", never, never)):
+            tvc_ctx.set_option("rq_min_tiles", rq)
+            tvc_ctx.set_option("ts_min_tiles", ts)
+            got[name] = gal.search(q, k) + (gal.search(g[:m], k, skip_self=True) if m <= n else (None, None))
     finally:
         tvc_ctx.set_option("pair_min_rows", 4096)
-        tvc_ctx.set_option("ts_min_tiles", 1 << 62)     # the default: off (measured slower, see the kernel's header)
+        tvc_ctx.set_option("rq_min_tiles", 64)
+        tvc_ctx.set_option("ts_min_tiles", never)     # the default: off (measured slower, see the kernel's header)
     ref_s, ref_i = O.search(q, g, k)
-    _check_topk(sims, idx, ref_s, ref_i, q @ g.T)
-    assert np.array_equal(idx, idx1) and np.array_equal(sims, sims1)
-    if idx_self is not None:
+    _check_topk(got["pair"][0], got["pair"][1], ref_s, ref_i, q @ g.T)
+    for name in ("rq", "ts"):
+        for a, b in zip(got[name], got["pair"]):
+            assert (a is None and b is None) or np.array_equal(a, b), name
+    if got["pair"][3] is not None:
         rs, ri = O.search(g[:m], g, k, skip_self=True)
-        _check_topk(sims_self, idx_self, rs, ri, g[:m] @ g.T)
+        _check_topk(got["pair"][2], got["pair"][3], rs, ri, g[:m] @ g.T)
 
 
 @pytest.mark.parametrize("n,d,m,k,shards", [(5000, 256, 700, 10, 3), (40000, 128, 5000, 10, 4), (900, 64, 33, 5, 2)])

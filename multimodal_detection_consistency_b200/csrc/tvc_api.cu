@@ -52,6 +52,7 @@ struct tvc_ctx {
   // pair kernel with a resident query tile: units of at least this many 256-row gallery tiles (the tile is
   // swapped once per unit, ~2 us); INT64_MAX = never (TVC_RQ_MIN_TILES / option "rq_min_tiles")
   int64_t rq_min_tiles = 64;
+  int64_t rq_resident = 0;    // resident query k-blocks (5..7); 0 = by dimension (TVC_RQ_RESIDENT, measurements)
   int64_t pace_every = 8;     // measured on the bench workload (profiles/r2h_pace.log): 2..8 tiles x 1..4 blocks
   int64_t pace_ahead = 2;     // all give 98.7-99.2 ms per step against 102.0-102.6 unpaced; 16 x 3: 101.4-101.8
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
@@ -412,6 +413,7 @@ int tvc_ctx_create(int device, tvc_ctx** out) {
   if (const char* e = getenv("TVC_PAIR_MIN_ROWS")) ctx->pair_min_rows = atoll(e);
   if (const char* e = getenv("TVC_TS_MIN_TILES")) ctx->ts_min_tiles = atoll(e);
   if (const char* e = getenv("TVC_RQ_MIN_TILES")) ctx->rq_min_tiles = atoll(e);
+  if (const char* e = getenv("TVC_RQ_RESIDENT")) ctx->rq_resident = atoll(e);
   if (const char* e = getenv("TVC_PACE_EVERY")) ctx->pace_every = atoll(e);
   if (const char* e = getenv("TVC_PACE_AHEAD")) ctx->pace_ahead = atoll(e);
   *out = ctx;
@@ -461,6 +463,10 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   }
   if (strcmp(name, "debug_flags") == 0) {
     ctx->debug_flags = value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "rq_resident") == 0) {
+    ctx->rq_resident = (value >= 5 && value <= 7) ? value : 0;
     return TVC_OK;
   }
   if (strcmp(name, "rq_min_tiles") == 0) {
@@ -880,7 +886,7 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
   if (resident_q)
     TVC_CUDA(ctx, launch_gemm_topk_ts(g->tmap3, q_bf, plan, cand_val, cand_idx, st));
   else if (plan.pair && unit_tiles >= ctx->rq_min_tiles)
-    TVC_CUDA(ctx, launch_gemm_topk_pair_rq(tq, g->tmap128, plan, cand_val, cand_idx, st));
+    TVC_CUDA(ctx, launch_gemm_topk_pair_rq(tq, g->tmap128, plan, cand_val, cand_idx, static_cast<int>(ctx->rq_resident), st));
   else if (plan.pair)
     TVC_CUDA(ctx, launch_gemm_topk_pair(tq, g->tmap128, plan, cand_val, cand_idx, st));
   else

@@ -59,7 +59,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   float* sStage = reinterpret_cast<float*>(smem + kSmemStage);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemBar);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index in a form the compiler can prove warp-uniform: the two issue loops run on the uniform datapath, one
+  // elected lane issues (see tvc_gemm_topk_pair.cu)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_units = plan_units(p);
 
@@ -85,21 +87,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const SearchUnit un = plan_unit(p, u);
-      const int split = un.split, mt = un.mt, t0 = un.t0, t1 = un.t1;
+      const int mt = un.mt, t0 = un.t0, t1 = un.t1;
       for (int nt = t0; nt < t1; ++nt) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
-          tma_load_2d(&tmap_q, &bars->full[stage], sA + stage * kABytes, kb * kBK, mt * kBM,
-                      kEvictLast);
-          tma_load_2d(&tmap_g, &bars->full[stage], sB + stage * kBBytes, kb * kBK, nt * kBN,
-                      kEvictNormal);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
+            tma_load_2d(&tmap_q, &bars->full[stage], sA + stage * kABytes, kb * kBK, mt * kBM,
+                        kEvictLast);
+            tma_load_2d(&tmap_g, &bars->full[stage], sB + stage * kBBytes, kb * kBK, nt * kBN,
+                        kEvictNormal);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -107,9 +112,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    const uint32_t sA_base = smem_u32(sA), sB_base = smem_u32(sB);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -124,21 +130,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(sA + stage * kABytes));
-          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(sB + stage * kBBytes));
+          const uint64_t da = umma_desc_sw128_kmajor(sA_base + static_cast<uint32_t>(stage * kABytes));
+          const uint64_t db = umma_desc_sw128_kmajor(sB_base + static_cast<uint32_t>(stage * kBBytes));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance the start address by 16 bf16 = 32 bytes (>>4 = 2) inside the swizzle row
-            umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                         idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance the start address by 16 bf16 = 32 bytes (>>4 = 2) inside the swizzle row
+              umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                           idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&bars->empty[stage]);  // slot reusable once these MMAs have read it
           }
-          umma_commit(&bars->empty[stage]);  // slot reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&bars->tmem_full[acc]);  // accumulator complete
+        if (elect_one()) umma_commit(&bars->tmem_full[acc]);  // accumulator complete
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -196,7 +206,7 @@ gemm_store_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* sA = smem + kSmemA;
   uint8_t* sB = smem + kSmemB;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemBar);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int total_units = m_tiles * n_tiles;
 
@@ -222,26 +232,30 @@ gemm_store_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int nt = u / m_tiles, mt = u - nt * m_tiles;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&bars->empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
-        tma_load_2d(&tmap_q, &bars->full[stage], sA + stage * kABytes, kb * kBK, mt * kBM,
-                    kEvictNormal);
-        tma_load_2d(&tmap_g, &bars->full[stage], sB + stage * kBBytes, kb * kBK, nt * kBN,
-                    kEvictNormal);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->full[stage], kABytes + kBBytes);
+          tma_load_2d(&tmap_q, &bars->full[stage], sA + stage * kABytes, kb * kBK, mt * kBM,
+                      kEvictNormal);
+          tma_load_2d(&tmap_g, &bars->full[stage], sB + stage * kBBytes, kb * kBK, nt * kBN,
+                      kEvictNormal);
+        }
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    const uint32_t sA_base = smem_u32(sA), sB_base = smem_u32(sB);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -253,19 +267,23 @@ gemm_store_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
-        const uint64_t da = umma_desc_sw128_kmajor(smem_u32(sA + stage * kABytes));
-        const uint64_t db = umma_desc_sw128_kmajor(smem_u32(sB + stage * kBBytes));
+        const uint64_t da = umma_desc_sw128_kmajor(sA_base + static_cast<uint32_t>(stage * kABytes));
+        const uint64_t db = umma_desc_sw128_kmajor(sB_base + static_cast<uint32_t>(stage * kBBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&bars->empty[stage]);
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                         idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&bars->empty[stage]);
+        }
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&bars->tmem_full[acc]);
+      if (elect_one()) umma_commit(&bars->tmem_full[acc]);
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

@@ -239,22 +239,17 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 //               after a unit's last MMA a multicast commit on a_empty lets both CTAs replace the resident tile
 //   thread 96   resident-tile loader: waits a_empty (previous unit computed), loads the next unit's k-blocks,
 //               completion on the leader's a_full - on its own thread so that the ring keeps streaming meanwhile
-constexpr int kRqResident = 7;
-constexpr int kRqSlots = 6;
+constexpr int kRqUnits = 13;                                 // 16 KB units of shared memory: resident + ring slots
+constexpr int kRqMaxSlots = 8;
 constexpr int kRqSlotBytes = kPABytes;                       // 16 KB: [128 rows x 64] bf16, A or B
-constexpr int kRqSmemRes = kRqResident * kRqSlotBytes;       // 112 KB
-constexpr int kRqSmemRing = kRqSmemRes + kRqSlots * kRqSlotBytes;   // end of the interleaved operand area
-// Layout experiment: resident k-block kb at 16 KB unit 2 kb, ring slot s at unit 2 s + 1, so that the A and the B
-// operand of an MMA on a resident k-block always differ in address bit 14
-__device__ __forceinline__ int rq_res_off(int kb) { return (2 * kb) * kRqSlotBytes; }
-__device__ __forceinline__ int rq_slot_off(int s) { return (2 * s + 1) * kRqSlotBytes; }
+constexpr int kRqSmemRing = kRqUnits * kRqSlotBytes;         // end of the operand area (208 KB)
 constexpr int kRqSmemBar = kRqSmemRing + kStageFloats * 4;
 constexpr int kRqSmemTotal = kRqSmemBar + 256 + 1024;
 static_assert(kPABytes == kPBBytes, "one slot size for both operands");
 
 struct RqBarriers {
-  uint64_t full[kRqSlots];      // used in the leader CTA only
-  uint64_t empty[kRqSlots];     // per CTA, arrived by the leader's multicast commit
+  uint64_t full[kRqMaxSlots];   // used in the leader CTA only
+  uint64_t empty[kRqMaxSlots];  // per CTA, arrived by the leader's multicast commit
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t a_full;              // leader only: the unit's resident query k-blocks of both CTAs have landed
@@ -262,7 +257,7 @@ struct RqBarriers {
   uint32_t tmem_base;
 };
 
-template <int KP>
+template <int KP, int kRqResident>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_g, const SearchPlan p,
@@ -270,12 +265,15 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int kRqSlots = kRqUnits - kRqResident;
+  constexpr int kRqSmemRes = kRqResident * kRqSlotBytes;
+  static_assert(kRqSlots <= kRqMaxSlots && kRqSlots >= 4, "ring size");
   float* sStage = reinterpret_cast<float*>(smem + kRqSmemRing);
   RqBarriers* bars = reinterpret_cast<RqBarriers*>(smem + kRqSmemBar);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const uint32_t rank = blockIdx.x & 1u;         // == %cluster_ctarank of a (2,1,1) cluster; 0 = leader
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int total_units = plan_units(p);
@@ -305,19 +303,23 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t res_base = smem_u32(smem);                    // resident k-block kb at res_base + kb * 16 KB
+  const uint32_t ring_base = res_base + kRqSmemRes;            // ring slot s at ring_base + s * 16 KB
+  const uint32_t bars_base = smem_u32(bars);
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ ring producer (both CTAs)
     int slot = 0;
     uint32_t phase = 0;
     bool pacing = p.pace != nullptr && rank == 0;
-    bool first_unit = true;
-    uint32_t a_ph = 0;
     auto push = [&](const CUtensorMap* tm, int c0, int c1, uint64_t hint) {
       mbar_wait(&bars->empty[slot], phase ^ 1u);
-      const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[slot]), 0);
-      if (rank == 0) mbar_arrive_expect_tx(&bars->full[slot], 2 * kRqSlotBytes);
-      tma_load_2d_pair(tm, full_leader, smem + rq_slot_off(slot), c0, c1, hint);
+      const uint32_t full_leader = (bars_base + static_cast<uint32_t>(offsetof(RqBarriers, full) + 8 * slot)) & kLeaderCtaMask;
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&bars->full[slot], 2 * kRqSlotBytes);
+        tma_load_2d_pair_u32(tm, full_leader, ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), c0, c1, hint);
+      }
+      __syncwarp();
       if (++slot == kRqSlots) {
         slot = 0;
         phase ^= 1u;
@@ -329,41 +331,56 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int q_row = mt * 256 + static_cast<int>(rank) * 128;
       const bool paced = pacing && u < p.full_tiles;
       unsigned int* pace_row = paced ? p.pace + static_cast<size_t>(u / num_pairs) * p.pace_blocks : nullptr;
-      {   // the unit's resident query k-blocks (the previous unit's MMAs must have read theirs for the last time)
-        if (!first_unit) {
-          mbar_wait(&bars->a_empty, a_ph);
-          a_ph ^= 1u;
-        }
-        first_unit = false;
-        const uint32_t a_full_leader = mapa_u32(smem_u32(&bars->a_full), 0);
-        if (rank == 0) mbar_arrive_expect_tx(&bars->a_full, static_cast<uint32_t>(2 * n_res * kRqSlotBytes));
-        for (int kb = 0; kb < n_res; ++kb)
-          tma_load_2d_pair(&tmap_q, a_full_leader, smem + rq_res_off(kb), kb * kBK, q_row, kEvictNormal);
-      }
       for (int nt = t0; nt < t1; ++nt) {
         if (paced && pacing && nt % p.pace_every == 0) {
           const int c = nt / p.pace_every;
-          atomicAdd(pace_row + c, 1u);
-          if (c >= p.pace_ahead) {
-            const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
-            const long long t_start = clock64();
-            while (*behind < static_cast<unsigned int>(num_pairs)) {
-              if (clock64() - t_start > kPaceTimeoutCycles) {
-                pacing = false;
-                break;
+          int keep = 1;
+          if (lane == 0) {
+            atomicAdd(pace_row + c, 1u);
+            if (c >= p.pace_ahead) {
+              const volatile unsigned int* behind = pace_row + (c - p.pace_ahead);
+              const long long t_start = clock64();
+              while (*behind < static_cast<unsigned int>(num_pairs)) {
+                if (clock64() - t_start > kPaceTimeoutCycles) {
+                  keep = 0;
+                  break;
+                }
+                __nanosleep(256);
               }
-              __nanosleep(256);
             }
           }
+          pacing = __shfl_sync(0xffffffffu, keep, 0) != 0;
         }
         const int g_row = nt * kBN + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          if (kb >= n_res) push(&tmap_q, kb * kBK, q_row, kEvictLast);
+        for (int kb = 0; kb < n_res; ++kb) push(&tmap_g, kb * kBK, g_row, kEvictNormal);
+        for (int kb = n_res; kb < p.kblocks; ++kb) {
+          push(&tmap_q, kb * kBK, q_row, kEvictLast);
           push(&tmap_g, kb * kBK, g_row, kEvictNormal);
         }
       }
     }
-  } else if (threadIdx.x == 32 && rank == 0) {
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ resident-tile loader (both CTAs)
+    uint32_t ph = 0;
+    bool first = true;
+    const uint32_t a_full_leader = (bars_base + static_cast<uint32_t>(offsetof(RqBarriers, a_full))) & kLeaderCtaMask;
+    for (int u = pair; u < total_units; u += num_pairs) {
+      const SearchUnit un = plan_unit(p, u);
+      const int q_row = un.mt * 256 + static_cast<int>(rank) * 128;
+      if (!first) {
+        mbar_wait_parked(&bars->a_empty, ph);   // the previous unit's MMAs have read the tile for the last time (a
+        ph ^= 1u;                               // whole unit away: sleep between polls)
+      }
+      first = false;
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&bars->a_full, static_cast<uint32_t>(2 * n_res * kRqSlotBytes));
+        for (int kb = 0; kb < n_res; ++kb)
+          tma_load_2d_pair_u32(&tmap_q, a_full_leader, res_base + static_cast<uint32_t>(kb * kRqSlotBytes), kb * kBK,
+                               q_row, kEvictNormal);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
     constexpr uint32_t idesc = umma_idesc_bf16_f32(256, kBN);
     int slot = 0;
@@ -376,6 +393,19 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
         phase ^= 1u;
       }
     };
+    auto mma4 = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool first_kb, int free_a_slot, int free_b_slot) {
+      const uint64_t da = umma_desc_sw128_kmajor(a_addr);
+      const uint64_t db = umma_desc_sw128_kmajor(b_addr);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                            (first_kb && k == 0) ? 0u : 1u);
+        if (free_a_slot >= 0) umma_commit_pair(&bars->empty[free_a_slot], 3);
+        umma_commit_pair(&bars->empty[free_b_slot], 3);
+      }
+      __syncwarp();
+    };
     for (int u = pair; u < total_units; u += num_pairs) {
       const SearchUnit un = plan_unit(p, u);
       const int t0 = un.t0, t1 = un.t1;
@@ -386,33 +416,30 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBN);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          uint64_t da;
-          int a_slot = -1;
-          if (kb < n_res) {
-            da = umma_desc_sw128_kmajor(smem_u32(smem + rq_res_off(kb)));
-          } else {
-            mbar_wait(&bars->full[slot], phase);
-            a_slot = slot;
-            da = umma_desc_sw128_kmajor(smem_u32(smem + rq_slot_off(slot)));
-            advance();
-          }
+        for (int kb = 0; kb < n_res; ++kb) {          // query k-block resident, gallery k-block from the ring
           mbar_wait(&bars->full[slot], phase);
           tc_fence_after();
-          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem + rq_slot_off(slot)));
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_ss_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
-          if (a_slot >= 0) umma_commit_pair(&bars->empty[a_slot], 3);
-          umma_commit_pair(&bars->empty[slot], 3);
+          mma4(d_tmem, res_base + static_cast<uint32_t>(kb * kRqSlotBytes),
+               ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), kb == 0, -1, slot);
           advance();
         }
-        umma_commit_pair(&bars->tmem_full[acc], 3);
+        for (int kb = n_res; kb < p.kblocks; ++kb) {  // both from the ring: query slot, then gallery slot
+          mbar_wait(&bars->full[slot], phase);
+          const int a_slot = slot;
+          advance();
+          mbar_wait(&bars->full[slot], phase);
+          tc_fence_after();
+          mma4(d_tmem, ring_base + static_cast<uint32_t>(a_slot * kRqSlotBytes),
+               ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), false, a_slot, slot);
+          advance();
+        }
+        if (elect_one()) umma_commit_pair(&bars->tmem_full[acc], 3);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      umma_commit_pair(&bars->a_empty, 3);   // both CTAs may now replace their resident k-blocks
+      if (elect_one()) umma_commit_pair(&bars->a_empty, 3);   // both CTAs may now replace their resident k-blocks
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ top-k epilogue (both CTAs)
@@ -455,15 +482,31 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
-template <int KP>
+template <int KP, int RES>
 cudaError_t launch_pair_rq_kp(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
                               int32_t* ci, cudaStream_t stream) {
   static SmemAttrOnce configured;
-  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_topk_pair_rq_kernel<KP>), kRqSmemTotal); e != cudaSuccess)
+  if (cudaError_t e = configured.ensure(reinterpret_cast<const void*>(gemm_topk_pair_rq_kernel<KP, RES>), kRqSmemTotal);
+      e != cudaSuccess)
     return e;
-  gemm_topk_pair_rq_kernel<KP><<<plan.grid, kThreads, kRqSmemTotal, stream>>>(tq, tg, plan, cv, ci);
+  gemm_topk_pair_rq_kernel<KP, RES><<<plan.grid, kThreads, kRqSmemTotal, stream>>>(tq, tg, plan, cv, ci);
   note_launch();
   return cudaGetLastError();
+}
+
+template <int KP>
+cudaError_t launch_pair_rq_res(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
+                               int32_t* ci, int resident, cudaStream_t stream) {
+  switch (resident) {
+    case 7:
+      return launch_pair_rq_kp<KP, 7>(tq, tg, plan, cv, ci, stream);
+    case 6:
+      return launch_pair_rq_kp<KP, 6>(tq, tg, plan, cv, ci, stream);
+    case 5:
+      return launch_pair_rq_kp<KP, 5>(tq, tg, plan, cv, ci, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
 }
 
 template <int KP>
@@ -495,15 +538,19 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
 }
 
 cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
-                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx, int resident,
                                      cudaStream_t stream) {
+  // 13 units of 16 KB: `resident` query k-blocks + a ring of the rest.  Up to 8 k-blocks (d <= 512) at most one
+  // is streamed and 6 slots are plenty; beyond, every streamed k-block takes two slots, and the ring must still
+  // hold ~2 k-blocks of prefetch on top of the 2 inside the tensor pipe: 8 slots, 5 resident.
+  if (resident <= 0) resident = plan.kblocks <= 8 ? 7 : 5;
   switch (plan.kp) {
     case 16:
-      return launch_pair_rq_kp<16>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+      return launch_pair_rq_res<16>(tmap_q, tmap_g128, plan, cand_val, cand_idx, resident, stream);
     case 32:
-      return launch_pair_rq_kp<32>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+      return launch_pair_rq_res<32>(tmap_q, tmap_g128, plan, cand_val, cand_idx, resident, stream);
     case 64:
-      return launch_pair_rq_kp<64>(tmap_q, tmap_g128, plan, cand_val, cand_idx, stream);
+      return launch_pair_rq_res<64>(tmap_q, tmap_g128, plan, cand_val, cand_idx, resident, stream);
     default:
       return cudaErrorInvalidValue;
   }

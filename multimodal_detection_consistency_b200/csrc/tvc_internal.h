@@ -97,7 +97,7 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
 
 // pair kernel with the first 7 k-blocks of the query tile resident in shared memory for the whole unit
 cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
-                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx,
+                                     const SearchPlan& plan, float* cand_val, int32_t* cand_idx, int resident,
                                      cudaStream_t stream);
 
 // resident-query revision (tvc_gemm_topk_ts.cu): the query tile lives in tensor memory for the whole unit;

@@ -885,7 +885,7 @@ static int search_chunk(CallScope& cs, tvc_gallery* g, const void* queries, bool
   const bool resident_q = plan.pair && g->tmap3_ok && plan.kblocks <= ts_max_kblocks() && unit_tiles >= ctx->ts_min_tiles;
   if (resident_q)
     TVC_CUDA(ctx, launch_gemm_topk_ts(g->tmap3, q_bf, plan, cand_val, cand_idx, st));
-  else if (plan.pair && unit_tiles >= ctx->rq_min_tiles)
+  else if (plan.pair && unit_tiles >= ctx->rq_min_tiles && plan.kblocks <= 32)
     TVC_CUDA(ctx, launch_gemm_topk_pair_rq(tq, g->tmap128, plan, cand_val, cand_idx, static_cast<int>(ctx->rq_resident), st));
   else if (plan.pair)
     TVC_CUDA(ctx, launch_gemm_topk_pair(tq, g->tmap128, plan, cand_val, cand_idx, st));

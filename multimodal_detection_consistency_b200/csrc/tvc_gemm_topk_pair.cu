@@ -230,15 +230,16 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // L2 -> SM traffic and of the shared-memory writes.  Not re-loading it at all is worth +5.9 % under the 1 kW cap
 // (stale-operand probe, debug bit 4, profiles/r2i_probe_a.log); the ring needs only 3 k-blocks of lookahead to
 // cover the L2 latency (4 of the 6 stages: same speed, 3: -11 %, profiles/r2k_ring.log).  So here the first
-// kRqResident = 7 k-blocks of this CTA's 128 query rows (112 KB at d >= 448) stay in shared memory for the whole
-// unit and the ring shrinks to 6 slots of 16 KB that carry the gallery k-blocks and the query k-blocks that did
-// not fit (17 slots per gallery tile at d = 768 = 3.5 k-blocks of lookahead).  Same MMAs on the same operands in
-// the same order as the kernel above: bit-identical results.
-//   thread 0    TMA producer of the ring (gallery k-blocks, streamed query k-blocks), paced
-//   thread 32   MMA issuer (leader): per unit waits a_full; A descriptors point into the resident area or a slot;
-//               after a unit's last MMA a multicast commit on a_empty lets both CTAs replace the resident tile
-//   thread 96   resident-tile loader: waits a_empty (previous unit computed), loads the next unit's k-blocks,
-//               completion on the leader's a_full - on its own thread so that the ring keeps streaming meanwhile
+// here 6 or 7 of the k-blocks of this CTA's 128 query rows (96 / 112 KB), spread evenly over the row, stay in
+// shared memory for the whole unit, and the ring becomes 7 or 6 slots of 16 KB that carry the gallery k-blocks
+// and the query k-blocks that did not fit.  Same MMAs on the same operands in the same order as the kernel
+// above: bit-identical results.
+//   warp 0    TMA producer of the ring (gallery k-blocks, streamed query k-blocks), paced
+//   warp 1    MMA issuer (leader): per unit waits a_full; A descriptors point into the resident area or a slot;
+//             after a unit's last MMA a multicast commit on a_empty lets both CTAs replace the resident tile
+//   warp 3    resident-tile loader: waits a_empty (previous unit computed), loads the next unit's k-blocks,
+//             completion on the leader's a_full - on its own warp so that the ring keeps streaming meanwhile
+// (all three as warp-uniform loops with one elected lane issuing)
 constexpr int kRqUnits = 13;                                 // 16 KB units of shared memory: resident + ring slots
 constexpr int kRqMaxSlots = 8;
 constexpr int kRqSlotBytes = kPABytes;                       // 16 KB: [128 rows x 64] bf16, A or B
@@ -278,6 +279,12 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int num_pairs = gridDim.x >> 1;
   const int total_units = plan_units(p);
   const int n_res = p.kblocks < kRqResident ? p.kblocks : kRqResident;   // resident query k-blocks
+  // WHICH k-blocks stay: spread evenly over the row (bit kb of res_mask), so that the streamed ones - two ring slots
+  // each instead of one - never come back to back and the ring's lookahead stays even (contiguous: 6 resident of 12
+  // was slower than 5, profiles/r2v_probe.log).  Resident k-block kb lives in unit popc(res_mask below bit kb).
+  uint32_t res_mask = 0;
+  for (int kb = 0; kb < p.kblocks; ++kb)
+    if ((kb + 1) * n_res / p.kblocks > kb * n_res / p.kblocks) res_mask |= 1u << kb;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -352,9 +359,8 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
           pacing = __shfl_sync(0xffffffffu, keep, 0) != 0;
         }
         const int g_row = nt * kBN + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < n_res; ++kb) push(&tmap_g, kb * kBK, g_row, kEvictNormal);
-        for (int kb = n_res; kb < p.kblocks; ++kb) {
-          push(&tmap_q, kb * kBK, q_row, kEvictLast);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (!((res_mask >> kb) & 1u)) push(&tmap_q, kb * kBK, q_row, kEvictLast);
           push(&tmap_g, kb * kBK, g_row, kEvictNormal);
         }
       }
@@ -374,9 +380,13 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
       first = false;
       if (elect_one()) {
         if (rank == 0) mbar_arrive_expect_tx(&bars->a_full, static_cast<uint32_t>(2 * n_res * kRqSlotBytes));
-        for (int kb = 0; kb < n_res; ++kb)
-          tma_load_2d_pair_u32(&tmap_q, a_full_leader, res_base + static_cast<uint32_t>(kb * kRqSlotBytes), kb * kBK,
-                               q_row, kEvictNormal);
+        int unit = 0;
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          if ((res_mask >> kb) & 1u) {
+            tma_load_2d_pair_u32(&tmap_q, a_full_leader, res_base + static_cast<uint32_t>(unit * kRqSlotBytes), kb * kBK,
+                                 q_row, kEvictNormal);
+            ++unit;
+          }
       }
       __syncwarp();
     }
@@ -416,22 +426,24 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBN);
-        for (int kb = 0; kb < n_res; ++kb) {          // query k-block resident, gallery k-block from the ring
-          mbar_wait(&bars->full[slot], phase);
-          tc_fence_after();
-          mma4(d_tmem, res_base + static_cast<uint32_t>(kb * kRqSlotBytes),
-               ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), kb == 0, -1, slot);
-          advance();
-        }
-        for (int kb = n_res; kb < p.kblocks; ++kb) {  // both from the ring: query slot, then gallery slot
-          mbar_wait(&bars->full[slot], phase);
-          const int a_slot = slot;
-          advance();
-          mbar_wait(&bars->full[slot], phase);
-          tc_fence_after();
-          mma4(d_tmem, ring_base + static_cast<uint32_t>(a_slot * kRqSlotBytes),
-               ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), false, a_slot, slot);
-          advance();
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          if ((res_mask >> kb) & 1u) {                // query k-block resident, gallery k-block from the ring
+            const int unit = __popc(res_mask & ((1u << kb) - 1u));
+            mbar_wait(&bars->full[slot], phase);
+            tc_fence_after();
+            mma4(d_tmem, res_base + static_cast<uint32_t>(unit * kRqSlotBytes),
+                 ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), kb == 0, -1, slot);
+            advance();
+          } else {                                    // both from the ring: query slot, then gallery slot
+            mbar_wait(&bars->full[slot], phase);
+            const int a_slot = slot;
+            advance();
+            mbar_wait(&bars->full[slot], phase);
+            tc_fence_after();
+            mma4(d_tmem, ring_base + static_cast<uint32_t>(a_slot * kRqSlotBytes),
+                 ring_base + static_cast<uint32_t>(slot * kRqSlotBytes), kb == 0, a_slot, slot);
+            advance();
+          }
         }
         if (elect_one()) umma_commit_pair(&bars->tmem_full[acc], 3);
         __syncwarp();
@@ -540,10 +552,11 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
 cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
                                      const SearchPlan& plan, float* cand_val, int32_t* cand_idx, int resident,
                                      cudaStream_t stream) {
-  // 13 units of 16 KB: `resident` query k-blocks + a ring of the rest.  Up to 8 k-blocks (d <= 512) at most one
-  // is streamed and 6 slots are plenty; beyond, every streamed k-block takes two slots, and the ring must still
-  // hold ~2 k-blocks of prefetch on top of the 2 inside the tensor pipe: 8 slots, 5 resident.
-  if (resident <= 0) resident = plan.kblocks <= 8 ? 7 : 5;
+  // 13 units of 16 KB: `resident` query k-blocks (spread evenly over the row) + a ring of the rest.  Measured
+  // (profiles/r2v_probe.log, bench GEMM, against the plain pair kernel): d = 768: 5 / 6 / 7 resident = +2.9 / +3.9 /
+  // +2.8 %; d = 512: +4.0 / +5.0 / +6.3 %.  A streamed k-block takes two ring slots, and the ring must still hold ~2
+  // k-blocks of prefetch on top of the 2 inside the tensor pipe.
+  if (resident <= 0) resident = plan.kblocks <= 8 ? 7 : 6;
   switch (plan.kp) {
     case 16:
       return launch_pair_rq_res<16>(tmap_q, tmap_g128, plan, cand_val, cand_idx, resident, stream);

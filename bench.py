@@ -743,7 +743,7 @@ def main():
                                  "gallery range once = 7.1e9, the floor of a 256-row-per-pair tiling; the pairs of a wave are "
                                  "paced to stay within 16 gallery tiles of each other (unpaced: 22.9e9 in round 1, 35.0e9 on "
                                  "this tree); 93 GB/s = 1.4% of HBM peak, kernel is tensor bound (DESIGN.md section 3a)",
-                    kernel="gemm_topk_pair_kernel<16> (tcgen05 cta_group::2 GEMM + in-register top-k epilogue)",
+                    kernel="gemm_topk_pair_rq_kernel<16, 6> / gemm_topk_pair_kernel<16> (tcgen05 cta_group::2 GEMM with half of the query tile resident in shared memory + in-register top-k epilogue)",
                     kernel_ms_per_step=k_ms / args.steps, kernel_launches=k_n,
                     kernel_share_of_step=k_ms / total_ms, peak_source=f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                     frac_of_burst_peak=(achieved / peaks["bf16"]) if achieved else None)

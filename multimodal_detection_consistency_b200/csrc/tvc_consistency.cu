@@ -895,10 +895,34 @@ __device__ int select_from_stage(const tvc_detector_params& p, EmbStage* st, int
   return kept;
 }
 
-// producer side: take the first `cap` distinct valid indices of a candidate list, start their copies
+// producer side: take the first `cap` distinct valid indices of a candidate list, start their copies.
+// Which candidates of the first chunk are taken depends on the list alone, so that part (shard lookup, the votes
+// and the 64-bit match) is planned BEFORE the producer waits for its stage - it was 1 of the 1.8 us between
+// "stage free" and "copies issued" in the per-query trace (scripts/trace_emb.py), i.e. of every stage's cycle.
+struct ChunkPlan {
+  long long gi;
+  int part;
+  unsigned keep;   // lanes of the chunk whose candidate is taken (first occurrences of valid indices)
+  bool take;
+};
+__device__ __forceinline__ ChunkPlan plan_first_chunk(const RowSource& src, long long first_chunk, int ncand) {
+  const int lane = threadIdx.x & 31;
+  ChunkPlan pl;
+  pl.gi = lane < ncand ? first_chunk : -1;
+  pl.part = lane < ncand ? find_part(src, pl.gi) : -1;
+  pl.take = pl.part >= 0;
+  const unsigned vmask = __ballot_sync(kFull, pl.take);
+  if (pl.take) {
+    const unsigned same = __match_any_sync(vmask, static_cast<unsigned long long>(pl.gi));
+    pl.take = (__ffs(same) - 1) == lane;   // first occurrence inside this chunk
+  }
+  pl.keep = __ballot_sync(kFull, pl.take);
+  return pl;
+}
+
 __device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const RowSource& src,
                                                    const long long* cand, int ncand, int cap, float* rows_grp,
-                                                   int d, uint64_t* bar, long long first_chunk) {
+                                                   int d, uint64_t* bar, const ChunkPlan& first) {
   const int lane = threadIdx.x & 31;
   const uint32_t row_bytes = static_cast<uint32_t>(d) * 4u;
   int n = 0, end = 0;
@@ -906,19 +930,28 @@ __device__ __forceinline__ uint32_t prefetch_group(EmbStage* st, int grp, const 
     const int c = c0 + lane;
     long long gi = -1;
     int part = -1;
-    if (c < ncand) {
-      gi = c0 == 0 ? first_chunk : cand[c];   // the first 32 candidates were loaded a query ahead
-      part = find_part(src, gi);
+    bool take;
+    unsigned keep;
+    if (c0 == 0) {
+      gi = first.gi;
+      part = first.part;
+      take = first.take;
+      keep = first.keep;
+    } else {
+      if (c < ncand) {
+        gi = cand[c];
+        part = find_part(src, gi);
+      }
+      take = part >= 0;
+      if (take)
+        for (int j = 0; j < n; ++j) take &= (st->pf_idx[grp][j] != gi);
+      const unsigned vmask = __ballot_sync(kFull, take);
+      if (take) {
+        const unsigned same = __match_any_sync(vmask, static_cast<unsigned long long>(gi));
+        take = (__ffs(same) - 1) == lane;   // first occurrence inside this chunk
+      }
+      keep = __ballot_sync(kFull, take);
     }
-    bool take = part >= 0;
-    if (take)
-      for (int j = 0; j < n; ++j) take &= (st->pf_idx[grp][j] != gi);
-    const unsigned vmask = __ballot_sync(kFull, take);
-    if (take) {
-      const unsigned same = __match_any_sync(vmask, static_cast<unsigned long long>(gi));
-      take = (__ffs(same) - 1) == lane;   // first occurrence inside this chunk
-    }
-    const unsigned keep = __ballot_sync(kFull, take);
     const int slot = n + __popc(keep & ((1u << lane) - 1u));
     if (take && slot < cap) {
       st->pf_idx[grp][slot] = gi;
@@ -1034,6 +1067,9 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
     for (long long i = s; i < my_n; i += n_stages, ++round) {
       const long long cur_ret = pre_ret, cur_gen = pre_gen;
       if (i + n_stages < my_n) preload(blockIdx.x + (i + n_stages) * static_cast<long long>(gridDim.x));
+      ChunkPlan plan_ret{}, plan_gen{};
+      if (has_ret) plan_ret = plan_first_chunk(a.ret, cur_ret, a.n_ret_cand);
+      if (gen_idx) plan_gen = plan_first_chunk(a.genr, cur_gen, a.n_gen_cand);
       if (round > 0) mbar_wait_parked(&s_empty[s], (round - 1) & 1u);
       const long long q = blockIdx.x + i * static_cast<long long>(gridDim.x);
       EmbStage* st = &s_stage[s];
@@ -1052,10 +1088,10 @@ consistency_emb_pipe_kernel(const tvc_detector_params p, long long nq, int d, co
       uint32_t bytes = static_cast<uint32_t>(ndirect) * row_bytes;
       if (has_ret)
         bytes += prefetch_group(st, 0, a.ret, reinterpret_cast<const long long*>(a.ret_idx) + q * a.n_ret_cand,
-                                a.n_ret_cand, R, rows + static_cast<size_t>(row_ret) * d, d, bar, cur_ret);
+                                a.n_ret_cand, R, rows + static_cast<size_t>(row_ret) * d, d, bar, plan_ret);
       if (gen_idx)
         bytes += prefetch_group(st, 1, a.genr, reinterpret_cast<const long long*>(a.gen_idx) + q * a.n_gen_cand,
-                                a.n_gen_cand, G, rows + static_cast<size_t>(row_gen) * d, d, bar, cur_gen);
+                                a.n_gen_cand, G, rows + static_cast<size_t>(row_gen) * d, d, bar, plan_gen);
       if (lane == 0) {
         st->q = q;
         if (!has_ret) { st->pf_n[0] = 0; st->pf_end[0] = 0; }

@@ -143,7 +143,12 @@ int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
  * "pace_every" / "pace_ahead" = the CTA pairs of a wave of the pair kernel stay within pace_ahead blocks
  * of pace_every gallery tiles of each other, so that a gallery tile is read from HBM once per wave
  * (defaults 8 / 2; pace_every = 0 switches pacing off; also TVC_PACE_EVERY / TVC_PACE_AHEAD in the
- * environment at context creation).  Results do not depend on any of them. */
+ * environment at context creation);
+ * "rq_min_tiles" = units of at least this many 256-row gallery tiles run on the pair kernel that keeps half of
+ * the query tile resident in shared memory (default 64; INT64_MAX = never; TVC_RQ_MIN_TILES), "rq_resident" =
+ * resident k-blocks 5..7 (0 = by dimension); "ts_min_tiles" = the same for the revision that keeps the query
+ * tile in tensor memory (measured slower: default never; TVC_TS_MIN_TILES); "debug_flags" = profiling only.
+ * Results do not depend on any of them (every kernel revision is bit-identical to the others). */
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value);
 /* Frees the context's grow-only per-stream device workspaces (query operands, candidate lists, host
  * staging windows) after synchronising the device; they are re-grown on demand.  For callers that

@@ -505,7 +505,13 @@ class TVCScorer:
         is not hidden behind a search.  One piece (= no pipelining) when a piece would fall under
         `min_chunk_queries`."""
         hc = self.host_chunks if pinned else self.host_chunks_pageable
-        for cand in (hc, 2):                                # too small for the configured split: try two halves
+        cands = [hc, 2]
+        if self.world > 1 and pinned and q_total // 4 >= self.min_chunk_queries // 2:
+            # a rank's slice on several GPUs: a piece of every rank together is one sharded search, so the first piece
+            # may be smaller per rank than on one GPU (512 queries x 8 ranks x 5 variants = 80 query tiles, a full
+            # wave); a quarter in front leaves a quarter of the upload exposed instead of the half two halves do
+            cands.insert(1, (1, 3))
+        for cand in cands:                                  # too small for the configured split: try the next
             weights = [1.0] * int(cand) if isinstance(cand, int) else [float(w) for w in cand]
             if len(weights) < 2 or min(weights) <= 0:
                 break
@@ -515,7 +521,8 @@ class TVCScorer:
                 cuts.append(int(round(q_total * acc / total)))
             cuts[-1] = q_total
             bounds = list(zip(cuts[:-1], cuts[1:]))
-            if min(b - a for a, b in bounds) >= self.min_chunk_queries:
+            floor = self.min_chunk_queries // 2 if (cand == (1, 3) and self.world > 1) else self.min_chunk_queries
+            if min(b - a for a, b in bounds) >= floor:
                 return bounds
         return [(0, q_total)]
 

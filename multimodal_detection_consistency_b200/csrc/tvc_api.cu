@@ -466,7 +466,7 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
     return TVC_OK;
   }
   if (strcmp(name, "rq_resident") == 0) {
-    ctx->rq_resident = (value >= 5 && value <= 7) ? value : 0;
+    ctx->rq_resident = (value >= 7 && value <= 9) ? value : 0;
     return TVC_OK;
   }
   if (strcmp(name, "rq_min_tiles") == 0) {

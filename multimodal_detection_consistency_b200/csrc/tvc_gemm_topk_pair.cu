@@ -230,9 +230,9 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 // L2 -> SM traffic and of the shared-memory writes.  Not re-loading it at all is worth +5.9 % under the 1 kW cap
 // (stale-operand probe, debug bit 4, profiles/r2i_probe_a.log); the ring needs only 3 k-blocks of lookahead to
 // cover the L2 latency (4 of the 6 stages: same speed, 3: -11 %, profiles/r2k_ring.log).  So here the first
-// here 6 or 7 of the k-blocks of this CTA's 128 query rows (96 / 112 KB), spread evenly over the row, stay in
-// shared memory for the whole unit, and the ring becomes 7 or 6 slots of 16 KB that carry the gallery k-blocks
-// and the query k-blocks that did not fit.  Same MMAs on the same operands in the same order as the kernel
+// here 8 of the k-blocks of this CTA's 128 query rows (128 KB), spread evenly over the row, stay in shared
+// memory for the whole unit, and the ring becomes 6 slots of 16 KB that carry the gallery k-blocks and the query
+// k-blocks that did not fit (the epilogue's slow path stages in thread-local memory to make room).  Same MMAs on the same operands in the same order as the kernel
 // above: bit-identical results.
 //   warp 0    TMA producer of the ring (gallery k-blocks, streamed query k-blocks), paced
 //   warp 1    MMA issuer (leader): per unit waits a_full; A descriptors point into the resident area or a slot;
@@ -240,11 +240,12 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
 //   warp 3    resident-tile loader: waits a_empty (previous unit computed), loads the next unit's k-blocks,
 //             completion on the leader's a_full - on its own warp so that the ring keeps streaming meanwhile
 // (all three as warp-uniform loops with one elected lane issuing)
-constexpr int kRqUnits = 13;                                 // 16 KB units of shared memory: resident + ring slots
+constexpr int kRqUnits = 14;                                 // 16 KB units of shared memory: resident + ring slots
+                                                             // (the epilogue's slow path stages in local memory)
 constexpr int kRqMaxSlots = 8;
 constexpr int kRqSlotBytes = kPABytes;                       // 16 KB: [128 rows x 64] bf16, A or B
 constexpr int kRqSmemRing = kRqUnits * kRqSlotBytes;         // end of the operand area (208 KB)
-constexpr int kRqSmemBar = kRqSmemRing + kStageFloats * 4;
+constexpr int kRqSmemBar = kRqSmemRing;
 constexpr int kRqSmemTotal = kRqSmemBar + 256 + 1024;
 static_assert(kPABytes == kPBBytes, "one slot size for both operands");
 
@@ -268,8 +269,7 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   constexpr int kRqSlots = kRqUnits - kRqResident;
   constexpr int kRqSmemRes = kRqResident * kRqSlotBytes;
-  static_assert(kRqSlots <= kRqMaxSlots && kRqSlots >= 4, "ring size");
-  float* sStage = reinterpret_cast<float*>(smem + kRqSmemRing);
+  static_assert(kRqSlots <= kRqMaxSlots && kRqSlots >= 4, "ring size");   // resident 6 / 7 / 8 -> 8 / 7 / 6 slots
   RqBarriers* bars = reinterpret_cast<RqBarriers*>(smem + kRqSmemBar);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -457,7 +457,6 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ top-k epilogue (both CTAs)
     const int q4 = warp & 3;
     const int row_in_tile = q4 * 32 + lane;
-    float* my_stage = sStage + row_in_tile;
     TopList<KP> top;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -473,7 +472,8 @@ gemm_topk_pair_rq_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         const uint32_t t_addr =
             tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-        if (!(p.debug & 1)) topk_consume_tile<KP>(top, thr, t_addr, my_stage, nt * kBN, p.n_rows, self_col, p.debug);
+        if (!(p.debug & 1))
+          topk_consume_tile<KP, kBN, true>(top, thr, t_addr, nullptr, nt * kBN, p.n_rows, self_col, p.debug);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
@@ -510,12 +510,12 @@ template <int KP>
 cudaError_t launch_pair_rq_res(const CUtensorMap& tq, const CUtensorMap& tg, const SearchPlan& plan, float* cv,
                                int32_t* ci, int resident, cudaStream_t stream) {
   switch (resident) {
+    case 9:
+      return launch_pair_rq_kp<KP, 9>(tq, tg, plan, cv, ci, stream);
+    case 8:
+      return launch_pair_rq_kp<KP, 8>(tq, tg, plan, cv, ci, stream);
     case 7:
       return launch_pair_rq_kp<KP, 7>(tq, tg, plan, cv, ci, stream);
-    case 6:
-      return launch_pair_rq_kp<KP, 6>(tq, tg, plan, cv, ci, stream);
-    case 5:
-      return launch_pair_rq_kp<KP, 5>(tq, tg, plan, cv, ci, stream);
     default:
       return cudaErrorInvalidValue;
   }
@@ -552,11 +552,12 @@ cudaError_t launch_gemm_topk_pair(const CUtensorMap& tmap_q, const CUtensorMap& 
 cudaError_t launch_gemm_topk_pair_rq(const CUtensorMap& tmap_q, const CUtensorMap& tmap_g128,
                                      const SearchPlan& plan, float* cand_val, int32_t* cand_idx, int resident,
                                      cudaStream_t stream) {
-  // 13 units of 16 KB: `resident` query k-blocks (spread evenly over the row) + a ring of the rest.  Measured
-  // (profiles/r2v_probe.log, bench GEMM, against the plain pair kernel): d = 768: 5 / 6 / 7 resident = +2.9 / +3.9 /
-  // +2.8 %; d = 512: +4.0 / +5.0 / +6.3 %.  A streamed k-block takes two ring slots, and the ring must still hold ~2
-  // k-blocks of prefetch on top of the 2 inside the tensor pipe.
-  if (resident <= 0) resident = plan.kblocks <= 8 ? 7 : 6;
+  // 14 units of 16 KB (the epilogue's slow path stages in thread-local memory, so no shared-memory staging
+  // buffer): `resident` query k-blocks (spread evenly over the row) + a ring of the rest.  Measured on the bench
+  // GEMM against the plain pair kernel (profiles/r3c_probe.log, r3d_probe.log): d = 768: 6 / 7 / 8 / 9 resident =
+  // +3.1 / +3.3 / +4.0 / +3.0 %; d = 512: +4.5 / +5.5 / +6.7 %.  A streamed k-block takes two ring slots, and the ring
+  // must still hold ~2 k-blocks of prefetch on top of the 2 inside the tensor pipe: 6 slots are the least that do.
+  if (resident <= 0) resident = 8;   // (ring: 14 - resident slots)
   switch (plan.kp) {
     case 16:
       return launch_pair_rq_res<16>(tmap_q, tmap_g128, plan, cand_val, cand_idx, resident, stream);

@@ -53,7 +53,9 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
 // One 128 x 256 accumulator buffer: read this thread's lane 32 columns at a time; a chunk whose
 // maximum does not beat the current KP-th best costs one tcgen05.ld + a max tree; otherwise the chunk
 // is staged through shared memory (keeps `top` in registers) and walked with bubble inserts.
-template <int KP, int NCOLS = kBN>
+// LOCAL_STAGE: the slow path keeps the chunk in thread-local memory (a 128-byte stack array per thread, L1
+// resident) instead of the 16 KB shared-memory staging buffer - for kernels that need that shared memory.
+template <int KP, int NCOLS = kBN, bool LOCAL_STAGE = false>
 __device__ __forceinline__ void topk_consume_tile(TopList<KP>& top, float& thr, uint32_t t_addr, float* my_stage,
                                                   int col_base, int n_rows, long long self_col,
                                                   int debug = 0) {
@@ -63,19 +65,23 @@ __device__ __forceinline__ void topk_consume_tile(TopList<KP>& top, float& thr, 
     tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
     tmem_ld_wait();
     if (max32(r) > thr && !(debug & 2)) {
-      // hit mask from the registers (static indices), values through smem for the dynamic walk;
+      // hit mask from the registers (static indices), values through smem / local memory for the dynamic walk;
       // ascending bit order = ascending column, which the tie rule needs
       uint32_t hits = 0;
+      float local_stage[LOCAL_STAGE ? 32 : 1];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        my_stage[j * kBM] = __uint_as_float(r[j]);
+        if (LOCAL_STAGE)
+          local_stage[LOCAL_STAGE ? j : 0] = __uint_as_float(r[j]);
+        else
+          my_stage[j * kBM] = __uint_as_float(r[j]);
         hits |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
       }
       const int col0 = col_base + c * 32;
       while (hits) {
         const int j = __ffs(hits) - 1;
         hits &= hits - 1;
-        const float x = my_stage[j * kBM];
+        const float x = LOCAL_STAGE ? local_stage[LOCAL_STAGE ? j : 0] : my_stage[j * kBM];
         const int col = col0 + j;
         if (x > thr && col < n_rows && col != self_col) {
           top.insert(x, col);

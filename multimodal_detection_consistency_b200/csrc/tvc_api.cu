@@ -6,6 +6,7 @@
 
 #include <map>
 #include <memory>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <string>
@@ -205,15 +206,31 @@ int get_ws(CallScope& cs, size_t bytes, uint8_t** out) {
   cudaStream_t st = cs.st;
   tvc_ctx::Ws& w = *cs.ws;
   if (w.bytes < bytes) {
+    static const bool trace = getenv("TVC_TRACE_WS") != nullptr;   // diagnostics: what a workspace growth costs
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t w_prev_bytes = w.bytes;
     if (w.ptr) {
       TVC_CUDA(ctx, cudaStreamSynchronize(st));
       TVC_CUDA(ctx, cudaFree(w.ptr));
       w.ptr = nullptr;
       w.bytes = 0;
     }
-    const size_t want = bytes + (bytes >> 3);
+    const auto t1 = std::chrono::steady_clock::now();
+    // Growing is expensive far beyond the allocation itself: cudaFree of the old block was measured at 0.7 s on a
+    // B200 with a few GB mapped (it synchronises the device and unmaps), cudaMalloc at 30-70 ms (TVC_TRACE_WS=1
+    // prints both).  So a workspace starts at 64 MB - every single-sample and few-thousand-row call of the drop-in
+    // API fits without ever growing - and doubles from there.
+    size_t want = bytes + (bytes >> 3);
+    if (want < (64u << 20)) want = 64u << 20;
+    if (want < 2 * w_prev_bytes) want = 2 * w_prev_bytes;
     TVC_CUDA(ctx, cudaMalloc(&w.ptr, want));
     w.bytes = want;
+    if (trace) {
+      const auto t2 = std::chrono::steady_clock::now();
+      fprintf(stderr, "tvc: workspace of stream %p grows to %zu bytes: free %.3f ms, malloc %.3f ms\n", (void*)st, want,
+              std::chrono::duration<double, std::milli>(t1 - t0).count(),
+              std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
   }
   *out = static_cast<uint8_t*>(w.ptr);
   return TVC_OK;

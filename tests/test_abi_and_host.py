@@ -128,7 +128,7 @@ def test_host_batch_piece_bounds():
     then to one piece when a piece would be smaller than min_chunk_queries."""
     import types
     from multimodal_detection_consistency_b200.pipeline import TVCScorer
-    sc = types.SimpleNamespace(host_chunks=(1, 6, 1), min_chunk_queries=1024)
+    sc = types.SimpleNamespace(host_chunks=(1, 6, 1), host_chunks_pageable=2, min_chunk_queries=1024, world=1)
     pb = lambda q: TVCScorer._piece_bounds(sc, q)  # noqa: E731
     assert pb(16384) == [(0, 2048), (2048, 14336), (14336, 16384)]
     assert pb(8192) == [(0, 1024), (1024, 7168), (7168, 8192)]
@@ -139,3 +139,8 @@ def test_host_batch_piece_bounds():
     assert pb(10001)[0][0] == 0 and pb(10001)[-1][1] == 10001 and all(a[1] == b[0] for a, b in zip(pb(10001), pb(10001)[1:]))
     sc.host_chunks = 1
     assert pb(16384) == [(0, 16384)]
+    # a rank's slice on several GPUs: a quarter-size first piece where the (1, 6, 1) split would fall under a wave
+    sc.host_chunks, sc.world = (1, 6, 1), 8
+    assert pb(2048) == [(0, 512), (512, 2048)]
+    assert pb(1024) == [(0, 1024)]
+    assert TVCScorer._piece_bounds(sc, 4096, pinned=False) == [(0, 2048), (2048, 4096)]

@@ -359,7 +359,8 @@ def roofline_bc(torch, tvc, args, scorer, out, img, txt, var, peaks):
     skew = (n_big * torch.rand(m_big, 10, device=dev) ** 3).long().clamp_(0, n_big - 1)
     cnt = torch.zeros(n_big, dtype=torch.int32, device=dev)
     us = _event_us(torch, lambda: ctx.k_occurrence(skew, n_big, 0, cnt), reps=10)
-    c_big = entry(us, 8 * m_big * 10 + 4 * n_big, entries=m_big * 10, bins=n_big, note="power-law skewed stream idx = N*u^3")
+    c_big = entry(us, 8 * m_big * 10 + 4 * n_big, entries=m_big * 10, bins=n_big, note="power-law skewed stream idx = N*u^3",
+                  kernel="k_occurrence_partition_tma_kernel + k_occurrence_bucket_kernel (bucketed two-pass path)")
     del skew, cnt
     return dict(emb=b_emb, sims=b_sims), dict(step=c_step, stream=c_big)
 

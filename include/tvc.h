@@ -147,7 +147,11 @@ int64_t tvc_ctx_launch_count(tvc_ctx* ctx);
  * "rq_min_tiles" = units of at least this many 256-row gallery tiles run on the pair kernel that keeps half of
  * the query tile resident in shared memory (default 64; INT64_MAX = never; TVC_RQ_MIN_TILES), "rq_resident" =
  * resident k-blocks 5..7 (0 = by dimension); "ts_min_tiles" = the same for the revision that keeps the query
- * tile in tensor memory (measured slower: default never; TVC_TS_MIN_TILES); "debug_flags" = profiling only.
+ * tile in tensor memory (measured slower: default never; TVC_TS_MIN_TILES); "debug_flags" = profiling only;
+ * "kocc_part_min" = tvc_k_occurrence takes its bucketed two-pass path (bucket-sort into 16-bit keys, count with
+ * shared-memory atomics) for index streams of at least this many entries (default 1 Mi; 0 = whenever the path
+ * applies: 16-byte aligned stream, histogram beyond shared memory and up to 4 161 536 bins; INT64_MAX = never;
+ * TVC_KOCC_PART_MIN).  It borrows 2 bytes per entry of the stream's workspace.
  * Results do not depend on any of them (every kernel revision is bit-identical to the others). */
 int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value);
 /* Frees the context's grow-only per-stream device workspaces (query operands, candidate lists, host

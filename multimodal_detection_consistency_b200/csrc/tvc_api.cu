@@ -56,6 +56,9 @@ struct tvc_ctx {
   int64_t rq_resident = 0;    // resident query k-blocks (5..7); 0 = by dimension (TVC_RQ_RESIDENT, measurements)
   int64_t pace_every = 8;     // measured on the bench workload (profiles/r2h_pace.log): 2..8 tiles x 1..4 blocks
   int64_t pace_ahead = 2;     // all give 98.7-99.2 ms per step against 102.0-102.6 unpaced; 16 x 3: 101.4-101.8
+  // kernel (c): index streams of at least this many entries (over histograms beyond shared memory, up to 4 Mi bins)
+  // take the bucketed two-pass path; 0 = whenever it applies, INT64_MAX = never (TVC_KOCC_PART_MIN / option)
+  int64_t kocc_part_min = 1ll << 20;   // measured on a B200: 1 M entries 37 vs 45 us, 5 M 50 vs 84, 50 M 222 vs 456
   int64_t emb_trace_ptr = 0;     // debugging: device buffer for kernel (b) pipeline timestamps
   int64_t emb_generic = 0;       // 1: kernel (b) embedding mode always takes the one-warp-per-query kernel
   bool timing = false;
@@ -431,6 +434,7 @@ int tvc_ctx_create(int device, tvc_ctx** out) {
   if (const char* e = getenv("TVC_TS_MIN_TILES")) ctx->ts_min_tiles = atoll(e);
   if (const char* e = getenv("TVC_RQ_MIN_TILES")) ctx->rq_min_tiles = atoll(e);
   if (const char* e = getenv("TVC_RQ_RESIDENT")) ctx->rq_resident = atoll(e);
+  if (const char* e = getenv("TVC_KOCC_PART_MIN")) ctx->kocc_part_min = atoll(e);
   if (const char* e = getenv("TVC_PACE_EVERY")) ctx->pace_every = atoll(e);
   if (const char* e = getenv("TVC_PACE_AHEAD")) ctx->pace_ahead = atoll(e);
   *out = ctx;
@@ -492,6 +496,10 @@ int tvc_ctx_set_option(tvc_ctx* ctx, const char* name, int64_t value) {
   }
   if (strcmp(name, "ts_min_tiles") == 0) {
     ctx->ts_min_tiles = value;
+    return TVC_OK;
+  }
+  if (strcmp(name, "kocc_part_min") == 0) {
+    ctx->kocc_part_min = value < 0 ? 0 : value;
     return TVC_OK;
   }
   if (strcmp(name, "pace_every") == 0) {
@@ -1491,13 +1499,23 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
   if (cs.rc != TVC_OK) return cs.rc;
   cudaStream_t st = cs.st;
   const size_t ib = up256(static_cast<size_t>(m) * k * 8), cb = up256(static_cast<size_t>(n_bins) * 4);
+  // long streams over histograms beyond shared memory take the bucketed two-pass path (option "kocc_part_min");
+  // a host stream is staged 256-byte aligned, so only a device stream can be misaligned for it
+  int64_t part_min;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    part_min = ctx->kocc_part_min;
+  }
+  const size_t pb = k_occurrence_part_scratch_bytes(idx_dev ? idx : nullptr, m, k, n_bins, part_min);
   uint8_t* ws = nullptr;
   {
-    int rc = get_ws(cs, 4096 + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
+    int rc = get_ws(cs, 4096 + pb + ((!idx_dev || !cnt_dev) ? ib + cb : 0), &ws);
     if (rc != TVC_OK) return rc;
   }
   int* flag_scratch = reinterpret_cast<int*>(ws);
   ws += 4096;
+  void* part_scratch = pb ? ws : nullptr;
+  ws += pb;
   const int64_t* d_idx = idx;
   if (!idx_dev) {
     TVC_CUDA(ctx, cudaMemcpyAsync(ws, idx, static_cast<size_t>(m) * k * 8, cudaMemcpyHostToDevice, st));
@@ -1510,7 +1528,7 @@ int tvc_k_occurrence(tvc_ctx* ctx, const int64_t* idx, int64_t m, int32_t k, int
       TVC_CUDA(ctx, cudaMemcpyAsync(d_cnt, counts, static_cast<size_t>(n_bins) * 4, cudaMemcpyHostToDevice, st));
   }
   if (zero_first) TVC_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, static_cast<size_t>(n_bins) * 4, st));
-  TVC_CUDA(ctx, launch_k_occurrence(d_idx, m, k, idx_base, n_bins, d_cnt, ctx->sm_count, flag_scratch, st));
+  TVC_CUDA(ctx, launch_k_occurrence(d_idx, m, k, idx_base, n_bins, d_cnt, ctx->sm_count, flag_scratch, part_scratch, st));
   if (!cnt_dev)
     TVC_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, static_cast<size_t>(n_bins) * 4, cudaMemcpyDeviceToHost, st));
   if (!idx_dev || !cnt_dev) TVC_CUDA(ctx, cudaStreamSynchronize(st));

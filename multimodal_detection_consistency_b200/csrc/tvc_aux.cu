@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "tvc_internal.h"
+#include "tvc_ptx.cuh"
 
 namespace tvc {
 
@@ -838,6 +839,402 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
   }
 }
 
+// ---- bucketed path: streams of millions of entries over histograms far beyond shared memory ----------------
+// Every entry of the RED path costs one atomic in the L2 (~180 G/s chip-wide, a fifth of what HBM delivers as
+// index stream).  The only way past that is to make the increments shared-memory ones, i.e. to bring the entries
+// of one bin range together first:
+//   pass 1 (k_occurrence_partition_kernel): a CTA reads a TILE of 8192 entries and writes it back bucket-sorted
+//     (bucket = bin >> 15) as 16-bit keys (bin & 32767) - tile-major, so the write is one contiguous 16 KB block
+//     and no bucket can overflow whatever the distribution - plus the tile's bucket boundaries (transposed,
+//     offs[bucket][tile]) and the bucket totals.  The rank of an entry inside its (thread, bucket) cell comes from
+//     THREAD-PRIVATE 16-bit counters (s_cell[bucket][thread]: plain conflict-free LDS + STS, 1/32 cycle per lane
+//     where a shared-memory atomic with return costs ~2), the cell bases from one in-place scan per bucket.
+//   pass 2 (k_occurrence_bucket_kernel): CTAs are dealt to the buckets in proportion to their totals (every CTA
+//     derives the same deal from the totals; hub-heavy buckets get many), a CTA counts its share of a bucket's
+//     segments - one segment per tile, the warps taking tiles in turn - in a 128 KB shared-memory histogram and
+//     flushes the non-zero counters with REDs to consecutive addresses.
+// HBM traffic: 8 B/entry read + 2 B written + 2 B read (+ 4 B/bin) against 8 B/entry of the single pass.
+// Measured on a B200 (profiles/r4i_probe.log, r4j_probe.log; 1 M bins, stream idx = N u^3): 50 M entries 222 us
+// against 456 us (0.28 against 0.14 of the HBM peak; uniform stream 200 against 336), 5 M entries 50 against 84,
+// 1 M entries 37 against 45.  Pass 1 is bound by the load/store pipe (ncu: 72 % busy, 3 900 shared-memory
+// wavefronts per tile of which ~1 000 are bank conflicts of the 16-bit scatter), pass 2 by the shared-memory atomics.
+constexpr int kPartThreads = 512;
+constexpr int kPartPer = 16;                               // entries per thread and tile
+constexpr int kPartTile = kPartThreads * kPartPer;         // 8192
+constexpr int kPartShift = 15;
+constexpr int kPartWidth = 1 << kPartShift;                // bins per bucket: 128 KB of counters
+constexpr int kPartMaxBuckets = 127;                       // histograms up to 4 161 536 bins (bucket 127 = no bin)
+constexpr int kPartTotalStride = 16;                       // one 64-bit bucket total per 128-byte line
+constexpr int kCountThreads = 1024;
+
+// global -> shared bulk copy (TMA, no tensor map), completion bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s_aux(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += y;
+  }
+  return v;
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kPartThreads, MIN_BLOCKS)
+k_occurrence_partition_kernel(const long long* __restrict__ idx, long long total, long long idx_base,
+                              long long n_bins, int n_buckets, long long n_tiles,
+                              unsigned short* __restrict__ keys, unsigned short* __restrict__ offs,
+                              unsigned long long* __restrict__ totals, long long tile0) {
+  // s_cell[bucket][thread]: first the number of entries thread `thread` holds for `bucket`, then (in place) the
+  // position of its first one inside the bucket.  16-bit cells: lanes 2i and 2i+1 share a bank (a 2-way conflict
+  // when they address different buckets) but the address is one multiply-add - the kernel is bound by its
+  // instruction count (ncu on the first version: 75 instructions per entry, issue slots 62 % busy, HBM 37 %), not
+  // by shared memory.  Bucket n_buckets is the bin-less one (unused slots, rows of other shards, the ragged end of
+  // the stream): every entry takes the same straight-line path and the bin-less ones land behind the tile's keys.
+  extern __shared__ __align__(16) unsigned char part_smem[];
+  unsigned short* s_cell = reinterpret_cast<unsigned short*>(part_smem);
+  unsigned short* s_sorted = s_cell + static_cast<size_t>(n_buckets + 1) * kPartThreads;
+  __shared__ int s_tot[kPartMaxBuckets + 1];
+  __shared__ int s_base[kPartMaxBuckets + 2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // cell of thread (warp w, lane l): 16-bit half (w & 1) of word (w >> 1) * 32 + l - the lanes of a warp sit in 32
+  // different banks whatever buckets they address
+  const int cell = ((warp >> 1) << 6) | (lane << 1) | (warp & 1);
+  const long long tile = tile0 + blockIdx.x;
+  const long long e0 = tile * kPartTile;
+  const longlong2* idx2 = reinterpret_cast<const longlong2*>(idx);
+  const bool full = e0 + kPartTile <= total;
+  const unsigned nb = static_cast<unsigned>(n_bins);                       // <= 127 * 32768 on this path
+  const unsigned binless = static_cast<unsigned>(n_buckets) << kPartShift;
+
+  auto load_half = [&](int half, long long (&v)[kPartPer / 2]) {
+#pragma unroll
+    for (int j = 0; j < kPartPer / 4; ++j) {
+      const long long e = e0 + static_cast<long long>((half * (kPartPer / 4) + j) * kPartThreads + tid) * 2;
+      long long a = idx_base - 1, c = idx_base - 1;          // outside the histogram
+      if (full || e + 1 < total) {
+        const longlong2 t = __ldcs(idx2 + (e >> 1));
+        a = t.x;
+        c = t.y;
+      } else if (e < total) {
+        a = idx[e];
+      }
+      v[2 * j] = a;
+      v[2 * j + 1] = c;
+    }
+  };
+  unsigned ent[kPartPer];          // bin (22 bits: bucket << 15 | key) | rank inside the (thread, bucket) cell << 22
+  auto count_half = [&](int half, const long long (&v)[kPartPer / 2]) {
+#pragma unroll
+    for (int j = 0; j < kPartPer / 2; ++j) {
+      const long long b = v[j] - idx_base;
+      const unsigned lo = static_cast<unsigned>(b), hi = static_cast<unsigned>(static_cast<unsigned long long>(b) >> 32);
+      const unsigned sel = (hi == 0u && lo < nb) ? lo : binless;
+      unsigned short* c = s_cell + (sel >> kPartShift) * kPartThreads + cell;
+      const unsigned old = *c;
+      *c = static_cast<unsigned short>(old + 1u);
+      ent[half * (kPartPer / 2) + j] = sel | (old << 22);
+    }
+  };
+  long long v[kPartPer / 2];
+  load_half(0, v);
+  {
+    uint4* z = reinterpret_cast<uint4*>(part_smem);
+    const int n16 = (n_buckets + 1) * kPartThreads * 2 / 16;
+    for (int i = tid; i < n16; i += kPartThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  count_half(0, v);
+  load_half(1, v);
+  count_half(1, v);
+  __syncthreads();
+  // cell bases, in place: a warp takes a bucket; the order of the cells in memory is the order of the threads inside
+  // the bucket (any fixed order does)
+  for (int b = warp; b <= n_buckets; b += kPartThreads / 32) {
+    unsigned* c = reinterpret_cast<unsigned*>(s_cell + b * kPartThreads);
+    unsigned w[kPartThreads / 64];
+    unsigned run = 0;
+#pragma unroll
+    for (int j = 0; j < kPartThreads / 64; ++j) w[j] = c[j * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < kPartThreads / 64; ++j) {
+      const unsigned lo = w[j] & 0xffffu, hi = w[j] >> 16;
+      w[j] = run | ((run + lo) << 16);
+      run += lo + hi;
+    }
+    const unsigned incl = warp_inclusive_scan(run, lane);
+    const unsigned base2 = (incl - run) * 0x10001u;          // a tile holds 8192 entries: the halves never carry
+#pragma unroll
+    for (int j = 0; j < kPartThreads / 64; ++j) c[j * 32 + lane] = w[j] + base2;
+    if (lane == 31) s_tot[b] = static_cast<int>(incl);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned t[4], run = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = lane * 4 + i;
+      t[i] = b <= n_buckets ? static_cast<unsigned>(s_tot[b]) : 0u;
+      run += t[i];
+    }
+    const unsigned incl = warp_inclusive_scan(run, lane);
+    unsigned base = incl - run;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = lane * 4 + i;
+      if (b <= n_buckets) s_base[b] = static_cast<int>(base);
+      base += t[i];
+    }
+  }
+  __syncthreads();
+  // bucket boundaries of the tile (s_base[n_buckets] = where the bin-less entries start = the number of keys)
+  if (tid <= n_buckets) offs[static_cast<long long>(tid) * n_tiles + tile] = static_cast<unsigned short>(s_base[tid]);
+  if (tid < n_buckets && s_tot[tid] > 0)
+    atomicAdd(totals + tid * kPartTotalStride, static_cast<unsigned long long>(s_tot[tid]));
+#pragma unroll
+  for (int j = 0; j < kPartPer; ++j) {
+    const unsigned w = ent[j];
+    const unsigned bucket = (w >> kPartShift) & 127u;
+    const unsigned pos = static_cast<unsigned>(s_base[bucket]) + s_cell[bucket * kPartThreads + cell] + (w >> 22);
+    s_sorted[pos] = static_cast<unsigned short>(w & (kPartWidth - 1));
+  }
+  __syncthreads();
+  const int n16 = (s_base[n_buckets] * 2 + 15) >> 4;
+  uint4* dst = reinterpret_cast<uint4*>(keys + tile * kPartTile);
+  const uint4* src = reinterpret_cast<const uint4*>(s_sorted);
+  for (int i = tid; i < n16; i += kPartThreads) __stcs(dst + i, src[i]);
+}
+
+// The same pass as a persistent kernel fed by the copy engine (histograms up to 31 buckets = 1 015 808 bins, two
+// CTAs per SM): ncu on the kernel above shows neither pipe saturated (LSU ~56 %, issue ~55 %) - the CTAs spend
+// ~40 % of their time waiting for their own index loads, and three 512-thread CTAs per SM do not overlap that away.
+// Here one thread hands the next tile (64 KB of int64 indices) to cp.async.bulk as soon as the count phase has
+// consumed the current one, so the load runs under the scan / scatter / copy-out phases; the count phase reads
+// the indices with conflict-free 128-bit LDS.  Same cells, same order, same output as the kernel above.
+// Two other ways of ranking were measured on the 50 M-entry stream and dropped (profiles/r4f_probe.log,
+// r4g_probe.log): five ballots over the bits of the bucket number with the running counts in registers (no shared
+// memory while counting, but 67 integer instructions per entry: ALU pipe 84 % busy, 158 us against 145) and
+// MATCH.ANY on the bucket number with one running count per (warp, bucket) (200 us skewed / 251 us uniform - the
+// match instruction takes time in proportion to the number of distinct values it finds).
+constexpr int kTmaCellBuckets = 32;                       // rows of cells: 31 buckets + the bin-less one
+constexpr size_t kTmaRawBytes = static_cast<size_t>(kPartTile) * 8;
+constexpr size_t kTmaSmemBytes = kTmaRawBytes + static_cast<size_t>(kTmaCellBuckets) * kPartThreads * 2 +
+                                 static_cast<size_t>(kPartTile) * 2 + 2 * (kTmaCellBuckets + 1) * 4 + 16;
+
+__global__ void __launch_bounds__(kPartThreads, 2)
+k_occurrence_partition_tma_kernel(const long long* __restrict__ idx, long long total, long long idx_base,
+                                  long long n_bins, int n_buckets, long long n_tiles,
+                                  unsigned short* __restrict__ keys, unsigned short* __restrict__ offs,
+                                  unsigned long long* __restrict__ totals) {
+  extern __shared__ __align__(128) unsigned char part_smem[];
+  const longlong2* s_raw = reinterpret_cast<const longlong2*>(part_smem);
+  unsigned short* s_cell = reinterpret_cast<unsigned short*>(part_smem + kTmaRawBytes);
+  unsigned short* s_sorted = s_cell + kTmaCellBuckets * kPartThreads;
+  int* s_tot = reinterpret_cast<int*>(s_sorted + kPartTile);
+  int* s_base = s_tot + kTmaCellBuckets + 1;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_base + kTmaCellBuckets + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cell = ((warp >> 1) << 6) | (lane << 1) | (warp & 1);
+  const unsigned nb = static_cast<unsigned>(n_bins);
+  const unsigned binless = static_cast<unsigned>(n_buckets) << kPartShift;
+  const int n_cell16 = (n_buckets + 1) * kPartThreads * 2 / 16;
+  long long tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  // Hands tile t to the copy engine (called by every thread, after a barrier that ends all reads of the previous
+  // tile).  The ragged end of the stream: the copy takes the 16-byte multiple, the threads write the odd entry and
+  // fill the empty slots with an index outside the histogram.
+  auto issue = [&](long long t) {
+    const long long first = t * kPartTile, left = total - first;
+    const unsigned n_ent = left < kPartTile ? static_cast<unsigned>(left) : static_cast<unsigned>(kPartTile);
+    const unsigned bytes = (n_ent * 8u) & ~15u;
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(s_full, bytes);
+      if (bytes) bulk_g2s_aux(part_smem, idx + first, bytes, s_full);
+    }
+    if (n_ent < static_cast<unsigned>(kPartTile)) {
+      long long* raw = reinterpret_cast<long long*>(part_smem);
+      for (unsigned i = (bytes >> 3) + tid; i < static_cast<unsigned>(kPartTile); i += kPartThreads)
+        raw[i] = i < n_ent ? idx[first + i] : idx_base - 1;
+    }
+  };
+  if (tid == 0) {
+    mbar_init(s_full, 1);
+    fence_mbar_init();
+  }
+  issue(tile);
+  {
+    uint4* z = reinterpret_cast<uint4*>(s_cell);
+    for (int i = tid; i < n_cell16; i += kPartThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  for (; tile < n_tiles; tile += gridDim.x) {
+    mbar_wait_parked(s_full, parity);
+    parity ^= 1u;
+    unsigned ent[kPartPer];
+#pragma unroll
+    for (int j = 0; j < kPartPer / 2; ++j) {
+      const longlong2 t = s_raw[j * kPartThreads + tid];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long b = (h ? t.y : t.x) - idx_base;
+        const unsigned lo = static_cast<unsigned>(b), hi = static_cast<unsigned>(static_cast<unsigned long long>(b) >> 32);
+        const unsigned sel = (hi == 0u && lo < nb) ? lo : binless;
+        unsigned short* c = s_cell + (sel >> kPartShift) * kPartThreads + cell;
+        const unsigned old = *c;
+        *c = static_cast<unsigned short>(old + 1u);
+        ent[2 * j + h] = sel | (old << 22);
+      }
+    }
+    __syncthreads();
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x);      // every thread has read its indices (barrier above)
+    for (int b = warp; b <= n_buckets; b += kPartThreads / 32) {
+      unsigned* c = reinterpret_cast<unsigned*>(s_cell + b * kPartThreads);
+      unsigned w[kPartThreads / 64];
+      unsigned run = 0;
+#pragma unroll
+      for (int j = 0; j < kPartThreads / 64; ++j) w[j] = c[j * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < kPartThreads / 64; ++j) {
+        const unsigned lo = w[j] & 0xffffu, hi = w[j] >> 16;
+        w[j] = run | ((run + lo) << 16);
+        run += lo + hi;
+      }
+      const unsigned incl = warp_inclusive_scan(run, lane);
+      const unsigned base2 = (incl - run) * 0x10001u;
+#pragma unroll
+      for (int j = 0; j < kPartThreads / 64; ++j) c[j * 32 + lane] = w[j] + base2;
+      if (lane == 31) s_tot[b] = static_cast<int>(incl);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned t = lane <= n_buckets ? static_cast<unsigned>(s_tot[lane]) : 0u;
+      const unsigned incl = warp_inclusive_scan(t, lane);
+      s_base[lane] = static_cast<int>(incl - t);
+      if (lane == 31) s_base[32] = static_cast<int>(incl);
+    }
+    __syncthreads();
+    if (tid <= n_buckets) offs[static_cast<long long>(tid) * n_tiles + tile] = static_cast<unsigned short>(s_base[tid]);
+    if (tid < n_buckets && s_tot[tid] > 0)
+      atomicAdd(totals + tid * kPartTotalStride, static_cast<unsigned long long>(s_tot[tid]));
+#pragma unroll
+    for (int j = 0; j < kPartPer; ++j) {
+      const unsigned w = ent[j];
+      const unsigned bucket = (w >> kPartShift) & 127u;
+      const unsigned pos = static_cast<unsigned>(s_base[bucket]) + s_cell[bucket * kPartThreads + cell] + (w >> 22);
+      s_sorted[pos] = static_cast<unsigned short>(w & (kPartWidth - 1));
+    }
+    __syncthreads();
+    const int n16 = (s_base[n_buckets] * 2 + 15) >> 4;
+    uint4* dst = reinterpret_cast<uint4*>(keys + tile * kPartTile);
+    const uint4* src = reinterpret_cast<const uint4*>(s_sorted);
+    for (int i = tid; i < n16; i += kPartThreads) __stcs(dst + i, src[i]);
+    uint4* z = reinterpret_cast<uint4*>(s_cell);
+    for (int i = tid; i < n_cell16; i += kPartThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kCountThreads, 1)
+k_occurrence_bucket_kernel(const unsigned short* __restrict__ keys, const unsigned short* __restrict__ offs,
+                           const unsigned long long* __restrict__ totals, int n_buckets, long long n_tiles,
+                           int* __restrict__ counts) {
+  extern __shared__ int s_bucket_hist[];      // kPartWidth counters
+  __shared__ int s_first[kPartMaxBuckets + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    // the deal: a bucket with entries gets 1 + its share of the CTAs that are left over - the same on every CTA
+    unsigned long long t[4], all = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = lane * 4 + i;
+      t[i] = b < n_buckets ? totals[b * kPartTotalStride] : 0ull;
+      all += t[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) all += __shfl_xor_sync(kFull, all, o);
+    const unsigned long long spare = gridDim.x - n_buckets;
+    unsigned n[4], run = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      n[i] = t[i] ? 1u + static_cast<unsigned>(t[i] * spare / all) : 0u;
+      run += n[i];
+    }
+    const unsigned incl = warp_inclusive_scan(run, lane);
+    unsigned base = incl - run;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = lane * 4 + i;
+      if (b < n_buckets) s_first[b] = static_cast<int>(base);
+      base += n[i];
+    }
+    if (lane == 31) s_first[n_buckets] = static_cast<int>(incl);
+  }
+  for (int i = tid; i < kPartWidth; i += kCountThreads) s_bucket_hist[i] = 0;
+  __syncthreads();
+  const int me = blockIdx.x;
+  if (me >= s_first[n_buckets]) return;
+  int b = 0;
+  {
+    int lo = 0, hi = n_buckets;                 // the last bucket whose first CTA is <= me owns CTAs (next first > me)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_first[mid] <= me) lo = mid; else hi = mid;
+    }
+    b = lo;
+  }
+  const int s = me - s_first[b], n = s_first[b + 1] - s_first[b];
+  const long long t_begin = n_tiles * s / n, t_end = n_tiles * (s + 1) / n;
+  const unsigned short* o0 = offs + static_cast<long long>(b) * n_tiles;
+  const unsigned short* o1 = o0 + n_tiles;
+  const unsigned* keys32 = reinterpret_cast<const unsigned*>(keys);
+  // warp w takes the tiles t_begin + w, + 32, + 64, ... (a hub-heavy bucket is cut into many CTAs of few tiles each:
+  // every warp must get some); lane l fetches the segment bounds of the warp's l-th tile of a group of 32
+  constexpr int kWarps = kCountThreads / 32;
+  for (long long g = t_begin + warp; g < t_end; g += 32ll * kWarps) {
+    const long long t = g + static_cast<long long>(lane) * kWarps;
+    unsigned st = 0, en = 0;
+    if (t < t_end) {
+      st = o0[t];
+      en = o1[t];
+    }
+    const long long left = (t_end - g + kWarps - 1) / kWarps;
+    const int nt = left < 32 ? static_cast<int>(left) : 32;
+    for (int i = 0; i < nt; ++i) {
+      const unsigned a = __shfl_sync(kFull, st, i), e = __shfl_sync(kFull, en, i);
+      if (a >= e) continue;
+      const unsigned* kw = keys32 + (g + static_cast<long long>(i) * kWarps) * (kPartTile / 2);
+      const unsigned w_end = (e + 1) >> 1;
+      for (unsigned w = (a >> 1) + lane; w < w_end; w += 128) {
+        unsigned x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = w + u * 32 < w_end ? __ldcs(kw + w + u * 32) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned ww = w + u * 32;
+          if (ww < w_end) {
+            // word ww holds keys 2 ww and 2 ww + 1; the first word may start one key early, the last end one late
+            if (2 * ww >= a) atomicAdd(&s_bucket_hist[x[u] & 0xffffu], 1);
+            if (2 * ww + 1 < e) atomicAdd(&s_bucket_hist[x[u] >> 16], 1);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int* out = counts + (static_cast<long long>(b) << kPartShift);
+  for (int i = tid; i < kPartWidth; i += kCountThreads) {
+    const int c = s_bucket_hist[i];
+    if (c) atomicAdd(out + i, c);
+  }
+}
+
 // ------------------------------------------------------------------------------- retrieval metrics
 // Recall@K / Precision@K / NDCG@K, reciprocal rank and average precision of every query from its
 // ranked top-k list and its set of relevant items (src/utils/metrics.py:386-574: binary relevance,
@@ -1058,11 +1455,104 @@ cudaError_t launch_merge_topk(const float* in_sim, const int64_t* in_idx, int64_
   return cudaGetLastError();
 }
 
+namespace {
+struct PartLayout {
+  long long n_tiles;
+  int n_buckets;
+  size_t totals_b, offs_b, keys_b;
+};
+PartLayout part_layout(long long total, long long n_bins) {
+  PartLayout l;
+  l.n_tiles = (total + kPartTile - 1) / kPartTile;
+  l.n_buckets = static_cast<int>((n_bins + kPartWidth - 1) >> kPartShift);
+  auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  l.totals_b = up(static_cast<size_t>(l.n_buckets) * kPartTotalStride * 8);
+  l.offs_b = up(static_cast<size_t>(l.n_buckets + 1) * l.n_tiles * 2);
+  l.keys_b = up(static_cast<size_t>(l.n_tiles) * kPartTile * 2);
+  return l;
+}
+}  // namespace
+
+size_t k_occurrence_part_scratch_bytes(const int64_t* idx, int64_t m, int k, int64_t n_bins, int64_t part_min) {
+  const long long total = m * k;
+  if (total <= 0 || total < part_min) return 0;
+  if (n_bins * 4 <= 48 * 1024 && total >= 64 * n_bins) return 0;                  // the shared-memory path
+  if (n_bins > static_cast<long long>(kPartMaxBuckets) << kPartShift) return 0;
+  if ((reinterpret_cast<uintptr_t>(idx) & 15u) != 0) return 0;
+  if ((total + kPartTile - 1) / kPartTile > 0x7fffffffll) return 0;
+  const PartLayout l = part_layout(total, n_bins);
+  return l.totals_b + l.offs_b + l.keys_b;
+}
+
 cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t idx_base,
                                 int64_t n_bins, int32_t* counts, int sm_count, int* hot_scratch,
-                                cudaStream_t stream) {
+                                void* part_scratch, cudaStream_t stream) {
   const long long total = m * k;
   if (total <= 0 || n_bins <= 0) return cudaSuccess;
+  if (part_scratch != nullptr) {
+    // bucketed path (the caller sized part_scratch with k_occurrence_part_scratch_bytes, 256-byte aligned)
+    const PartLayout l = part_layout(total, n_bins);
+    uint8_t* base = static_cast<uint8_t*>(part_scratch);
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(base);
+    unsigned short* offs = reinterpret_cast<unsigned short*>(base + l.totals_b);
+    unsigned short* keys = reinterpret_cast<unsigned short*>(base + l.totals_b + l.offs_b);
+    cudaError_t e = cudaMemsetAsync(totals, 0, l.totals_b, stream);
+    if (e != cudaSuccess) return e;
+    static SmemAttrOnce attr_part2, attr_part3, attr_count;
+    constexpr int kMaxSmem = 227 * 1024 - 2048;      // dynamic part: the kernels hold up to 1 KB of static tables
+    if ((e = attr_part2.ensure(reinterpret_cast<const void*>(k_occurrence_partition_kernel<2>), kMaxSmem)) != cudaSuccess) return e;
+    if ((e = attr_part3.ensure(reinterpret_cast<const void*>(k_occurrence_partition_kernel<3>), kMaxSmem)) != cudaSuccess) return e;
+    if ((e = attr_count.ensure(reinterpret_cast<const void*>(k_occurrence_bucket_kernel), kMaxSmem)) != cudaSuccess) return e;
+    const size_t smem1 = static_cast<size_t>(l.n_buckets + 1) * kPartThreads * 2 + static_cast<size_t>(kPartTile) * 2;
+    // measurements: TVC_KOCC_PART_OCC=2|3 pins the register budget (CTAs per SM), TVC_KOCC_PART_KIND=1 the general
+    // (shared-memory cell) partition kernel where the vote kernel would run
+    static const int occ_env = [] {
+      const char* v = getenv("TVC_KOCC_PART_OCC");
+      return v ? atoi(v) : 0;
+    }();
+    static const int kind_env = [] {
+      const char* v = getenv("TVC_KOCC_PART_KIND");
+      return v ? atoi(v) : 0;
+    }();
+    const long long* ip = reinterpret_cast<const long long*>(idx);
+    long long tile0 = 0;
+    if (l.n_buckets < kTmaCellBuckets && kind_env != 1) {
+      // persistent, copy-engine fed
+      static SmemAttrOnce attr_tma;
+      if ((e = attr_tma.ensure(reinterpret_cast<const void*>(k_occurrence_partition_tma_kernel),
+                               static_cast<int>(kTmaSmemBytes))) != cudaSuccess) return e;
+      const long long cap = 2ll * sm_count;
+      const unsigned g = static_cast<unsigned>(l.n_tiles < cap ? l.n_tiles : cap);
+      k_occurrence_partition_tma_kernel<<<g, kPartThreads, kTmaSmemBytes, stream>>>(ip, total, idx_base, n_bins, l.n_buckets,
+                                                                                  l.n_tiles, keys, offs, totals);
+      note_launch();
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      tile0 = l.n_tiles;
+    }
+    if (tile0 < l.n_tiles) {
+      const unsigned g = static_cast<unsigned>(l.n_tiles - tile0);
+      const bool three = occ_env ? occ_env >= 3 : (smem1 + 2048) * 3 <= static_cast<size_t>(227 * 1024);
+      if (three)
+        k_occurrence_partition_kernel<3><<<g, kPartThreads, smem1, stream>>>(ip, total, idx_base, n_bins, l.n_buckets,
+                                                                            l.n_tiles, keys, offs, totals, tile0);
+      else
+        k_occurrence_partition_kernel<2><<<g, kPartThreads, smem1, stream>>>(ip, total, idx_base, n_bins, l.n_buckets,
+                                                                            l.n_tiles, keys, offs, totals, tile0);
+      note_launch();
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // CTAs of pass 2: each one zeroes and flushes 32768 counters, so few and long ones (TVC_KOCC_PART_GRID = CTAs per SM)
+    static const int grid_env = [] {
+      const char* v = getenv("TVC_KOCC_PART_GRID");
+      return v ? atoi(v) : 0;
+    }();
+    int grid2 = sm_count * (grid_env > 0 ? grid_env : 3);      // measured 1 / 2 / 3 / 4 per SM: 251 / 228 / 222 / 231 us
+    if (grid2 < 2 * l.n_buckets) grid2 = 2 * l.n_buckets;
+    k_occurrence_bucket_kernel<<<grid2, kCountThreads, kPartWidth * 4, stream>>>(keys, offs, totals, l.n_buckets,
+                                                                                 l.n_tiles, counts);
+    note_launch();
+    return cudaGetLastError();
+  }
   const int block = 256;
   const long long quads = (total + 3) / 4;
   long long blocks = (quads + block - 1) / block;

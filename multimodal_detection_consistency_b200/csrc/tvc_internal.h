@@ -133,9 +133,13 @@ cudaError_t launch_rerank(const float* cand_val, const int32_t* cand_idx, int64_
 cudaError_t launch_merge_topk(const float* in_sim, const int64_t* in_idx, int64_t m, int parts, int k,
                               float* out_sim, int64_t* out_idx, cudaStream_t stream);
 
+// part_scratch: nullptr = single-pass kernels; otherwise k_occurrence_part_scratch_bytes(...) bytes (256-byte aligned)
+// for the bucketed two-pass path.  That function returns 0 when the path does not apply (stream shorter than
+// part_min entries, histogram that fits shared memory or exceeds 4 Mi bins, misaligned stream).
+size_t k_occurrence_part_scratch_bytes(const int64_t* idx, int64_t m, int k, int64_t n_bins, int64_t part_min);
 cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t idx_base,
                                 int64_t n_bins, int32_t* counts, int sm_count, int* flag_scratch,
-                                cudaStream_t stream);
+                                void* part_scratch, cudaStream_t stream);
 
 struct MetricKs {
   int n;

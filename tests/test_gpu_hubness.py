@@ -112,3 +112,62 @@ def test_k_occurrence_hot_bins(tvc_ctx, m, k, n_bins, hub_share):
     got = tvc_ctx.k_occurrence(t, n_bins)
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), O.k_occurrence(idx, n_bins))
+
+
+@pytest.fixture
+def bucketed(tvc_ctx):
+    """Every applicable stream takes the bucketed two-pass path, whatever its length (default: from 1 Mi entries)."""
+    tvc_ctx.set_option("kocc_part_min", 0)
+    yield tvc_ctx
+    tvc_ctx.set_option("kocc_part_min", 1 << 20)
+
+
+@pytest.mark.parametrize("total,n_bins,base", [(3, 40000, 0), (8192, 32768, 0), (8193, 32769, 0), (20000, 100000, 0),
+                                               (8192 * 2 + 5, 70000, 1000), (300001, 32768 * 4, 0),
+                                               (1000003, 1000000, 17), (250000, 127 * 32768, 5), (500000, 2000000, 3), (40000, 33 * 32768, 0), (90000, 4 * 1024 * 1024, 0),
+                                               (400000, 20000, 0)])
+def test_k_occurrence_bucketed_path_exact(bucketed, total, n_bins, base):
+    """Kernel (c), bucketed path (partition into 32768-bin buckets as 16-bit keys, shared-memory count): bit-exact
+    with np.bincount on skewed streams with unused slots (-1) and out-of-range entries, ragged last tiles, bucket
+    boundaries at odd key positions, one to 127 buckets (beyond 127 x 32768 bins the single-pass kernel runs), non-zero
+    idx_base, host and device streams, accumulation into existing counts."""
+    import torch
+    rng = np.random.default_rng(total)
+    idx = (n_bins * rng.random(total) ** 3).astype(np.int64) + base
+    idx[rng.random(total) < 0.05] = -1
+    idx[rng.random(total) < 0.02] = n_bins + base + 7
+    want = O.k_occurrence(idx, n_bins, base)
+    got = bucketed.k_occurrence(idx, n_bins, idx_base=base)                     # host stream
+    assert np.array_equal(got, want)
+    t = torch.from_numpy(idx).cuda()
+    c = bucketed.k_occurrence(t, n_bins, idx_base=base)
+    c = bucketed.k_occurrence(t, n_bins, idx_base=base, counts=c)               # accumulate
+    torch.cuda.synchronize()
+    assert np.array_equal(c.cpu().numpy(), 2 * want)
+    if total > 100:                                                             # misaligned view: single-pass kernel
+        c2 = bucketed.k_occurrence(t[1:], n_bins, idx_base=base)
+        torch.cuda.synchronize()
+        assert np.array_equal(c2.cpu().numpy(), O.k_occurrence(idx[1:], n_bins, base))
+
+
+@pytest.mark.parametrize("hub_share", [0.0, 0.5, 0.97])
+def test_k_occurrence_bucketed_equals_single_pass_at_stream_size(tvc_ctx, hub_share):
+    """A 6 M-entry stream over 1 M bins (above the default switch-over): the bucketed path, the single-pass path and
+    torch.bincount agree bit for bit - uniform, hub-heavy (buckets of very different size: the CTA deal) and a
+    stream that is almost one bin."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n_bins, m, k = 1_000_000, 600_000, 10
+    idx = torch.randint(0, n_bins, (m, k), device="cuda", generator=g)
+    hubs = torch.tensor([5, 40_000, 999_999], device="cuda")
+    hot = torch.rand(m, k, device="cuda", generator=g) < hub_share
+    idx[hot] = hubs[torch.randint(0, 3, (int(hot.sum()),), device="cuda", generator=g)]
+    want = torch.bincount(idx.reshape(-1), minlength=n_bins).to(torch.int32)
+    a = tvc_ctx.k_occurrence(idx, n_bins)                                       # default: bucketed at this size
+    tvc_ctx.set_option("kocc_part_min", (1 << 63) - 1)
+    try:
+        b = tvc_ctx.k_occurrence(idx, n_bins)
+    finally:
+        tvc_ctx.set_option("kocc_part_min", 1 << 20)
+    torch.cuda.synchronize()
+    assert torch.equal(a, want) and torch.equal(b, want)

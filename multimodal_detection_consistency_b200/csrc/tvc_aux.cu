@@ -854,9 +854,9 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
 //     segments - one segment per tile, the warps taking tiles in turn - in a 128 KB shared-memory histogram and
 //     flushes the non-zero counters with REDs to consecutive addresses.
 // HBM traffic: 8 B/entry read + 2 B written + 2 B read (+ 4 B/bin) against 8 B/entry of the single pass.
-// Measured on a B200 (profiles/r4i_probe.log, r4j_probe.log; 1 M bins, stream idx = N u^3): 50 M entries 222 us
-// against 456 us (0.28 against 0.14 of the HBM peak; uniform stream 200 against 336), 5 M entries 50 against 84,
-// 1 M entries 37 against 45.  Pass 1 is bound by the load/store pipe (ncu: 72 % busy, 3 900 shared-memory
+// Measured on a B200 (profiles/r4i_probe.log, r4j_probe.log, r4k_probe.log; 1 M bins, stream idx = N u^3): 50 M
+// entries 200 us against 456 us (0.31 against 0.14 of the HBM peak; uniform stream 201 against 336), 5 M entries 50
+// against 84, 1 M entries 37 against 45.  Pass 1 is bound by the load/store pipe (ncu: 72 % busy, 3 900 shared-memory
 // wavefronts per tile of which ~1 000 are bank conflicts of the 16-bit scatter), pass 2 by the shared-memory atomics.
 constexpr int kPartThreads = 512;
 constexpr int kPartPer = 16;                               // entries per thread and tile
@@ -1144,7 +1144,7 @@ k_occurrence_partition_tma_kernel(const long long* __restrict__ idx, long long t
 __global__ void __launch_bounds__(kCountThreads, 1)
 k_occurrence_bucket_kernel(const unsigned short* __restrict__ keys, const unsigned short* __restrict__ offs,
                            const unsigned long long* __restrict__ totals, int n_buckets, long long n_tiles,
-                           int* __restrict__ counts) {
+                           int* __restrict__ counts, int lanes_env, int visit_cost) {
   extern __shared__ int s_bucket_hist[];      // kPartWidth counters
   __shared__ int s_first[kPartMaxBuckets + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1155,6 +1155,7 @@ k_occurrence_bucket_kernel(const unsigned short* __restrict__ keys, const unsign
     for (int i = 0; i < 4; ++i) {
       const int b = lane * 4 + i;
       t[i] = b < n_buckets ? totals[b * kPartTotalStride] : 0ull;
+      if (t[i]) t[i] += static_cast<unsigned long long>(visit_cost) * static_cast<unsigned long long>(n_tiles);   // a visit costs like that many entries
       all += t[i];
     }
 #pragma unroll
@@ -1195,8 +1196,14 @@ k_occurrence_bucket_kernel(const unsigned short* __restrict__ keys, const unsign
   const unsigned short* o1 = o0 + n_tiles;
   const unsigned* keys32 = reinterpret_cast<const unsigned*>(keys);
   // warp w takes the tiles t_begin + w, + 32, + 64, ... (a hub-heavy bucket is cut into many CTAs of few tiles each:
-  // every warp must get some); lane l fetches the segment bounds of the warp's l-th tile of a group of 32
+  // every warp must get some); lane l fetches the segment bounds of the warp's l-th tile of a group of 32.  A warp
+  // works on 32 / L segments at once, L lanes each: a thin bucket's segment (86 keys per tile for a 1 % bucket) would
+  // leave most of a full warp's 128 word slots empty and cost one memory round trip per tile.
   constexpr int kWarps = kCountThreads / 32;
+  const unsigned long long seg_words = totals[b * kPartTotalStride] / (2ull * static_cast<unsigned long long>(n_tiles));
+  const int lanes_log2 = lanes_env > 0 ? lanes_env : (seg_words <= 40 ? 3 : seg_words <= 80 ? 4 : 5);
+  const int sub = lane >> lanes_log2, sl = lane & ((1 << lanes_log2) - 1), nsub = 32 >> lanes_log2;
+  const unsigned step = 4u << lanes_log2;
   for (long long g = t_begin + warp; g < t_end; g += 32ll * kWarps) {
     const long long t = g + static_cast<long long>(lane) * kWarps;
     unsigned st = 0, en = 0;
@@ -1206,18 +1213,18 @@ k_occurrence_bucket_kernel(const unsigned short* __restrict__ keys, const unsign
     }
     const long long left = (t_end - g + kWarps - 1) / kWarps;
     const int nt = left < 32 ? static_cast<int>(left) : 32;
-    for (int i = 0; i < nt; ++i) {
-      const unsigned a = __shfl_sync(kFull, st, i), e = __shfl_sync(kFull, en, i);
-      if (a >= e) continue;
-      const unsigned* kw = keys32 + (g + static_cast<long long>(i) * kWarps) * (kPartTile / 2);
-      const unsigned w_end = (e + 1) >> 1;
-      for (unsigned w = (a >> 1) + lane; w < w_end; w += 128) {
+    for (int i = 0; i < nt; i += nsub) {                          // (warp-uniform trip count)
+      const int mine = i + sub;                                   // <= 31; the lanes beyond the group's tiles hold 0, 0
+      const unsigned a = __shfl_sync(kFull, st, mine), e = __shfl_sync(kFull, en, mine);
+      const unsigned* kw = keys32 + (g + static_cast<long long>(mine) * kWarps) * (kPartTile / 2);
+      const unsigned w_end = a < e ? (e + 1) >> 1 : 0u;
+      for (unsigned w = (a >> 1) + sl; w < w_end; w += step) {     // (per-lane trip counts: no warp-wide operation inside)
         unsigned x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = w + u * 32 < w_end ? __ldcs(kw + w + u * 32) : 0u;
+        for (int u = 0; u < 4; ++u) x[u] = w + (u << lanes_log2) < w_end ? __ldcs(kw + w + (u << lanes_log2)) : 0u;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const unsigned ww = w + u * 32;
+          const unsigned ww = w + (u << lanes_log2);
           if (ww < w_end) {
             // word ww holds keys 2 ww and 2 ww + 1; the first word may start one key early, the last end one late
             if (2 * ww >= a) atomicAdd(&s_bucket_hist[x[u] & 0xffffu], 1);
@@ -1548,8 +1555,20 @@ cudaError_t launch_k_occurrence(const int64_t* idx, int64_t m, int k, int64_t id
     }();
     int grid2 = sm_count * (grid_env > 0 ? grid_env : 3);      // measured 1 / 2 / 3 / 4 per SM: 251 / 228 / 222 / 231 us
     if (grid2 < 2 * l.n_buckets) grid2 = 2 * l.n_buckets;
+    // measurements: TVC_KOCC_PART_LANES = log2 of the lanes per segment (3..5; default by segment length),
+    // TVC_KOCC_PART_VISIT = what a (bucket, tile) visit weighs in the deal, in entries
+    static const int lanes_env = [] {
+      const char* v = getenv("TVC_KOCC_PART_LANES");
+      const int x = v ? atoi(v) : 0;
+      return x >= 3 && x <= 5 ? x : 0;
+    }();
+    static const int visit_env = [] {
+      const char* v = getenv("TVC_KOCC_PART_VISIT");
+      return v ? atoi(v) : -1;
+    }();
     k_occurrence_bucket_kernel<<<grid2, kCountThreads, kPartWidth * 4, stream>>>(keys, offs, totals, l.n_buckets,
-                                                                                 l.n_tiles, counts);
+                                                                                 l.n_tiles, counts, lanes_env,
+                                                                                 visit_env >= 0 ? visit_env : 128);   // measured 0 / 128 / 512: 204.7 / 200.0 / 202.9 us
     note_launch();
     return cudaGetLastError();
   }

@@ -204,8 +204,14 @@ int tvc_gallery_import_ipc(tvc_ctx* ctx, const void* handle, int64_t n, int32_t 
 /* group of up to 16 plain galleries / views with disjoint global index ranges; owns nothing */
 int tvc_gallery_group_create(tvc_ctx* ctx, tvc_gallery** parts, int32_t n_parts, tvc_gallery** out);
 
-/* Exact top-k of every query row against the gallery: out_sim [m, k] f32, out_idx [m, k] i64.
- * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K.
+/* Top-k of every query row against the gallery (IndexFlatIP semantics): out_sim [m, k] f32, out_idx [m, k] i64.
+ * Entries with similarity < threshold are dropped (pass -INFINITY for none). 1 <= k <= TVC_MAX_K (56; larger k:
+ * TVC_ERR_UNSUPPORTED - the Python mirrors then take tvc_similarity_matrix + a chunked top-k).
+ * How exact: a row's candidates are its KP best gallery rows by the bf16 tensor-core score (KP = 16 / 32 / 64 for
+ * k <= 10 / 26 / 56, per gallery range); they are re-scored from the fp32 masters, so the returned similarities and
+ * the order among the candidates are fp32.  A true top-k row can be missed only if bf16 rounding (~1e-3 for unit
+ * rows) pushes it below bf16 rank KP, i.e. only among rows within ~1e-3 of the k-th similarity - the band in which
+ * north_star allows index disagreement.  Galleries built with TVC_GALLERY_NO_MASTER return the bf16 scores.
  * Replaces: index.search(q, k)  src/retrieval.py:652-656 (:130-137, :235-264); sklearn
  * cosine_similarity + argsort  src/retrieval.py:669-671; ReferenceBank._compute_similarities + `>= thr`
  * + argsort  src/ref_bank.py:462-484, 191-203; _faiss_retrieve / _numpy_retrieve

@@ -659,7 +659,8 @@ class Gallery:
         row can only be missed if bf16 rounding (~1e-3 for unit rows) pushes it below bf16 rank KP, i.e. only
         among rows whose similarities lie within ~1e-3 of the k-th - the band north_star allows index
         disagreement in.  With keep_master=False (TVC_GALLERY_NO_MASTER) the scores are the bf16 ones.
-        k > MAX_K (56) raises TvcError(TVC_ERR_UNSUPPORTED)."""
+        k > MAX_K (56) is served by a chunked fp32 similarity matrix + top-k (_search_wide) instead of the fused
+        epilogue; the C entry point itself returns TVC_ERR_UNSUPPORTED for such k."""
         q = _rows(queries)
         if q.ndim == 1:
             q = q.reshape(1, -1)

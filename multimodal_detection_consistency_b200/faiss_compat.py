@@ -22,7 +22,10 @@ METRIC_INNER_PRODUCT = 0
 
 
 class IndexFlatIP:
-    """Exact inner-product index resident in HBM (bf16 GEMM operand + fp32 master for re-rank)."""
+    """Flat inner-product index resident in HBM (bf16 GEMM operand + fp32 master for re-rank).  Exhaustive like
+    faiss.IndexFlatIP (every row is scored); the k results are the fp32-re-scored best of the 16-64 best rows by
+    bf16 score, so a row can differ from FAISS's only inside the ~1e-3 band around the k-th similarity
+    (Gallery.search documents the bound); any k is accepted (k > 56 takes a chunked similarity matrix + top-k)."""
 
     def __init__(self, d: int, *_, **__):
         self.d = int(d)

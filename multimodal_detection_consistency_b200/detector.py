@@ -187,8 +187,7 @@ class AdversarialDetector:
             images += [image] + refs
         temb_all = _np(clip.encode_text(texts))
         iemb_all = _np(clip.encode_image(images))
-        return [(temb_all[t0:t0 + tn], iemb_all[i0:i0 + inn], variants, refs, gen_time)
-                for t0, tn, i0, inn, variants, refs, gen_time in meta]
+        return temb_all, iemb_all, meta
 
     def detect_adversarial(self, image, text: str, methods: Optional[List[str]] = None) -> Dict[str, Any]:
         """src/detector.py:345-439."""
@@ -223,62 +222,72 @@ class AdversarialDetector:
 
     def _detect_group(self, samples: Sequence[Tuple[Any, str]], methods: Sequence[str]) -> List[Dict[str, Any]]:
         """Encode every sample, bucket by (V, G), one kernel launch per bucket."""
-        enc = self._encode_samples(samples, methods)
+        temb_all, iemb_all, meta = self._encode_samples(samples, methods)
         buckets: Dict[Tuple[int, int], List[int]] = {}
-        for i, (temb, iemb, variants, refs, _) in enumerate(enc):
-            buckets.setdefault((len(variants), len(refs)), []).append(i)
+        for i, m in enumerate(meta):
+            buckets.setdefault((m[1] - 1, m[3] - 1), []).append(i)
         results: List[Optional[Dict[str, Any]]] = [None] * len(samples)
         aug_on = "text_variants" in methods and self._get_text_augmenter() is not None
         sd_on = "sd_reference" in methods and self._get_sd_generator() is not None
         active = [m for m in methods if (m == "text_variants" and aug_on) or (m == "sd_reference" and sd_on)
                   or m == "consistency"]
+        methods_list = list(methods)
         for (v, g), members in buckets.items():
-            img = np.stack([enc[i][1][0] for i in members])
-            txt = np.stack([enc[i][0][0] for i in members])
-            var = np.stack([enc[i][0][1:] for i in members]) if v else None
-            gen = np.stack([enc[i][1][1:] for i in members]) if g else None
+            # the bucket's operands are gathered from the two encoder outputs by row index (one C-level gather each
+            # instead of stacking per-sample views)
+            t0s = np.fromiter((meta[i][0] for i in members), np.int64, len(members))
+            i0s = np.fromiter((meta[i][2] for i in members), np.int64, len(members))
+            img, txt = iemb_all[i0s], temb_all[t0s]
+            var = temb_all[t0s[:, None] + np.arange(1, v + 1)] if v else None
+            gen = iemb_all[i0s[:, None] + np.arange(1, g + 1)] if g else None
             params = self._params(v, g, active)
             scores, flags, (sv, _, sg) = self._context().consistency_emb(params, img, txt, var, gen=gen,
                                                                         return_sims=True)
+            # plain Python floats once per bucket (ndarray.tolist), not one NumPy scalar conversion per field
+            s_rows, f_rows = np.asarray(scores).tolist(), np.asarray(flags).tolist()
+            sv_rows = np.asarray(sv).tolist() if v else None
+            sg_rows = np.asarray(sg).tolist() if g else None
             for row, i in enumerate(members):
-                results[i] = self._result_dict(scores[row], int(flags[row]), sv[row] if v else np.zeros(0),
-                                               sg[row] if g else np.zeros(0), active, aug_on, sd_on, enc[i][4],
-                                               list(methods))
+                results[i] = self._result_dict(s_rows[row], int(f_rows[row]), sv_rows[row] if v else [],
+                                               sg_rows[row] if g else [], active, aug_on, sd_on, meta[i][6],
+                                               list(methods_list))
         for m in active:
             if m in self.detection_stats["method_usage"]:
                 self.detection_stats["method_usage"][m] += len(samples)
         return results  # type: ignore[return-value]
 
     def _result_dict(self, s, flag, sv, sg, active, aug_on, sd_on, gen_time, methods) -> Dict[str, Any]:
+        """One sample's reference-shaped result (src/detector.py:396-427) from its row of kernel (b) outputs; `s`,
+        `sv`, `sg` are lists of Python floats."""
         ix = N.SCORE_INDEX
-        s0 = float(s[ix["original_similarity"]])
+        s0 = s[ix["original_similarity"]]
         scores: Dict[str, float] = {}
         details: Dict[str, Any] = {}
         if "text_variants" in active:
             if len(sv):
-                mean_v, std_v = float(s[ix["text_variant_consistency"]]), float(s[ix["text_variant_std"]])
+                mean_v, std_v = s[ix["text_variant_consistency"]], s[ix["text_variant_std"]]
                 details["text_variants"] = {
-                    "original_similarity": s0, "variant_similarities": [float(x) for x in sv],
+                    "original_similarity": s0, "variant_similarities": list(sv),
                     "mean_variant_similarity": mean_v, "std_variant_similarity": std_v,
                     "consistency_score": 1.0 - abs(s0 - mean_v), "variability_score": 1.0 - std_v,
-                    "num_variants": int(len(sv))}
+                    "num_variants": len(sv)}
             else:
                 details["text_variants"] = {"error": "no text variants generated"}
-            scores["text_variants"] = float(s[ix["det_text_variants"]])
+            scores["text_variants"] = s[ix["det_text_variants"]]
         if "sd_reference" in active:
             if len(sg):
                 details["sd_reference"] = {
-                    "reference_similarities": [float(x) for x in sg],
-                    "mean_similarity": float(s[ix["generative_consistency"]]),
-                    "max_similarity": float(s[ix["generative_max"]]), "std_similarity": float(s[ix["generative_std"]]),
-                    "num_references": int(len(sg)), "generation_time": gen_time}
+                    "reference_similarities": list(sg),
+                    "mean_similarity": s[ix["generative_consistency"]],
+                    "max_similarity": s[ix["generative_max"]], "std_similarity": s[ix["generative_std"]],
+                    "num_references": len(sg), "generation_time": gen_time}
             else:
                 details["sd_reference"] = {"error": "no reference images generated"}
-            scores["sd_reference"] = float(s[ix["det_sd_reference"]])
+            scores["sd_reference"] = s[ix["det_sd_reference"]]
         if "consistency" in active:
             details["consistency"] = {"image_text_similarity": s0, "consistency_score": s0}
-            scores["consistency"] = float(s[ix["det_consistency"]])
-        return {"is_adversarial": bool(flag & N.FLAG_DET_ADV), "aggregated_score": float(s[ix["aggregated_score"]]),
+            scores["consistency"] = s[ix["det_consistency"]]
+        return {"is_adversarial": bool(flag & N.FLAG_DET_ADV), "aggregated_score": s[ix["aggregated_score"]],
                 "detection_scores": scores, "detection_details": details, "detection_time": 0.0,
                 "methods_used": methods, "threshold": self.config.detection_threshold}
 

@@ -1,7 +1,8 @@
 // Bandwidth-bound kernels around the GEMM: operand preparation, candidate re-rank / merge / exchange and
 // kernel (c), the k-occurrence histogram.  128-bit loads, warp shuffles, shared-memory staging,
 // warp-aggregated atomics (__match_any_sync: one RED per distinct bin a warp holds, used where the sampling
-// pre-pass finds the stream repeating itself inside a warp); no tensor cores.
+// pre-pass finds the stream repeating itself inside a warp) and, for index streams from 1 Mi entries, a bucketed
+// two-pass path (copy-engine-fed bucket sort into 16-bit keys, then shared-memory atomics); no tensor cores.
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <math.h>
@@ -843,7 +844,8 @@ k_occurrence_kernel(const long long* __restrict__ idx, long long total, long lon
 // Every entry of the RED path costs one atomic in the L2 (~180 G/s chip-wide, a fifth of what HBM delivers as
 // index stream).  The only way past that is to make the increments shared-memory ones, i.e. to bring the entries
 // of one bin range together first:
-//   pass 1 (k_occurrence_partition_kernel): a CTA reads a TILE of 8192 entries and writes it back bucket-sorted
+//   pass 1 (k_occurrence_partition_tma_kernel / k_occurrence_partition_kernel): a CTA takes a TILE of 8192 entries
+//     and writes it back bucket-sorted
 //     (bucket = bin >> 15) as 16-bit keys (bin & 32767) - tile-major, so the write is one contiguous 16 KB block
 //     and no bucket can overflow whatever the distribution - plus the tile's bucket boundaries (transposed,
 //     offs[bucket][tile]) and the bucket totals.  The rank of an entry inside its (thread, bucket) cell comes from

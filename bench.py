@@ -722,12 +722,20 @@ def main():
         # power-capped clock for a moment, and these kernels are latency / issue bound, i.e. scale with the SM clock
         torch.cuda.synchronize()
         time.sleep(2.0)
-        roof_b, roof_c = roofline_bc(torch, tvc, args, scorer, o, img, txt, var, measured_peaks())
+        # (the extras explain the headline; a failure in one of them is reported in its block, never allowed to take
+        # the line down)
+        try:
+            roof_b, roof_c = roofline_bc(torch, tvc, args, scorer, o, img, txt, var, measured_peaks())
+        except Exception as e:  # noqa: BLE001
+            roof_b = roof_c = {"error": f"{type(e).__name__}: {e}"}
         del o
         scorer.reset_hubness()
         if g_host is not None:
             import numpy as np
-            latency, dropin = dropin_blocks(np, args, g_host, b_host, *(t.cpu().numpy() for t in (img, txt, var)))
+            try:
+                latency, dropin = dropin_blocks(np, args, g_host, b_host, *(t.cpu().numpy() for t in (img, txt, var)))
+            except Exception as e:  # noqa: BLE001
+                latency = dropin = {"error": f"{type(e).__name__}: {e}"}
 
     scorer.close()
     if rank != 0:
